@@ -1,0 +1,69 @@
+"""ctypes binding of the C-ABI library (include/socialways_b200.h).
+
+There is NO fallback: if libsocialways_b200.so is missing or a call fails, this raises.  Build the
+library with `python -m socialways_b200.build` (or __graft_entry__.build()).
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsocialways_b200.so")
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+
+_PROTOTYPES = {
+    "sw_abi_version": (_I, []),
+    "sw_last_cuda_error": (_I, []),
+    "sw_error_string": (ctypes.c_char_p, [_I]),
+    "sw_decode_pack_floats": (_I, []),
+    "sw_pool_pack_floats": (_I, []),
+    "sw_lstm_seq_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "sw_pool_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "sw_decode_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "sw_bestofk_metrics": (_I, [_P, _P, _F, _I, _I, _I, _P, _P]),
+}
+
+_lib = None
+
+
+class SocialWaysCudaError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SocialWaysCudaError(
+                f"{LIB_PATH} not found: the CUDA extension is required (no CPU fallback). "
+                "Build it with `python -m socialways_b200.build`.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(handle, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return sorted(_PROTOTYPES)
+
+
+def check(code, what):
+    if code != 0:
+        msg = lib().sw_error_string(code).decode()
+        raise SocialWaysCudaError(f"{what} failed: {msg} (code {code})")
+
+
+def ptr(t):
+    """Device pointer of a contiguous fp32/int32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise SocialWaysCudaError("socialways_b200 kernels take CUDA tensors only (no CPU path)")
+    if not t.is_contiguous():
+        raise SocialWaysCudaError("tensor must be contiguous")
+    return t.data_ptr()

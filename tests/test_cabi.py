@@ -1,0 +1,58 @@
+"""CPU checks of the drop-in boundary: the library builds, loads, and exports every symbol that
+include/socialways_b200.h declares (no compute calls here: there is no GPU on the CPU tier)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "socialways_b200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(sw_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from socialways_b200 import build, _lib
+    build.build()
+    assert os.path.exists(_lib.LIB_PATH)
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 9
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in the header but not exported"
+    assert sorted(_lib.exported_symbols()) == declared, "ctypes prototypes out of sync with the header"
+    lib = _lib.lib()
+    assert lib.sw_abi_version() == 1
+    assert lib.sw_decode_pack_floats() == 160 * 160 + 160 + 160 * 80 + 80 + 160 + 2
+    assert lib.sw_pool_pack_floats() == 128 + 64 * 32 + 64
+    assert b"argument" in lib.sw_error_string(-1)
+
+
+def test_null_pointers_are_rejected_without_touching_the_gpu():
+    from socialways_b200 import _lib
+    lib = _lib.lib()
+    assert lib.sw_decode_fwd(None, None, None, None, None, None, None, None, 1, 1, 1, 148, None) == -1
+    assert lib.sw_pool_fwd(None, None, None, None, None, None, None, None, 1, 1, None) == -1
+    assert lib.sw_bestofk_metrics(None, None, 1.0, 1, 1, 1, None, None) == -1
+    assert lib.sw_lstm_seq_fwd(None, None, 2, 1, 8, None, None, None, None, None, None, None, None, None, 148, None) == -1
+
+
+def test_product_path_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "socialways_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", ""), fn
+
+
+def test_no_cpu_fallback():
+    import pytest
+    import torch
+    import socialways_b200 as sw
+    g = sw.Generator(use_social=True)
+    with pytest.raises(sw.SocialWaysCudaError):
+        g.predict_k(torch.zeros(4, 8, 2), torch.zeros(1, 4, 32), 12, [[0, 4]])
