@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Headline benchmark: predicted trajectories / second of the Social Ways K-sample inference path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): ETH-shaped synthetic scenes, 8 agents per scene, obs 8 / pred 12,
+K = 20 samples per agent, hidden 64, use_social = True, fp32.  One "step" = one pass of the hot path
+(observation encode -> pairwise social attention pooling -> K-sample 12-step decode -> best-of-K
+ADE/FDE) over one batch of `--scenes` scenes per GPU.  One predicted trajectory = one (agent, sample)
+pair x 12 steps.
+
+`value`   : whole-job trajectories/s with the inputs already resident in HBM (device-timed, CUDA events,
+            max over ranks).
+`e2e`     : same metric through the public API with HOST (pinned) inputs: per step the observations,
+            ground truth and noise are copied host->device and the per-agent metrics device->host,
+            all inside the timed region (copies of step i+1 overlap compute of step i on a second stream).
+`roofline`: the decode kernel (dominant), algorithmic FLOPs per trajectory over its
+            CUDA-event time on the launching stream, against the measured bf16 tensor peak
+            (MEASURED_PEAKS.json) -- the kernel is compute-bound.
+`cpu_baseline`: the CPU oracle port of the reference's test() loop (one scene at a time, K serial
+            predict() calls, per-agent attention loop) on the host cores, bounded sample.
+`--impl reference`: the same CPU arm as its own JSON line (the reference is Python over torch and
+            cannot travel to the GPU box; the oracle port restates it).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+A_PER_SCENE, N_PAST, N_NEXT, K_SAMPLES = 8, 8, 12, 20
+FLOPS_PER_TRAJ = 1_726_848          # 12 x DecoderFC (83 360) + 11 x encoder step (66 048)
+FLOPS_PER_TRAJ_EXECUTED = 12 * 2 * (64 * 160 + 160 * 80 + 80 * 2) + 11 * 2 * 68 * 256 + 2 * 96 * 160
+
+
+def make_scenes(n_scenes, seed):
+    from golden_data import synthetic_scenes
+    return synthetic_scenes([A_PER_SCENE] * n_scenes, n_past=N_PAST, n_next=N_NEXT, seed=seed)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"], src="measured")
+    return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i] == "Active" for r in self.rows)]
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+def cpu_arm(n_scenes, repeats=1):
+    """CPU oracle port of test() (train.py:563-616): per scene, K serial predict() calls with the
+    reference's per-agent attention loop, all host threads.  Returns (traj/s, threads, seconds)."""
+    from oracle import socialways_oracle as so
+    torch.set_num_threads(os.cpu_count() or 1)
+    P = so.init_weights(seed=0)
+    data = make_scenes(n_scenes, seed=1234)
+    sc = so.IsoScale(data["obsvs"], data["preds"])
+    obsv = torch.from_numpy(sc.normalize(data["obsvs"]))
+    pred = torch.from_numpy(sc.normalize(data["preds"]))
+    best = None
+    for _ in range(repeats):
+        torch.manual_seed(0)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            for a, b in data["batches"]:
+                errs = []
+                for k in range(K_SAMPLES):
+                    noise = torch.rand(b - a, 32)
+                    hat = so.predict(P, obsv[a:b], noise, N_NEXT, None, use_social=True, pool="loop")
+                    errs.append((((hat[:, :, :2] - pred[a:b]) / sc.sx) ** 2).sum(dim=2).sqrt())
+                e = torch.stack(errs)
+                _ = (e.mean(2).min(0)[0].sum().item(), e[:, :, -1].min(0)[0].sum().item())
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    traj = n_scenes * A_PER_SCENE * K_SAMPLES
+    return traj / best, torch.get_num_threads(), best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        cpu_arm(max(1, args.cpu_scenes // 8))
+    t_total, traj_total = 0.0, 0
+    for _ in range(args.steps):
+        v, cores, dt = cpu_arm(args.cpu_scenes)
+        t_total += dt
+        traj_total += args.cpu_scenes * A_PER_SCENE * K_SAMPLES
+    value = traj_total / t_total
+    sample = f"{args.cpu_scenes} scenes x {A_PER_SCENE} agents x K={K_SAMPLES} per step"
+    print(json.dumps({
+        "impl": "reference", "metric": "predicted_trajectories_per_sec", "value": value, "unit": "traj/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.cpu_scenes),
+        "cpu_baseline": {"value": value, "unit": "traj/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "traj/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_config(args, scenes):
+    return {"workload": f"ETH-shaped synthetic K-sample inference: {scenes} scenes/GPU/step x {A_PER_SCENE} agents, "
+                        f"obs {N_PAST} pred {N_NEXT}, K={K_SAMPLES}, hidden 64, use_social=True",
+            "scenes_per_gpu_per_step": scenes, "agents_per_scene": A_PER_SCENE, "K": K_SAMPLES,
+            "obs_len": N_PAST, "pred_len": N_NEXT, "parallelism": f"scenes sharded x{args.gpus}, no collective",
+            "l2_policy": "per-step inputs+outputs (noise 128 B + pred 192 B per trajectory) exceed the 126 MB L2"}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import socialways_b200 as sw
+    from socialways_b200 import ops
+    from oracle import socialways_oracle as so          # weights init + CPU baseline only
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    P = so.init_weights(seed=0)
+    gen = sw.Generator(use_social=True)
+    gen.load_state_dict({k: v for k, v in P.items() if not k.startswith("D.")})
+    gen = gen.to(dev)
+
+    n_scenes = args.scenes
+    data = make_scenes(n_scenes, seed=100 + rank)            # every rank its own shard of scenes
+    sc = so.IsoScale(data["obsvs"], data["preds"])
+    obsv_h = torch.from_numpy(sc.normalize(data["obsvs"])).pin_memory()
+    pred_h = torch.from_numpy(sc.normalize(data["preds"])).pin_memory()
+    n = obsv_h.shape[0]
+    g = torch.Generator().manual_seed(7 + rank)
+    noise_h = torch.rand(K_SAMPLES, n, 32, generator=g).pin_memory()
+    scenes = ops.SceneIndex(data["batches"], n, dev)
+    traj_per_step = n * K_SAMPLES
+
+    obsv_d, pred_d, noise_d = obsv_h.to(dev), pred_h.to(dev), noise_h.to(dev)
+    out = torch.empty(K_SAMPLES, n, N_NEXT, 4, device=dev)
+    pk = gen.packs()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    dec_events = []
+
+    def step_resident(timed):
+        enc = ops.lstm_seq(pk["enc"], obsv_d, want_x_last=True)
+        ub = torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])
+        pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
+        if timed:
+            e0, e1 = ev(), ev()
+            e0.record()
+        ops.decode(pk["enc"], pk["dec"], enc["h"], enc["c"], pooled, noise_d, enc["x_last"], N_NEXT, out=out)
+        if timed:
+            e1.record()
+            dec_events.append((e0, e1))
+        return ops.bestofk_metrics(out, pred_d, sc.sx)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing ----------------
+    for _ in range(args.warmup):
+        step_resident(False)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(args.steps):
+        m = step_resident(True)
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1)
+    dec_ms = sum(a.elapsed_time(b) for a, b in dec_events) / len(dec_events)
+    metrics_sum = m.sum(0).cpu().numpy() / n
+
+    # ---------------- end-to-end: host buffers in, metrics out, copies inside the timed region ----------------
+    copy_stream = torch.cuda.Stream()
+    bufs = [dict(obsv=torch.empty_like(obsv_d), pred=torch.empty_like(pred_d), noise=torch.empty_like(noise_d),
+                 ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
+    res_h = [torch.empty(n, 4).pin_memory() for _ in range(2)]
+    out2 = out
+
+    def upload(i):
+        b = bufs[i % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(b["free"])
+            b["obsv"].copy_(obsv_h, non_blocking=True)
+            b["pred"].copy_(pred_h, non_blocking=True)
+            b["noise"].copy_(noise_h, non_blocking=True)
+            b["ready"].record(copy_stream)
+
+    def e2e_steps(count):
+        main = torch.cuda.current_stream()
+        for b in bufs:
+            b["free"].record(main)
+        upload(0)
+        for i in range(count):
+            b = bufs[i % 2]
+            if i + 1 < count:
+                upload(i + 1)
+            main.wait_event(b["ready"])
+            hat = gen.predict_k(b["obsv"], b["noise"], N_NEXT, scenes, out=out2)
+            met = ops.bestofk_metrics(hat, b["pred"], sc.sx)
+            res_h[i % 2].copy_(met, non_blocking=True)
+            b["free"].record(main)
+        main.synchronize()
+
+    e2e_steps(max(2, min(args.warmup, 3)))
+    barrier()
+    w0 = time.perf_counter()
+    x0, x1 = ev(), ev()
+    x0.record()
+    e2e_steps(args.steps)
+    x1.record()
+    barrier()
+    e2e_wall = time.perf_counter() - w0
+    e2e_s = x0.elapsed_time(x1) * 1e-3          # device clock; the wall clock (below) must agree
+    clocks = sampler.stop() if rank == 0 else None
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s, dec_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s, dec_ms = (float(x) for x in t.cpu())
+
+    if rank == 0:
+        pk_ = peaks()
+        value = world * traj_per_step * args.steps / (ms * 1e-3)
+        e2e_value = world * traj_per_step * args.steps / e2e_s
+        ach = traj_per_step * FLOPS_PER_TRAJ / (dec_ms * 1e-3) / 1e12
+        peak = pk_["bf16_sustained"]
+        h2d = obsv_h.numel() * 4 + pred_h.numel() * 4 + noise_h.numel() * 4
+        line = {
+            "metric": "predicted_trajectories_per_sec", "value": value, "unit": "traj/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, n_scenes),
+            "e2e": {"value": e2e_value, "unit": "traj/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n * 16,
+                    "wall_s": e2e_wall, "device_s": e2e_s},
+            "gpu_launches": 4 * args.steps,
+            "clocks": clocks,
+            "roofline": {"kernel": "decode_fwd_kernel", "bound": "tensor", "achieved": ach, "peak": peak,
+                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                         "peak_source": f"bf16_tflops_sustained ({pk_['src']})",
+                         "kernel_ms": dec_ms, "kernel_share_of_step": dec_ms / (ms / args.steps),
+                         "flops_per_traj_algorithmic": FLOPS_PER_TRAJ,
+                         "flops_per_traj_executed": FLOPS_PER_TRAJ_EXECUTED,
+                         "note": "fp32 FFMA path (parity mode); CUDA-core fp32 peak is ~74 TFLOP/s"},
+            "accuracy": {"ade_avg": float(metrics_sum[0]), "fde_avg": float(metrics_sum[1]),
+                         "ade_min": float(metrics_sum[2]), "fde_min": float(metrics_sum[3]),
+                         "note": "random-init weights, synthetic data"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, dt = cpu_arm(args.cpu_scenes)
+            line["cpu_baseline"] = {"value": v, "unit": "traj/s", "cores": cores, "kind": "port",
+                                    "sample": f"{args.cpu_scenes} scenes x {A_PER_SCENE} agents x K={K_SAMPLES} "
+                                              f"({dt:.1f} s of CPU work, same generator)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenes", type=int, default=16384, help="scenes per GPU per step")
+    ap.add_argument("--cpu-scenes", type=int, default=384, help="scenes in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

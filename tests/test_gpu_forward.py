@@ -21,7 +21,7 @@ def _generator(P, use_social=True):
     g = sw.Generator(use_social=use_social)
     sd = {k: v for k, v in P.items() if not k.startswith("D.")}
     g.load_state_dict(sd, strict=True)
-    return g.cuda()
+    return g.cuda().requires_grad_(False)      # inference path; the autograd path has its own tests
 
 
 @pytest.mark.parametrize("case", ["ops_ragged.npz", "ops_zara.npz"])
