@@ -39,6 +39,7 @@ int sw_last_cuda_error(void);
 const char* sw_error_string(int code);
 int sw_decode_pack_floats(void);
 int sw_pool_pack_floats(void);
+int sw_decode_pack_t_floats(void);
 
 /* LSTM over a sequence.  Replaces: get_traj_4d (train.py:130-134, when in_dim == 2) + EncoderLstm.forward
  * (train.py:262-269; observation pass at :404) and Discriminator.obsv_encoder_lstm (train.py:296-299).
@@ -47,10 +48,23 @@ int sw_pool_pack_floats(void);
  *   y_out    [n_rows][n_steps][64] every h_t, or NULL
  *   h_out,c_out [n_rows][64] state after the last step
  *   x_last   [n_rows][4] last 4-d state (train.py:416), or NULL
- *   stash_*  backward-pass stash ([T][N][64][5] gates+cell, [T][N][64] h, [T][N][4] inputs), all NULL for inference */
+ *   stash_gates [T][tiles][5][64][32] (i,f,g,o,c per unit) and stash_xh [T][tiles][68][32] (the {x4;h} operand
+ *            of every step): backward-pass stash in tile-image layout, both NULL for inference */
 int sw_lstm_seq_fwd(const float* lstm_pack, const float* x, int in_dim, int n_rows, int n_steps,
                     const float* h_in, const float* c_in, float* y_out, float* h_out, float* c_out,
-                    float* x_last, float* stash_gates, float* stash_h, float* stash_x4, int sm_count, void* stream);
+                    float* x_last, float* stash_gates, float* stash_xh, int sm_count, void* stream);
+
+/* Backward of sw_lstm_seq_fwd from a zero initial state.  Replaces autograd through nn.LSTM
+ * (train.py:254,268 for the generator, :278,299 for D) as walked by d_loss.backward() / g_loss.backward()
+ * (train.py:495,538).  Tile-image layout = [..][tiles = ceil(N/32)][k][32 rows].
+ *   lstm_pack_t [256][68] = transpose of lstm_pack rows 0..67; stash_gates from the forward call
+ *   dh_last,dc_last [N][64] gradients w.r.t. the final state (NULL = zero)
+ *   g_gates out [T][tiles][256][32] pre-activation gate gradients; the weight gradient is the plain GEMM
+ *           d(lstm_pack)[0:68] = sum stash_xh[..][k][r] * g_gates[..][n][r], d(lstm_pack)[68] = sum g_gates
+ *   dx out [N][T][4] gradient w.r.t. the 4-d inputs, or NULL */
+int sw_lstm_seq_bwd(const float* lstm_pack_t, const float* stash_gates, const float* dh_last,
+                    const float* dc_last, float* g_gates, float* dx, int n_rows, int n_steps,
+                    int sm_count, void* stream);
 
 /* Fused pairwise social features + embedding MLP + attention pooling.  Replaces: SocialFeatures,
  * BearingMTX, DCA_MTX (train.py:208-241), EmbedSocialFeatures.forward (train.py:178-189) and
@@ -62,13 +76,40 @@ int sw_pool_fwd(const float* pool_pack, const float* x_last, const float* h, con
                 const int* scene_offsets, const int* agent_scene, float* pooled, float* attn,
                 int n_agents, int max_scene, void* stream);
 
+/* Backward of sw_pool_fwd.  Replaces autograd through AttentionPooling.forward / EmbedSocialFeatures.fc
+ * (train.py:160-175,183-188) inside g_loss.backward() (train.py:538).
+ *   dS [N][64] gradient of the pooled vector, tdot [N] = dS_i . S_i, attn from the forward call,
+ *   pair_offsets [n_scenes+1] (int64) start of every scene's A*A block of ordered pairs
+ *   dub out [N][65] gradient of (u | beta); dh_direct out [N][64] = sum_i a_ij dS_i
+ *   st_a1 [P][32], st_g2 [P][64], st_g1 [P][32], st_f [P][4] out: per-pair layer-1 activations, layer-2 /
+ *   layer-1 pre-activation gradients and (features, 1); the MLP weight gradients are plain GEMMs of these */
+int sw_pool_bwd(const float* pool_pack, const float* x_last, const float* h, const float* ub,
+                const float* dS, const float* tdot, const float* attn, const int* scene_offsets,
+                const int* agent_scene, const long long* pair_offsets, float* dub, float* dh_direct,
+                float* st_a1, float* st_g2, float* st_g1, float* st_f, int n_agents, int max_scene,
+                void* stream);
+
 /* K-sample autoregressive decode in one launch.  Replaces the loop of predict() (train.py:418-432:
  * DecoderFC.forward :330-335 + integration :423-425 + one EncoderLstm step :430 per predicted step) and
  * the serial best-of-K loop around it in test() (train.py:583-585): row = k * n_agents + n.
  *   h0,c0 [N][64], pooled [N][64] or NULL (use_social False, train.py:413), noise [K][N][32],
- *   x_last [N][4]; out [K][N][n_next][4] = (p, v) per step (train.py:425,432) */
+ *   x_last [N][4]; out [K][N][n_next][4] = (p, v) per step (train.py:425,432)
+ *   stash_xh [T][tiles][68][32], stash_gates [T-1][tiles][5][64][32], stash_a1 [T][tiles][160][32],
+ *   stash_a2 [T][tiles][80][32]: backward-pass stash (tile images), all NULL for inference */
 int sw_decode_fwd(const float* lstm_pack, const float* dec_pack, const float* h0, const float* c0,
                   const float* pooled, const float* noise, const float* x_last, float* out,
+                  float* stash_xh, float* stash_gates, float* stash_a1, float* stash_a2,
+                  int n_agents, int n_samples, int n_next, int sm_count, void* stream);
+
+/* Backward of sw_decode_fwd.  Replaces autograd through the decode loop (train.py:418-430) inside
+ * g_loss.backward() (train.py:538).  dec_pack_t (sw_decode_pack_t_floats() floats) =
+ * W1h^T [160][64] | W2^T [80][160] | W34 [80][2].  d_out [K*N][T][4] gradient of the emitted (p, v).
+ * Outputs (tile images): g_gates [T-1][tiles][256][32], g_a1 [T][tiles][160][32], g_a2 [T][tiles][80][32],
+ * g_v [T][tiles][2][32]; dh0, dc0 [K*N][64] gradients of the initial state.  Weight gradients = plain GEMMs
+ * of the forward stash images against these (packing.py / autograd_path.py). */
+int sw_decode_bwd(const float* lstm_pack_t, const float* dec_pack_t, const float* c0,
+                  const float* stash_gates, const float* stash_a1, const float* stash_a2, const float* d_out,
+                  float* g_gates, float* g_a1, float* g_a2, float* g_v, float* dh0, float* dc0,
                   int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 
 /* Best-of-K error metrics.  Replaces train.py:587 and :602-607 of test().

@@ -4,8 +4,8 @@ Public surface = the reference's own operator interface for the path (reference_
 C-ABI CUDA library (include/socialways_b200.h, csrc/).  No CPU fallback exists.
 """
 from ._lib import SocialWaysCudaError, LIB_PATH, exported_symbols  # noqa: F401
-from .reference_api import (AttentionPooling, DecoderFC, DecoderLstm, EmbedSocialFeatures, EncoderLstm,  # noqa: F401
-                            Generator, SocialFeatures, get_traj_4d, predict_cv)
+from .reference_api import (AttentionPooling, DecoderFC, DecoderLstm, Discriminator, EmbedSocialFeatures,  # noqa: F401
+                            EncoderLstm, Generator, SocialFeatures, get_traj_4d, predict_cv)
 from . import ops, packing  # noqa: F401
 
 __version__ = "0.1.0"

@@ -19,9 +19,13 @@ _PROTOTYPES = {
     "sw_error_string": (ctypes.c_char_p, [_I]),
     "sw_decode_pack_floats": (_I, []),
     "sw_pool_pack_floats": (_I, []),
-    "sw_lstm_seq_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "sw_decode_pack_t_floats": (_I, []),
+    "sw_lstm_seq_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
+    "sw_lstm_seq_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "sw_pool_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
-    "sw_decode_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "sw_pool_bwd": (_I, [_P] * 16 + [_I, _I, _P]),
+    "sw_decode_fwd": (_I, [_P] * 12 + [_I, _I, _I, _I, _P]),
+    "sw_decode_bwd": (_I, [_P] * 13 + [_I, _I, _I, _I, _P]),
     "sw_bestofk_metrics": (_I, [_P, _P, _F, _I, _I, _I, _P, _P]),
 }
 

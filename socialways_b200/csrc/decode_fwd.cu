@@ -37,11 +37,14 @@ struct DecodeSmem {
 constexpr int DP_W1 = 0, DP_B1 = 160 * 160, DP_W2 = DP_B1 + 160, DP_B2 = DP_W2 + 160 * 80,
               DP_W34 = DP_B2 + 80, DP_B34 = DP_W34 + 160, DP_TOTAL = DP_B34 + 2;
 
+template <bool STASH>
 __global__ void __launch_bounds__(SW_THREADS, 1)
 decode_fwd_kernel(const float* __restrict__ lstm_pack, const float* __restrict__ dec_pack,
                   const float* __restrict__ h0, const float* __restrict__ c0,
                   const float* __restrict__ pooled, const float* __restrict__ noise,
                   const float* __restrict__ x_last, float* __restrict__ out,
+                  float* __restrict__ stash_xh /*[T][tiles][68][32]*/, float* __restrict__ stash_gates /*[T-1][tiles][5][64][32]*/,
+                  float* __restrict__ stash_a1 /*[T][tiles][160][32]*/, float* __restrict__ stash_a2 /*[T][tiles][80][32]*/,
                   int n_agents, long long n_rows, int n_next, int n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecodeSmem& s = *reinterpret_cast<DecodeSmem*>(smem_raw);
@@ -121,6 +124,7 @@ decode_fwd_kernel(const float* __restrict__ lstm_pack, const float* __restrict__
                             make_float4(lrelu02(acc[0][j]), lrelu02(acc[1][j]), lrelu02(acc[2][j]), lrelu02(acc[3][j]));
             }
             __syncthreads();
+            if (STASH) store_image(stash_a1 + ((size_t)t * n_tiles + tile) * (160 * SW_ROWS), s.a1, 160 * SW_ROWS);
             // ---- layer 2: 160 -> 80, LeakyReLU(0.2) ----
             {
                 float acc[4][10];
@@ -139,6 +143,7 @@ decode_fwd_kernel(const float* __restrict__ lstm_pack, const float* __restrict__
                             make_float4(lrelu02(acc[0][j]), lrelu02(acc[1][j]), lrelu02(acc[2][j]), lrelu02(acc[3][j]));
             }
             __syncthreads();
+            if (STASH) store_image(stash_a2 + ((size_t)t * n_tiles + tile) * (80 * SW_ROWS), s.a2, 80 * SW_ROWS);
             // ---- folded layers 3+4: 80 -> 2 velocity; integrate; emit (p, v); feed back as x4 ----
             {
                 float v = 0.0f;
@@ -158,10 +163,13 @@ decode_fwd_kernel(const float* __restrict__ lstm_pack, const float* __restrict__
                             make_float4(p_cur, p_other, v, v_other);
                 }
             }
-            if (t + 1 == n_next) break;
+            if (!STASH && t + 1 == n_next) break;
             __syncthreads();
+            if (STASH) store_image(stash_xh + ((size_t)t * n_tiles + tile) * XB, X, XB);
+            if (t + 1 == n_next) break;
             // ---- encoder LSTM step on (p, v): {x4 ; h} -> h', c' ----
-            lstm_tile_step<false>(s.wl, X, s.xb[(t + 1) & 1] + 4 * SW_ROWS, c, lmL, nullptr, 0, rows_valid);
+            lstm_tile_step<STASH>(s.wl, X, s.xb[(t + 1) & 1] + 4 * SW_ROWS, c, lmL,
+                                  STASH ? stash_gates + ((size_t)t * n_tiles + tile) * SW_GATE_STASH_FLOATS : nullptr);
             __syncthreads();
         }
         __syncthreads();
@@ -172,21 +180,22 @@ decode_fwd_kernel(const float* __restrict__ lstm_pack, const float* __restrict__
 
 extern "C" int sw_decode_fwd(const float* lstm_pack, const float* dec_pack, const float* h0, const float* c0,
                              const float* pooled, const float* noise, const float* x_last, float* out,
+                             float* stash_xh, float* stash_gates, float* stash_a1, float* stash_a2,
                              int n_agents, int n_samples, int n_next, int sm_count, void* stream) {
     if (!lstm_pack || !dec_pack || !h0 || !c0 || !noise || !x_last || !out) return SW_ERR_ARG;
     if (n_agents <= 0 || n_samples <= 0 || n_next <= 0 || sm_count <= 0) return SW_ERR_ARG;
     const long long n_rows = (long long)n_agents * n_samples;
     const long long tiles = (n_rows + SW_ROWS - 1) / SW_ROWS;
     if (tiles > 0x7fffffffLL) return SW_ERR_UNSUPPORTED;
-    static bool attr_set = false;
+    const bool stash = stash_xh != nullptr;
+    if (stash && (!stash_a1 || !stash_a2 || (n_next > 1 && !stash_gates))) return SW_ERR_ARG;
     const int smem = (int)sizeof(sw::DecodeSmem);
-    if (!attr_set) {
-        SW_CUDA_TRY(cudaFuncSetAttribute(sw::decode_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
-    }
+    auto kern = stash ? sw::decode_fwd_kernel<true> : sw::decode_fwd_kernel<false>;
+    SW_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
-    sw::decode_fwd_kernel<<<grid, SW_THREADS, smem, (cudaStream_t)stream>>>(
-        lstm_pack, dec_pack, h0, c0, pooled, noise, x_last, out, n_agents, n_rows, n_next, (int)tiles);
+    kern<<<grid, SW_THREADS, smem, (cudaStream_t)stream>>>(lstm_pack, dec_pack, h0, c0, pooled, noise, x_last, out, stash_xh,
+                                                           stash_gates, stash_a1, stash_a2, n_agents, n_rows, n_next,
+                                                           (int)tiles);
     SW_CUDA_TRY(cudaGetLastError());
     return SW_OK;
 }

@@ -29,8 +29,9 @@ __global__ void __launch_bounds__(SW_THREADS, 2)
 lstm_seq_fwd_kernel(const float* __restrict__ lstm_pack, const float* __restrict__ x, int in_dim, int n_rows,
                     int T, const float* __restrict__ h_in, const float* __restrict__ c_in,
                     float* __restrict__ y_out, float* __restrict__ h_out, float* __restrict__ c_out, float* __restrict__ x_last,
-                    float* __restrict__ stash_gates /*[T][N][64][5]*/, float* __restrict__ stash_h /*[T][N][64]*/,
-                    float* __restrict__ stash_x4 /*[T][N][4]*/, int n_tiles) {
+                    float* __restrict__ stash_gates /*[T][tiles][5][64][32]*/,
+                    float* __restrict__ stash_xh /*[T][tiles][68][32]: the {x4 ; h_{t-1}} operand of every step*/,
+                    int n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SeqSmem& s = *reinterpret_cast<SeqSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -75,24 +76,18 @@ lstm_seq_fwd_kernel(const float* __restrict__ lstm_pack, const float* __restrict
                 }
                 X[0 * SW_ROWS + tid] = st.x; X[1 * SW_ROWS + tid] = st.y;
                 X[2 * SW_ROWS + tid] = st.z; X[3 * SW_ROWS + tid] = st.w;
-                if (tid < rows_valid) {
-                    if (STASH) *reinterpret_cast<float4*>(stash_x4 + ((size_t)t * n_rows + row0 + tid) * 4) = st;
-                    if (t == T - 1 && x_last) *reinterpret_cast<float4*>(x_last + (size_t)(row0 + tid) * 4) = st;
-                }
+                if (tid < rows_valid && t == T - 1 && x_last)
+                    *reinterpret_cast<float4*>(x_last + (size_t)(row0 + tid) * 4) = st;
             }
             __syncthreads();
+            if (STASH) store_image(stash_xh + ((size_t)t * n_tiles + tile) * (SW_LSTM_K * SW_ROWS), X, SW_LSTM_K * SW_ROWS);
             lstm_tile_step<STASH>(s.wl, X, Hn, c, lm,
-                                  STASH ? stash_gates + ((size_t)t * n_rows + row0) * (SW_H * 5) : nullptr, SW_H * 5,
-                                  rows_valid);
+                                  STASH ? stash_gates + ((size_t)t * n_tiles + tile) * SW_GATE_STASH_FLOATS : nullptr);
             __syncthreads();
-            if (STASH || y_out) {   // h_t row-major: for the weight-gradient GEMM / the module's return value
+            if (y_out) {   // h_t row-major: the module's return value (train.py:268-269)
                 for (int i = tid; i < SW_ROWS * SW_H; i += SW_THREADS) {
                     const int r = i >> 6, k = i & 63;
-                    if (r < rows_valid) {
-                        const float v = Hn[k * SW_ROWS + r];
-                        if (STASH) stash_h[((size_t)t * n_rows + row0 + r) * SW_H + k] = v;
-                        if (y_out) y_out[((size_t)(row0 + r) * T + t) * SW_H + k] = v;
-                    }
+                    if (r < rows_valid) y_out[((size_t)(row0 + r) * T + t) * SW_H + k] = Hn[k * SW_ROWS + r];
                 }
             }
         }
@@ -113,13 +108,13 @@ lstm_seq_fwd_kernel(const float* __restrict__ lstm_pack, const float* __restrict
 }  // namespace sw
 
 extern "C" int sw_lstm_seq_fwd(const float* lstm_pack, const float* x, int in_dim, int n_rows, int n_steps,
-                               const float* h_in, const float* c_in, float* y_out, float* h_out, float* c_out, float* x_last, float* stash_gates, float* stash_h,
-                               float* stash_x4, int sm_count, void* stream) {
+                               const float* h_in, const float* c_in, float* y_out, float* h_out, float* c_out,
+                               float* x_last, float* stash_gates, float* stash_xh, int sm_count, void* stream) {
     if (!lstm_pack || !x || !h_out || !c_out) return SW_ERR_ARG;
     if (n_rows <= 0 || sm_count <= 0 || (in_dim != 2 && in_dim != 4)) return SW_ERR_ARG;
     if (n_steps < (in_dim == 2 ? 2 : 1) || n_steps > sw::SEQ_T_MAX) return SW_ERR_UNSUPPORTED;
     const bool stash = stash_gates != nullptr;
-    if (stash && (!stash_h || !stash_x4)) return SW_ERR_ARG;
+    if (stash && !stash_xh) return SW_ERR_ARG;
     if ((h_in == nullptr) != (c_in == nullptr)) return SW_ERR_ARG;
     const int tiles = (n_rows + SW_ROWS - 1) / SW_ROWS;
     const int smem = (int)sizeof(sw::SeqSmem);
@@ -128,7 +123,7 @@ extern "C" int sw_lstm_seq_fwd(const float* lstm_pack, const float* x, int in_di
     // two CTAs fit per SM (104 KB each): let short grids spread over more SMs' worth of slots
     const int grid = tiles < 2 * sm_count ? tiles : 2 * sm_count;
     kern<<<grid, SW_THREADS, smem, (cudaStream_t)stream>>>(lstm_pack, x, in_dim, n_rows, n_steps, h_in, c_in, y_out, h_out, c_out, x_last,
-                                                          stash_gates, stash_h, stash_x4, tiles);
+                                                          stash_gates, stash_xh, tiles);
     SW_CUDA_TRY(cudaGetLastError());
     return SW_OK;
 }

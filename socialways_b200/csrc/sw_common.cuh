@@ -136,16 +136,15 @@ __device__ __forceinline__ void load_rows_kmajor(float* __restrict__ dst, float*
 #define SW_LSTM_K 68
 #define SW_LSTM_PACK_FLOATS (69 * 256)
 
-struct LstmGates {  // post-activation gates of one (row, unit): what the backward pass needs
-    float i, f, g, o;
-};
+// Backward-pass stash of one LSTM tile step ("tile k-major", the shared-memory image):
+//   gates [5][64][32] floats: post-activation i, f, g, o and the new cell state c, per unit, 32 rows contiguous.
+#define SW_GATE_STASH_FLOATS (5 * SW_H * SW_ROWS)
 
 template <bool STASH>
 __device__ __forceinline__ void lstm_tile_step(const float* __restrict__ Wl /*smem [69][256]*/,
                                                const float* __restrict__ X /*smem [68][32]*/,
                                                float* __restrict__ Hout /*smem [64][32]*/, float (&c)[4][2],
-                                               const LaneMap<1>& lm, float* __restrict__ stash_row0, int stash_ld,
-                                               int rows_valid) {
+                                               const LaneMap<1>& lm, float* __restrict__ stash /*global, tile image*/) {
     float acc[4][8];
     const float* b = Wl + 68 * SW_G + lm.cg * 8;
 #pragma unroll
@@ -155,26 +154,76 @@ __device__ __forceinline__ void lstm_tile_step(const float* __restrict__ Wl /*sm
     fma_tile<8, 1>(acc, X, Wl, SW_G, SW_LSTM_K, lm);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-        float hv[4];
+        float gi[4], gf[4], gg[4], go[4], hv[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float gi = sigmoidf_acc(acc[i][u * 4 + 0]);
-            const float gf = sigmoidf_acc(acc[i][u * 4 + 1]);
-            const float gg = tanhf_acc(acc[i][u * 4 + 2]);
-            const float go = sigmoidf_acc(acc[i][u * 4 + 3]);
-            c[i][u] = fmaf(gf, c[i][u], gi * gg);
-            hv[i] = go * tanhf_acc(c[i][u]);
-            if (STASH) {
-                const int r = lm.rg * 4 + i;
-                if (r < rows_valid) {
-                    // stash layout per row: [i f g o c] x 64 units, unit-major: 5 floats per unit
-                    float* s = stash_row0 + (size_t)r * stash_ld + (lm.cg * 2 + u) * 5;
-                    s[0] = gi; s[1] = gf; s[2] = gg; s[3] = go; s[4] = c[i][u];
-                }
-            }
+            gi[i] = sigmoidf_acc(acc[i][u * 4 + 0]);
+            gf[i] = sigmoidf_acc(acc[i][u * 4 + 1]);
+            gg[i] = tanhf_acc(acc[i][u * 4 + 2]);
+            go[i] = sigmoidf_acc(acc[i][u * 4 + 3]);
+            c[i][u] = fmaf(gf[i], c[i][u], gi[i] * gg[i]);
+            hv[i] = go[i] * tanhf_acc(c[i][u]);
         }
-        *reinterpret_cast<float4*>(Hout + (lm.cg * 2 + u) * SW_ROWS + lm.rg * 4) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        const int off = (lm.cg * 2 + u) * SW_ROWS + lm.rg * 4;
+        *reinterpret_cast<float4*>(Hout + off) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+        if (STASH) {
+            float* s = stash + off;
+            *reinterpret_cast<float4*>(s + 0 * SW_H * SW_ROWS) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+            *reinterpret_cast<float4*>(s + 1 * SW_H * SW_ROWS) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+            *reinterpret_cast<float4*>(s + 2 * SW_H * SW_ROWS) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+            *reinterpret_cast<float4*>(s + 3 * SW_H * SW_ROWS) = make_float4(go[0], go[1], go[2], go[3]);
+            *reinterpret_cast<float4*>(s + 4 * SW_H * SW_ROWS) = make_float4(c[0][u], c[1][u], c[2][u], c[3][u]);
+        }
     }
+}
+
+// Reverse of lstm_tile_step for thread (rg, cg): from dL/dh_t (shared DH[64][32]) and the running dL/dc_t
+// (registers) to the pre-activation gate gradients DG[n'][32] (shared, gate-interleaved n' = 4*unit+gate,
+// the layout of the pack columns) and dL/dc_{t-1} (registers).  `st` = this step's gate stash image,
+// `c_prev` = previous step's cell image (nullptr: zero initial state).  Rows >= rows_valid produce zeros.
+__device__ __forceinline__ void lstm_tile_bwd_gates(const float* __restrict__ st, const float* __restrict__ c_prev,
+                                                    const float* __restrict__ DH, float* __restrict__ DG,
+                                                    float (&dc)[4][2], const LaneMap<1>& lm, int rows_valid) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int unit = lm.cg * 2 + u;
+        const int off = unit * SW_ROWS + lm.rg * 4;
+        const float4 vi = __ldg(reinterpret_cast<const float4*>(st + 0 * SW_H * SW_ROWS + off));
+        const float4 vf = __ldg(reinterpret_cast<const float4*>(st + 1 * SW_H * SW_ROWS + off));
+        const float4 vg = __ldg(reinterpret_cast<const float4*>(st + 2 * SW_H * SW_ROWS + off));
+        const float4 vo = __ldg(reinterpret_cast<const float4*>(st + 3 * SW_H * SW_ROWS + off));
+        const float4 vc = __ldg(reinterpret_cast<const float4*>(st + 4 * SW_H * SW_ROWS + off));
+        float4 vp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c_prev) vp = *reinterpret_cast<const float4*>(c_prev + off);   // global stash or shared image
+        const float4 vdh = *reinterpret_cast<const float4*>(DH + off);
+        const float gi[4] = {vi.x, vi.y, vi.z, vi.w}, gf[4] = {vf.x, vf.y, vf.z, vf.w}, gg[4] = {vg.x, vg.y, vg.z, vg.w},
+                    go[4] = {vo.x, vo.y, vo.z, vo.w}, cc[4] = {vc.x, vc.y, vc.z, vc.w}, cp[4] = {vp.x, vp.y, vp.z, vp.w},
+                    dh[4] = {vdh.x, vdh.y, vdh.z, vdh.w};
+        float dai[4], daf[4], dag[4], dao[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool valid = (lm.rg * 4 + i) < rows_valid;
+            const float tc = tanhf_acc(cc[i]);
+            const float d_o = dh[i] * tc;
+            const float dct = fmaf(dh[i] * go[i], 1.0f - tc * tc, dc[i][u]);
+            dai[i] = valid ? dct * gg[i] * gi[i] * (1.0f - gi[i]) : 0.0f;
+            daf[i] = valid ? dct * cp[i] * gf[i] * (1.0f - gf[i]) : 0.0f;
+            dag[i] = valid ? dct * gi[i] * (1.0f - gg[i] * gg[i]) : 0.0f;
+            dao[i] = valid ? d_o * go[i] * (1.0f - go[i]) : 0.0f;
+            dc[i][u] = valid ? dct * gf[i] : 0.0f;
+        }
+        float* g = DG + (unit * 4) * SW_ROWS + lm.rg * 4;
+        *reinterpret_cast<float4*>(g + 0 * SW_ROWS) = make_float4(dai[0], dai[1], dai[2], dai[3]);
+        *reinterpret_cast<float4*>(g + 1 * SW_ROWS) = make_float4(daf[0], daf[1], daf[2], daf[3]);
+        *reinterpret_cast<float4*>(g + 2 * SW_ROWS) = make_float4(dag[0], dag[1], dag[2], dag[3]);
+        *reinterpret_cast<float4*>(g + 3 * SW_ROWS) = make_float4(dao[0], dao[1], dao[2], dao[3]);
+    }
+}
+
+// cooperative copy of a tile image (n floats, n % 4 == 0) shared <-> global
+__device__ __forceinline__ void store_image(float* __restrict__ gdst, const float* __restrict__ ssrc, int n) {
+    for (int i = threadIdx.x * 4; i < n; i += blockDim.x * 4)
+        *reinterpret_cast<float4*>(gdst + i) = *reinterpret_cast<const float4*>(ssrc + i);
 }
 
 }  // namespace sw

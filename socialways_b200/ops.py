@@ -52,6 +52,22 @@ class SceneIndex:
         self.offsets = torch.from_numpy(offs).to(device)
         self.agent_scene = torch.from_numpy(np.repeat(np.arange(self.n_scenes, dtype=np.int32), sizes)).to(device)
         self.sizes = sizes
+        pairs = np.concatenate([[0], np.cumsum(sizes.astype(np.int64) ** 2)])
+        self.n_pairs = int(pairs[-1])
+        self._pairs_np = pairs
+        self._pair_offsets = None
+        self.device = device
+
+    @property
+    def pair_offsets(self):
+        """[n_scenes+1] int64 offsets of every scene's A x A block of ordered pairs (backward pass only)."""
+        if self._pair_offsets is None:
+            self._pair_offsets = torch.from_numpy(self._pairs_np).to(self.device)
+        return self._pair_offsets
+
+
+def n_tiles(n_rows):
+    return (n_rows + 31) // 32
 
 
 def lstm_seq(lstm_pack, x, h_in=None, c_in=None, want_y=False, want_x_last=False, stash=False):
@@ -63,18 +79,31 @@ def lstm_seq(lstm_pack, x, h_in=None, c_in=None, want_y=False, want_x_last=False
     c = torch.empty(n, H, device=dev)
     y = torch.empty(n, t, H, device=dev) if want_y else None
     xl = torch.empty(n, 4, device=dev) if want_x_last else None
-    sg = sh = sx = None
+    sg = sx = None
     if stash:
-        sg = torch.empty(t, n, H, 5, device=dev)
-        sh = torch.empty(t, n, H, device=dev)
-        sx = torch.empty(t, n, 4, device=dev)
+        sg = torch.empty(t, n_tiles(n), 5, H, 32, device=dev)
+        sx = torch.empty(t, n_tiles(n), 68, 32, device=dev)
     code = _lib.lib().sw_lstm_seq_fwd(_lib.ptr(_f32(lstm_pack)), _lib.ptr(x), d, n, t,
                                       _lib.ptr(None if h_in is None else _f32(h_in)),
                                       _lib.ptr(None if c_in is None else _f32(c_in)),
                                       _lib.ptr(y), _lib.ptr(h), _lib.ptr(c), _lib.ptr(xl),
-                                      _lib.ptr(sg), _lib.ptr(sh), _lib.ptr(sx), sm_count(dev), _stream())
+                                      _lib.ptr(sg), _lib.ptr(sx), sm_count(dev), _stream())
     _lib.check(code, "sw_lstm_seq_fwd")
-    return dict(h=h, c=c, y=y, x_last=xl, stash_gates=sg, stash_h=sh, stash_x4=sx)
+    return dict(h=h, c=c, y=y, x_last=xl, stash_gates=sg, stash_xh=sx)
+
+
+def lstm_seq_bwd(lstm_pack_t, stash_gates, dh_last, dc_last, n_rows, want_dx=False):
+    """sw_lstm_seq_bwd -> gate gradients [T, tiles, 256, 32] (and dL/dx [N,T,4] if asked)."""
+    t = stash_gates.shape[0]
+    dev = stash_gates.device
+    g = torch.empty(t, n_tiles(n_rows), 256, 32, device=dev)
+    dx = torch.empty(n_rows, t, 4, device=dev) if want_dx else None
+    code = _lib.lib().sw_lstm_seq_bwd(_lib.ptr(_f32(lstm_pack_t)), _lib.ptr(stash_gates),
+                                      _lib.ptr(None if dh_last is None else _f32(dh_last)),
+                                      _lib.ptr(None if dc_last is None else _f32(dc_last)),
+                                      _lib.ptr(g), _lib.ptr(dx), n_rows, t, sm_count(dev), _stream())
+    _lib.check(code, "sw_lstm_seq_bwd")
+    return (g, dx) if want_dx else g
 
 
 def pool(pool_pack, x_last, h, ub, scenes, want_attn=False):
@@ -89,20 +118,67 @@ def pool(pool_pack, x_last, h, ub, scenes, want_attn=False):
     return (pooled, attn) if want_attn else pooled
 
 
-def decode(lstm_pack, dec_pack, h0, c0, pooled, noise, x_last, n_next, out=None):
-    """sw_decode_fwd.  noise [K,N,32] -> out [K,N,n_next,4]."""
+def pool_bwd(pool_pack, x_last, h, ub, d_pooled, tdot, attn, scenes):
+    """sw_pool_bwd -> (dub [N,65], dh_direct [N,64], per-pair stashes A1 [P,32], G2 [P,64], G1 [P,32], F [P,4])."""
+    n, dev, p = h.shape[0], h.device, scenes.n_pairs
+    dub = torch.empty(n, 65, device=dev)
+    dh = torch.empty(n, H, device=dev)
+    st_a1, st_g2 = torch.zeros(p, 32, device=dev), torch.zeros(p, 64, device=dev)
+    st_g1, st_f = torch.zeros(p, 32, device=dev), torch.zeros(p, 4, device=dev)
+    code = _lib.lib().sw_pool_bwd(_lib.ptr(_f32(pool_pack)), _lib.ptr(_f32(x_last)), _lib.ptr(_f32(h)), _lib.ptr(_f32(ub)),
+                                  _lib.ptr(_f32(d_pooled)), _lib.ptr(_f32(tdot)), _lib.ptr(_f32(attn)),
+                                  _lib.ptr(scenes.offsets), _lib.ptr(scenes.agent_scene), _lib.ptr(scenes.pair_offsets),
+                                  _lib.ptr(dub), _lib.ptr(dh), _lib.ptr(st_a1), _lib.ptr(st_g2), _lib.ptr(st_g1),
+                                  _lib.ptr(st_f), n, scenes.max_scene, _stream())
+    _lib.check(code, "sw_pool_bwd")
+    return dub, dh, st_a1, st_g2, st_g1, st_f
+
+
+def decode(lstm_pack, dec_pack, h0, c0, pooled, noise, x_last, n_next, out=None, stash=False):
+    """sw_decode_fwd.  noise [K,N,32] -> out [K,N,n_next,4] (plus the backward stash if asked)."""
     noise = _f32(noise)
     k, n, z = noise.shape
     if z != Z or h0.shape != (n, H):
         raise ValueError("decode: noise must be [K, N, 32] and h0 [N, 64]")
+    dev = noise.device
     if out is None:
-        out = torch.empty(k, n, n_next, 4, device=noise.device)
+        out = torch.empty(k, n, n_next, 4, device=dev)
+    st = [None] * 4
+    if stash:
+        tl = n_tiles(k * n)
+        st = [torch.empty(n_next, tl, 68, 32, device=dev), torch.empty(max(n_next - 1, 1), tl, 5, H, 32, device=dev),
+              torch.empty(n_next, tl, 160, 32, device=dev), torch.empty(n_next, tl, 80, 32, device=dev)]
     code = _lib.lib().sw_decode_fwd(_lib.ptr(_f32(lstm_pack)), _lib.ptr(_f32(dec_pack)), _lib.ptr(_f32(h0)),
                                     _lib.ptr(_f32(c0)), _lib.ptr(None if pooled is None else _f32(pooled)),
-                                    _lib.ptr(noise), _lib.ptr(_f32(x_last)), _lib.ptr(out), n, k, n_next,
-                                    sm_count(noise.device), _stream())
+                                    _lib.ptr(noise), _lib.ptr(_f32(x_last)), _lib.ptr(out),
+                                    _lib.ptr(st[0]), _lib.ptr(st[1]), _lib.ptr(st[2]), _lib.ptr(st[3]),
+                                    n, k, n_next, sm_count(dev), _stream())
     _lib.check(code, "sw_decode_fwd")
+    if stash:
+        return out, dict(xh=st[0], gates=st[1][:n_next - 1], a1=st[2], a2=st[3])
     return out
+
+
+def decode_bwd(lstm_pack_t, dec_pack_t, c0, stash, d_out, n_agents, n_samples):
+    """sw_decode_bwd.  d_out [K*N, T, 4] -> dict of gradient images + dh0/dc0 [K*N, 64]."""
+    d_out = _f32(d_out)
+    t = d_out.shape[-2]
+    rows = n_agents * n_samples
+    dev = d_out.device
+    tl = n_tiles(rows)
+    g_gates = torch.empty(max(t - 1, 1), tl, 256, 32, device=dev)
+    g_a1 = torch.empty(t, tl, 160, 32, device=dev)
+    g_a2 = torch.empty(t, tl, 80, 32, device=dev)
+    g_v = torch.empty(t, tl, 2, 32, device=dev)
+    dh0 = torch.empty(rows, H, device=dev)
+    dc0 = torch.empty(rows, H, device=dev)
+    gates = stash["gates"] if t > 1 else None
+    code = _lib.lib().sw_decode_bwd(_lib.ptr(_f32(lstm_pack_t)), _lib.ptr(_f32(dec_pack_t)), _lib.ptr(_f32(c0)),
+                                    _lib.ptr(gates), _lib.ptr(stash["a1"]), _lib.ptr(stash["a2"]), _lib.ptr(d_out),
+                                    _lib.ptr(g_gates), _lib.ptr(g_a1), _lib.ptr(g_a2), _lib.ptr(g_v), _lib.ptr(dh0),
+                                    _lib.ptr(dc0), n_agents, n_samples, t, sm_count(dev), _stream())
+    _lib.check(code, "sw_decode_bwd")
+    return dict(gates=g_gates[:t - 1], a1=g_a1, a2=g_a2, v=g_v, dh0=dh0, dc0=dc0)
 
 
 def bestofk_metrics(pred, gt, ss):

@@ -177,6 +177,57 @@ class DecoderLstm(nn.Module):
         raise SocialWaysCudaError("DecoderLstm is not on the Social Ways path (train.py:375-376 uses DecoderFC)")
 
 
+class Discriminator(nn.Module):
+    """train.py:272-316.  The observation LSTM runs in sw_lstm_seq_fwd / sw_lstm_seq_bwd; the four
+    small FC heads (64->32->32, 48->32->32, 64->32->1, 64->32->2) are library GEMMs in this round."""
+
+    def __init__(self, n_next, hidden_dim, n_latent_code):
+        super().__init__()
+        self.lstm_dim = hidden_dim
+        self.n_next = n_next
+        self.obsv_encoder_lstm = nn.LSTM(4, hidden_dim, batch_first=True)
+        self.obsv_encoder_fc = nn.Sequential(nn.Linear(hidden_dim, hidden_dim // 2), nn.LeakyReLU(0.2),
+                                             nn.Linear(hidden_dim // 2, hidden_dim // 2))
+        self.pred_encoder = nn.Sequential(nn.Linear(n_next * 4, hidden_dim // 2), nn.LeakyReLU(0.2),
+                                          nn.Linear(hidden_dim // 2, hidden_dim // 2))
+        self.classifier = nn.Sequential(nn.Linear(hidden_dim, hidden_dim // 2), nn.LeakyReLU(0.2),
+                                        nn.Linear(hidden_dim // 2, 1))
+        self.latent_decoder = nn.Sequential(nn.Linear(hidden_dim, hidden_dim // 2), nn.LeakyReLU(0.2),
+                                            nn.Linear(self.lstm_dim // 2, n_latent_code))
+
+    def packed_lstm(self):
+        _require_path_sizes(self.lstm_dim)
+        l = self.obsv_encoder_lstm
+        return packing.pack_disc_lstm(l.weight_ih_l0, l.weight_hh_l0, l.bias_ih_l0, l.bias_hh_l0)
+
+    def encode_obsv(self, obsv):
+        """Last hidden state of the observation LSTM from a zero state (train.py:296-301)."""
+        if not obsv.is_cuda:
+            raise SocialWaysCudaError("Discriminator runs on CUDA tensors only (no CPU fallback)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.obsv_encoder_lstm.parameters()):
+            from .autograd_path import LstmSeqFn
+            return LstmSeqFn.apply(self.packed_lstm(), obsv)[0]
+        with torch.no_grad():
+            return ops.lstm_seq(self.packed_lstm(), obsv)["h"]
+
+    def heads(self, obsv_h, pred):
+        obsv_code = self.obsv_encoder_fc(obsv_h)
+        pred_code = self.pred_encoder(pred.reshape(-1, self.n_next * 4))
+        both_codes = torch.cat([obsv_code, pred_code], dim=1)
+        return self.classifier(both_codes), self.latent_decoder(both_codes)
+
+    def forward(self, obsv, pred):
+        return self.heads(self.encode_obsv(obsv), pred)
+
+    def load(self, backup):
+        """train.py:311-316: restores the nn.Linear layers ONLY (the LSTM is not rolled back)."""
+        for m_from, m_to in zip(backup.modules(), self.modules()):
+            if isinstance(m_to, nn.Linear):
+                m_to.weight.data = m_from.weight.data.clone()
+                if m_to.bias is not None:
+                    m_to.bias.data = m_from.bias.data.clone()
+
+
 class Generator(nn.Module):
     """The four generator modules of train.py:370-376 + predict() (train.py:392-432)."""
 

@@ -1,0 +1,225 @@
+"""train() and test() of the reference (train.py:439-560, :563-616) over the CUDA modules.
+
+Same control flow, RNG consumption order (numpy scalars for the smoothed labels, torch CPU RNG for
+the noise, train.py:471-473,584), loss definitions, optimiser settings, unrolling + Linear-only
+rollback quirk (train.py:498-499,541-543) and printed lines as the reference.  Differences, all
+arithmetic-neutral: the K samples of test() are decoded in one launch (the noise is still drawn
+per (scene, k) from the torch CPU RNG in the reference's order), and the discriminator's
+observation LSTM is evaluated once per D pass for the fake and the real branch (same weights,
+same input -- the reference evaluates it twice with identical results, train.py:482,487).
+"""
+import copy
+import os
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.optim as opt
+
+from . import ops
+from .reference_api import Discriminator, Generator, get_traj_4d, predict_cv
+from .scale import Scale
+
+
+class SocialWaysTrainer:
+    def __init__(self, data, batch_size=256, hidden_size=64, use_social=False, n_unrolling_steps=1,
+                 lr_g=1e-4, lr_d=1e-3, device="cuda", weights=None, n_latent_codes=2,
+                 use_info_loss=True, loss_info_w=0.5):
+        self.device = torch.device(device)
+        self.batch_size, self.n_unrolling_steps = batch_size, n_unrolling_steps
+        self.use_info_loss, self.loss_info_w, self.n_latent_codes = use_info_loss, loss_info_w, n_latent_codes
+        # ---- train.py:89-124: data, 4/5 split over scenes, Scale ----
+        obsv = np.array(data["obsvs"], dtype=np.float32, copy=True)
+        pred = np.array(data["preds"], dtype=np.float32, copy=True)
+        self.dataset_t = np.asarray(data["times"])
+        the_batches = np.asarray(data["batches"])
+        self.train_size = max(1, (len(the_batches) * 4) // 5)
+        self.n_past, self.n_next = obsv.shape[1], pred.shape[1]
+        self.n_train_samples = int(the_batches[self.train_size - 1][1])
+        self.n_test_samples = obsv.shape[0] - self.n_train_samples
+        if self.n_test_samples == 0:
+            self.n_test_samples = 1
+            the_batches = np.array([the_batches[0], the_batches[0]])
+        self.the_batches = the_batches
+        self.train_batches = the_batches[:self.train_size]
+        self.test_batches = the_batches[self.train_size:]
+        self.scale = Scale()
+        self.scale.max_x = max(np.max(obsv[:, :, 0]), np.max(pred[:, :, 0]))
+        self.scale.min_x = min(np.min(obsv[:, :, 0]), np.min(pred[:, :, 0]))
+        self.scale.max_y = max(np.max(obsv[:, :, 1]), np.max(pred[:, :, 1]))
+        self.scale.min_y = min(np.min(obsv[:, :, 1]), np.min(pred[:, :, 1]))
+        self.scale.calc_scale(keep_ratio=True)
+        self.ss = self.scale.sx
+        self.dataset_obsv = torch.from_numpy(self.scale.normalize(obsv)).to(self.device)
+        self.dataset_pred = torch.from_numpy(self.scale.normalize(pred)).to(self.device)
+        # ---- train.py:370-386: modules (same construction order => same init stream), optimisers ----
+        self.generator = Generator(hidden_size, 1, 3, hidden_size, hidden_size // 2, use_social=use_social)
+        self.D = Discriminator(self.n_next, hidden_size, n_latent_codes)
+        if weights is not None:
+            self.load_reference_weights(weights)
+        self.generator.to(self.device)
+        self.D.to(self.device)
+        self.noise_len = hidden_size // 2
+        self.predictor_optimizer = opt.Adam(self.generator.optimizer_parameters(), lr=lr_g, betas=(0.9, 0.999))
+        self.D_optimizer = opt.Adam(self.D.parameters(), lr=lr_d, betas=(0.9, 0.999))
+        self.mse_loss = nn.MSELoss()
+        self.epoch = 1
+        self.loss_log = []
+
+    # reference module-global names
+    encoder = property(lambda self: self.generator.encoder)
+    feature_embedder = property(lambda self: self.generator.feature_embedder)
+    attention = property(lambda self: self.generator.attention)
+    decoder = property(lambda self: self.generator.decoder)
+
+    def load_reference_weights(self, weights):
+        """`weights`: {"encoder.embed.weight": ..., "D.classifier.0.bias": ...} (reference state_dict keys)."""
+        as_t = lambda v: v if torch.is_tensor(v) else torch.from_numpy(np.asarray(v))
+        self.generator.load_state_dict({k: as_t(v) for k, v in weights.items() if not k.startswith("D.")})
+        self.D.load_state_dict({k[2:]: as_t(v) for k, v in weights.items() if k.startswith("D.")})
+
+    def predict(self, obsv_p, noise, n_next, sub_batches=()):
+        return self.generator.predict(obsv_p, noise, n_next, sub_batches)
+
+    # ------------------------------------------------------------------ train.py:439-560
+    def train(self, verbose=True):
+        tic = time.perf_counter()
+        train_ADE, train_FDE = 0, 0
+        batch_size_accum = 0
+        sub_batches = []
+        D, mse_loss, dev = self.D, self.mse_loss, self.device
+        for ii, batch_i in enumerate(self.train_batches):
+            batch_size_accum += batch_i[1] - batch_i[0]
+            sub_batches.append(batch_i)
+            if ii >= self.train_size - 1 or \
+                    batch_size_accum + (self.the_batches[ii + 1][1] - self.the_batches[ii + 1][0]) > self.batch_size:
+                obsv = self.dataset_obsv[sub_batches[0][0]:sub_batches[-1][1]]
+                pred = self.dataset_pred[sub_batches[0][0]:sub_batches[-1][1]]
+                sub_batches = np.asarray(sub_batches) - sub_batches[0][0]
+                bs = int(batch_size_accum)
+                obsv_4d, pred_4d = get_traj_4d(obsv, pred)
+                zeros = (torch.zeros(bs, 1) + np.random.uniform(0, 0.1)).to(dev)          # :471
+                ones = (torch.ones(bs, 1) * np.random.uniform(0.9, 1.0)).to(dev)           # :472
+                noise = torch.rand(bs, self.noise_len).to(dev)                             # :473 (CPU RNG)
+                backup = None
+                # ============== Train Discriminator ================ :476-499
+                for u in range(self.n_unrolling_steps + 1):
+                    D.zero_grad()
+                    with torch.no_grad():
+                        pred_hat_4d = self.predict(obsv, noise, self.n_next, sub_batches)
+                    obsv_h = D.encode_obsv(obsv_4d)
+                    fake_labels, code_hat = D.heads(obsv_h, pred_hat_4d)
+                    d_loss_fake = mse_loss(fake_labels, zeros)
+                    d_loss_info = mse_loss(code_hat.squeeze(), noise[:, :self.n_latent_codes])
+                    real_labels, code_hat = D.heads(obsv_h, pred_4d)
+                    d_loss_real = mse_loss(real_labels, ones)
+                    d_loss = d_loss_fake + d_loss_real
+                    if self.use_info_loss:
+                        d_loss = d_loss + self.loss_info_w * d_loss_info
+                    d_loss.backward()
+                    self.D_optimizer.step()
+                    if u == 0 and self.n_unrolling_steps > 0:
+                        backup = copy.deepcopy(D)
+                # =============== Train Generator ================= :501-543
+                D.zero_grad()
+                self.predictor_optimizer.zero_grad()
+                pred_hat_4d = self.predict(obsv, noise, self.n_next, sub_batches)
+                with torch.no_grad():          # D's observation code does not depend on the generator
+                    obsv_h = D.encode_obsv(obsv_4d)
+                gen_labels, code_hat = D.heads(obsv_h, pred_hat_4d)
+                g_loss_fooling = mse_loss(gen_labels, ones)
+                g_loss_info = mse_loss(code_hat.squeeze(), noise[:, :self.n_latent_codes])
+                g_loss = g_loss_fooling
+                if self.use_info_loss:
+                    g_loss = g_loss + self.loss_info_w * g_loss_info
+                g_loss.backward()
+                self.predictor_optimizer.step()
+                if self.n_unrolling_steps > 0:
+                    D.load(backup)
+                    del backup
+                with torch.no_grad():                                                      # :546-551
+                    err_all = torch.pow((pred_hat_4d[:, :, :2] - pred) / self.ss, 2)
+                    err_all = err_all.sum(dim=2).sqrt()
+                    e = err_all.sum().item() / self.n_next
+                    train_ADE += e
+                    train_FDE += err_all[:, -1].sum().item()
+                self.loss_log.append(dict(d_loss=d_loss.item(), d_fake=d_loss_fake.item(), d_real=d_loss_real.item(),
+                                          d_info=d_loss_info.item(), g_fool=g_loss_fooling.item(),
+                                          g_info=g_loss_info.item()))
+                batch_size_accum = 0
+                sub_batches = []
+        train_ADE /= self.n_train_samples
+        train_FDE /= self.n_train_samples
+        toc = time.perf_counter()
+        if verbose:
+            print(" Epc=%4d, Train ADE,FDE = (%.3f, %.3f) | time = %.1f" % (self.epoch, train_ADE, train_FDE, toc - tic))
+        return train_ADE, train_FDE
+
+    # ------------------------------------------------------------------ train.py:563-616
+    def test(self, n_gen_samples=20, linear=False, write_to_file=None, just_one=False, verbose=True):
+        ade_avg_12, fde_avg_12 = 0, 0
+        ade_min_12, fde_min_12 = 0, 0
+        for ii, batch_i in enumerate(self.test_batches):
+            obsv = self.dataset_obsv[batch_i[0]:batch_i[1]]
+            pred = self.dataset_pred[batch_i[0]:batch_i[1]]
+            current_t = self.dataset_t[batch_i[0]]
+            bs = int(batch_i[1] - batch_i[0])
+            with torch.no_grad():
+                linear_preds = predict_cv(obsv, self.n_next)
+                if linear and not write_to_file:
+                    all_preds = torch.cat([linear_preds, torch.zeros_like(linear_preds)], dim=2).unsqueeze(0)
+                else:
+                    # one torch.rand(bs, noise_len) per sample, in the reference's order (:583-584)
+                    noise = torch.stack([torch.rand(bs, self.noise_len) for _ in range(n_gen_samples)]).to(self.device)
+                    all_preds = self.generator.predict_k(obsv, noise, self.n_next)          # [K, bs, T, 4]
+                m = ops.bestofk_metrics(all_preds.contiguous(), pred.contiguous(), self.ss)  # :587,602-607
+                if write_to_file:
+                    file_name = os.path.join(write_to_file, str(self.epoch) + '-' + str(current_t) + '.npz')
+                    print('saving to ', file_name)
+                    np.savez(file_name, timestamp=current_t,
+                             obsvs=self.scale.denormalize(obsv[:, :, :2].cpu().numpy()),
+                             preds_our=self.scale.denormalize(all_preds[:, :, :, :2].cpu().numpy()),
+                             preds_gtt=self.scale.denormalize(pred[:, :, :2].cpu().numpy()),
+                             preds_lnr=self.scale.denormalize(linear_preds[:, :, :2].cpu().numpy()))
+                sums = m.sum(dim=0).tolist()
+                ade_avg_12 += sums[0]
+                fde_avg_12 += sums[1]
+                ade_min_12 += sums[2]
+                fde_min_12 += sums[3]
+            if just_one:
+                break
+        ade_avg_12 /= self.n_test_samples
+        fde_avg_12 /= self.n_test_samples
+        ade_min_12 /= self.n_test_samples
+        fde_min_12 /= self.n_test_samples
+        if verbose:
+            print('Avg ADE,FDE (12)= (%.3f, %.3f) | Min(20) ADE,FDE (12)= (%.3f, %.3f)'
+                  % (ade_avg_12, fde_avg_12, ade_min_12, fde_min_12))
+        return dict(ade_avg=ade_avg_12, fde_avg=fde_avg_12, ade_min=ade_min_12, fde_min=fde_min_12)
+
+    # ------------------------------------------------------------------ train.py:622-663
+    def state(self):
+        return {'epoch': self.epoch,
+                'attentioner_dict': self.attention.state_dict(),
+                'feature_embedder_dict': self.feature_embedder.state_dict(),
+                'encoder_dict': self.encoder.state_dict(),
+                'decoder_dict': self.decoder.state_dict(),
+                'pred_optimizer': self.predictor_optimizer.state_dict(),
+                'D_dict': self.D.state_dict(),
+                'D_optimizer': self.D_optimizer.state_dict()}
+
+    def load_state(self, checkpoint):
+        self.attention.load_state_dict(checkpoint['attentioner_dict'])
+        self.feature_embedder.load_state_dict(checkpoint['feature_embedder_dict'])
+        self.encoder.load_state_dict(checkpoint['encoder_dict'])
+        self.decoder.load_state_dict(checkpoint['decoder_dict'])
+        self.predictor_optimizer.load_state_dict(checkpoint['pred_optimizer'])
+        self.D.load_state_dict(checkpoint['D_dict'])
+        self.D_optimizer.load_state_dict(checkpoint['D_optimizer'])
+        return checkpoint['epoch'] + 1
+
+    def reference_weights(self):
+        out = {k: v.detach().clone() for k, v in self.generator.state_dict().items()}
+        out.update({"D." + k: v.detach().clone() for k, v in self.D.state_dict().items()})
+        return out

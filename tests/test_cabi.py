@@ -33,10 +33,10 @@ def test_library_exports_every_declared_symbol():
 def test_null_pointers_are_rejected_without_touching_the_gpu():
     from socialways_b200 import _lib
     lib = _lib.lib()
-    assert lib.sw_decode_fwd(None, None, None, None, None, None, None, None, 1, 1, 1, 148, None) == -1
+    assert lib.sw_decode_fwd(*([None] * 12), 1, 1, 1, 148, None) == -1
     assert lib.sw_pool_fwd(None, None, None, None, None, None, None, None, 1, 1, None) == -1
     assert lib.sw_bestofk_metrics(None, None, 1.0, 1, 1, 1, None, None) == -1
-    assert lib.sw_lstm_seq_fwd(None, None, 2, 1, 8, None, None, None, None, None, None, None, None, None, 148, None) == -1
+    assert lib.sw_lstm_seq_fwd(None, None, 2, 1, 8, *([None] * 8), 148, None) == -1
 
 
 def test_product_path_never_imports_the_oracle():
