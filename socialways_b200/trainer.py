@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 import torch.optim as opt
 
+from . import distributed as swdist
 from . import ops
 from .reference_api import Discriminator, Generator, get_traj_4d, predict_cv
 from .scale import Scale
@@ -25,7 +26,7 @@ from .scale import Scale
 class SocialWaysTrainer:
     def __init__(self, data, batch_size=256, hidden_size=64, use_social=False, n_unrolling_steps=1,
                  lr_g=1e-4, lr_d=1e-3, device="cuda", weights=None, n_latent_codes=2,
-                 use_info_loss=True, loss_info_w=0.5):
+                 use_info_loss=True, loss_info_w=0.5, world=None):
         self.device = torch.device(device)
         self.batch_size, self.n_unrolling_steps = batch_size, n_unrolling_steps
         self.use_info_loss, self.loss_info_w, self.n_latent_codes = use_info_loss, loss_info_w, n_latent_codes
@@ -64,6 +65,7 @@ class SocialWaysTrainer:
         self.predictor_optimizer = opt.Adam(self.generator.optimizer_parameters(), lr=lr_g, betas=(0.9, 0.999))
         self.D_optimizer = opt.Adam(self.D.parameters(), lr=lr_d, betas=(0.9, 0.999))
         self.mse_loss = nn.MSELoss()
+        self.world_size, self.rank = swdist.world() if world is None else world
         self.epoch = 1
         self.loss_log = []
 
@@ -102,57 +104,75 @@ class SocialWaysTrainer:
                 zeros = (torch.zeros(bs, 1) + np.random.uniform(0, 0.1)).to(dev)          # :471
                 ones = (torch.ones(bs, 1) * np.random.uniform(0.9, 1.0)).to(dev)           # :472
                 noise = torch.rand(bs, self.noise_len).to(dev)                             # :473 (CPU RNG)
+                if self.world_size > 1:
+                    # labels / noise are drawn for the GLOBAL batch on every rank (identical
+                    # RNG streams), then each rank keeps the rows of its own block of scenes
+                    lo, hi, sub_batches = swdist.shard_scenes(sub_batches, self.world_size, self.rank)
+                    obsv, pred, obsv_4d, pred_4d = obsv[lo:hi], pred[lo:hi], obsv_4d[lo:hi], pred_4d[lo:hi]
+                    zeros, ones, noise = zeros[lo:hi], ones[lo:hi], noise[lo:hi]
+                    mse_loss = lambda a, b, _bs=bs: swdist.global_mse(a, b, _bs * max(1, a.numel() // max(1, a.shape[0])))
+                have_rows = obsv.shape[0] > 0
                 backup = None
                 # ============== Train Discriminator ================ :476-499
                 for u in range(self.n_unrolling_steps + 1):
                     D.zero_grad()
-                    with torch.no_grad():
-                        pred_hat_4d = self.predict(obsv, noise, self.n_next, sub_batches)
-                    obsv_h = D.encode_obsv(obsv_4d)
-                    fake_labels, code_hat = D.heads(obsv_h, pred_hat_4d)
-                    d_loss_fake = mse_loss(fake_labels, zeros)
-                    d_loss_info = mse_loss(code_hat.squeeze(), noise[:, :self.n_latent_codes])
-                    real_labels, code_hat = D.heads(obsv_h, pred_4d)
-                    d_loss_real = mse_loss(real_labels, ones)
-                    d_loss = d_loss_fake + d_loss_real
-                    if self.use_info_loss:
-                        d_loss = d_loss + self.loss_info_w * d_loss_info
-                    d_loss.backward()
+                    if have_rows:
+                        with torch.no_grad():
+                            pred_hat_4d = self.predict(obsv, noise, self.n_next, sub_batches)
+                        obsv_h = D.encode_obsv(obsv_4d)
+                        fake_labels, code_hat = D.heads(obsv_h, pred_hat_4d)
+                        d_loss_fake = mse_loss(fake_labels, zeros)
+                        d_loss_info = mse_loss(code_hat.squeeze(1) if code_hat.shape[1] == 1 else code_hat,
+                                               noise[:, :self.n_latent_codes])
+                        real_labels, code_hat = D.heads(obsv_h, pred_4d)
+                        d_loss_real = mse_loss(real_labels, ones)
+                        d_loss = d_loss_fake + d_loss_real
+                        if self.use_info_loss:
+                            d_loss = d_loss + self.loss_info_w * d_loss_info
+                        d_loss.backward()
+                    swdist.allreduce_grads(D.parameters(), self.world_size)
                     self.D_optimizer.step()
                     if u == 0 and self.n_unrolling_steps > 0:
                         backup = copy.deepcopy(D)
                 # =============== Train Generator ================= :501-543
                 D.zero_grad()
                 self.predictor_optimizer.zero_grad()
-                pred_hat_4d = self.predict(obsv, noise, self.n_next, sub_batches)
-                with torch.no_grad():          # D's observation code does not depend on the generator
-                    obsv_h = D.encode_obsv(obsv_4d)
-                gen_labels, code_hat = D.heads(obsv_h, pred_hat_4d)
-                g_loss_fooling = mse_loss(gen_labels, ones)
-                g_loss_info = mse_loss(code_hat.squeeze(), noise[:, :self.n_latent_codes])
-                g_loss = g_loss_fooling
-                if self.use_info_loss:
-                    g_loss = g_loss + self.loss_info_w * g_loss_info
-                g_loss.backward()
+                if have_rows:
+                    pred_hat_4d = self.predict(obsv, noise, self.n_next, sub_batches)
+                    with torch.no_grad():          # D's observation code does not depend on the generator
+                        obsv_h = D.encode_obsv(obsv_4d)
+                    gen_labels, code_hat = D.heads(obsv_h, pred_hat_4d)
+                    g_loss_fooling = mse_loss(gen_labels, ones)
+                    g_loss_info = mse_loss(code_hat.squeeze(1) if code_hat.shape[1] == 1 else code_hat,
+                                           noise[:, :self.n_latent_codes])
+                    g_loss = g_loss_fooling
+                    if self.use_info_loss:
+                        g_loss = g_loss + self.loss_info_w * g_loss_info
+                    g_loss.backward()
+                swdist.allreduce_grads(list(self.generator.optimizer_parameters()), self.world_size)
                 self.predictor_optimizer.step()
                 if self.n_unrolling_steps > 0:
                     D.load(backup)
                     del backup
-                with torch.no_grad():                                                      # :546-551
-                    err_all = torch.pow((pred_hat_4d[:, :, :2] - pred) / self.ss, 2)
-                    err_all = err_all.sum(dim=2).sqrt()
-                    e = err_all.sum().item() / self.n_next
-                    train_ADE += e
-                    train_FDE += err_all[:, -1].sum().item()
+                if have_rows:
+                    with torch.no_grad():                                                  # :546-551
+                        err_all = torch.pow((pred_hat_4d[:, :, :2] - pred) / self.ss, 2)
+                        err_all = err_all.sum(dim=2).sqrt()
+                        e = err_all.sum().item() / self.n_next
+                        train_ADE += e
+                        train_FDE += err_all[:, -1].sum().item()
+                if not have_rows:
+                    d_loss = d_loss_fake = d_loss_real = d_loss_info = g_loss_fooling = g_loss_info = torch.zeros(())
                 self.loss_log.append(dict(d_loss=d_loss.item(), d_fake=d_loss_fake.item(), d_real=d_loss_real.item(),
                                           d_info=d_loss_info.item(), g_fool=g_loss_fooling.item(),
                                           g_info=g_loss_info.item()))
                 batch_size_accum = 0
                 sub_batches = []
+        train_ADE, train_FDE = swdist.allreduce_scalars([train_ADE, train_FDE], dev, self.world_size)
         train_ADE /= self.n_train_samples
         train_FDE /= self.n_train_samples
         toc = time.perf_counter()
-        if verbose:
+        if verbose and self.rank == 0:
             print(" Epc=%4d, Train ADE,FDE = (%.3f, %.3f) | time = %.1f" % (self.epoch, train_ADE, train_FDE, toc - tic))
         return train_ADE, train_FDE
 

@@ -146,3 +146,17 @@ def test_checkpoint_keys_match_reference():
                      ("encoder", 'encoder_dict'), ("decoder", 'decoder_dict'), ("D", 'D_dict')):
         want = {k[len(tag) + 1:]: tuple(v.shape) for k, v in ref.items() if k.startswith(tag + ".")}
         assert {k: tuple(v.shape) for k, v in st[key].items()} == want
+
+
+def test_sharded_training_matches_single_gpu():
+    """N-rank NCCL run of the sharded step vs one GPU (needs >= 2 visible GPUs; `gpurun --gpus 2`)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(here, "multigpu_train_check.py")], capture_output=True, text=True, timeout=600)
+    assert "MULTIGPU_TRAIN_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

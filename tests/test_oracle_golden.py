@@ -147,3 +147,30 @@ def test_training_epochs_and_test_metrics(case, data_fn, social):
     want = g[f"{tag}.test_metrics"]
     got = np.array([m2["ade_avg"], m2["fde_avg"], m2["ade_min"], m2["fde_min"]])
     np.testing.assert_allclose(got, want, atol=1e-4, rtol=0)       # the 1e-4 ADE/FDE bar of north_star
+
+
+@pytest.mark.parametrize("n,c", [(216, 6), (768, 8)])
+def test_product_toy_generator_matches_reference(n, c):
+    """socialways_b200.toy (what the repo's create_toy.py entry point runs) vs the reference's dataset."""
+    from socialways_b200.toy import create_samples, pack_scenes
+    g = load_golden(f"toy_{n}_{c}.npz")
+    np.random.seed(30)
+    samples, ts = create_samples(n, c, 3, n_per_batch=6)
+    obsvs, preds, times, batches = pack_scenes(samples, ts)
+    assert np.array_equal(obsvs, g["obsvs"]) and np.array_equal(preds, g["preds"])
+    assert np.array_equal(times, g["times"]) and np.array_equal(batches, g["batches"])
+
+
+def test_scale_matches_oracle():
+    from socialways_b200.scale import Scale
+    d = so.toy_samples(216, 6)
+    ref = so.IsoScale(d["obsvs"], d["preds"])
+    s = Scale()
+    s.min_x, s.max_x = min(d["obsvs"][..., 0].min(), d["preds"][..., 0].min()), max(d["obsvs"][..., 0].max(), d["preds"][..., 0].max())
+    s.min_y, s.max_y = min(d["obsvs"][..., 1].min(), d["preds"][..., 1].min()), max(d["obsvs"][..., 1].max(), d["preds"][..., 1].max())
+    s.calc_scale(keep_ratio=True)
+    assert s.sx == ref.sx == s.sy
+    a = d["obsvs"].copy()
+    n1 = s.normalize(a.copy())
+    assert np.array_equal(n1, ref.normalize(a))
+    assert np.allclose(s.denormalize(n1), a, atol=1e-6)

@@ -1,0 +1,83 @@
+#!/usr/bin/env python3
+"""Social Ways trajectory prediction -- B200-native drop-in for the reference train.py.
+
+Same command line as the reference (train.py:19-50: --batch-size --epochs --model --latent-dim
+--d-learning-rate --g-learning-rate --unrolling-steps --hidden-size --dataset), same defaults, same
+printed lines, same checkpoint dictionary (train.py:653-663) and prediction dumps (train.py:591-599).
+Flags ADDED here (the reference hard-codes these as module constants / paths, train.py:56-57,83):
+  --use-social      flip the `use_social` constant (reference default False, train.py:83)
+  --input-file      dataset npz (reference: '../hotel-8-12.npz')
+  --model-file      checkpoint path (reference: '../trained_models/<model>-<dataset>.pt')
+  --out-dir         where test() dumps go (reference: '../medium/<dataset>/<model>/<epoch>')
+  --seed            seeds numpy and torch (the reference seeds nothing)
+  --test-samples    K of the periodic test() call (reference: 128, train.py:668)
+All arithmetic runs in the sm_100a kernels of socialways_b200 (no CPU fallback).
+"""
+import argparse
+import os
+
+import numpy as np
+import torch
+from tqdm import trange
+
+parser = argparse.ArgumentParser(description='Social Ways trajectory prediction.')
+parser.add_argument('--batch-size', '--b', type=int, default=256, metavar='N',
+                    help='input batch size for training (default: 256)')
+parser.add_argument('--epochs', '--e', type=int, default=1000, metavar='N',
+                    help='number of epochs to train (default: 1000)')
+parser.add_argument('--model', '--m', default='socialWays', choices=['socialWays'],
+                    help='pick a specific network to train (default: "socialWays")')
+parser.add_argument('--latent-dim', '--ld', type=int, default=10, metavar='N',
+                    help='dimension of latent space (default: 10)')
+parser.add_argument('--d-learning-rate', '--d-lr', type=float, default=1E-3, metavar='N',
+                    help='learning rate of discriminator (default: 1E-3)')
+parser.add_argument('--g-learning-rate', '--g-lr', type=float, default=1E-4, metavar='N',
+                    help='learning rate of generator (default: 1E-4)')
+parser.add_argument('--unrolling-steps', '--unroll', type=int, default=1, metavar='N',
+                    help='number of steps to unroll gan (default: 1)')
+parser.add_argument('--hidden-size', '--h-size', type=int, default=64, metavar='N',
+                    help='size of network intermediate layer (default: 64)')
+parser.add_argument('--dataset', '--data', default='hotel', choices=['hotel'],
+                    help='pick a specific dataset (default: "hotel")')
+parser.add_argument('--use-social', action='store_true')
+parser.add_argument('--input-file', default='../hotel-8-12.npz')
+parser.add_argument('--model-file', default=None)
+parser.add_argument('--out-dir', default=None)
+parser.add_argument('--seed', type=int, default=None)
+parser.add_argument('--test-samples', type=int, default=128)
+
+
+def main():
+    args = parser.parse_args()
+    from socialways_b200.trainer import SocialWaysTrainer
+    model_file = args.model_file or '../trained_models/' + args.model + '-' + args.dataset + '.pt'
+    if args.seed is not None:
+        np.random.seed(args.seed)
+        torch.manual_seed(args.seed)
+    print(os.path.dirname(os.path.realpath(__file__)))
+    data = np.load(args.input_file)
+    tr = SocialWaysTrainer(data, batch_size=args.batch_size, hidden_size=args.hidden_size,
+                           use_social=args.use_social, n_unrolling_steps=args.unrolling_steps,
+                           lr_g=args.g_learning_rate, lr_d=args.d_learning_rate)
+    print(args.input_file, ' # Training samples: ', tr.n_train_samples)
+    print('hidden dim = %d | lr(G) =  %.5f | lr(D) =  %.5f' % (args.hidden_size, args.g_learning_rate, args.d_learning_rate))
+    if os.path.isfile(model_file):                                   # train.py:622-637
+        print('Loading model from ' + model_file)
+        start_epoch = tr.load_state(torch.load(model_file))
+    else:
+        start_epoch = 1
+    for epoch in trange(start_epoch, args.epochs + 1):               # train.py:646-668
+        tr.epoch = epoch
+        tr.train()
+        if epoch % 50 == 0:
+            print('Saving model to file ...', model_file)
+            os.makedirs(os.path.dirname(os.path.abspath(model_file)), exist_ok=True)
+            torch.save(tr.state(), model_file)
+        if epoch % 5 == 0:
+            wr_dir = os.path.join(args.out_dir or ('../medium/' + args.dataset + '/' + args.model), str(epoch))
+            os.makedirs(wr_dir, exist_ok=True)
+            tr.test(args.test_samples, write_to_file=wr_dir, just_one=True)
+
+
+if __name__ == '__main__':
+    main()
