@@ -112,6 +112,14 @@ int sw_decode_bwd(const float* lstm_pack_t, const float* dec_pack_t, const float
                   float* g_gates, float* g_a1, float* g_a2, float* g_v, float* dh0, float* dc0,
                   int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 
+/* Tensor-core variant of sw_decode_fwd: tcgen05.mma with BF16 operands in shared memory and FP32 accumulators
+ * in TMEM (fast mode, not the fp32 parity mode).  tc_w16 / tc_f32 from packing.pack_decoder_tc;
+ * sizes via sw_decode_tc_pack_sizes.  Other arguments as sw_decode_fwd (no backward stash). */
+int sw_decode_fwd_tc(const void* tc_w16, const float* tc_f32, const float* h0, const float* c0,
+                     const float* pooled, const float* noise, const float* x_last, float* out,
+                     int n_agents, int n_samples, int n_next, int sm_count, void* stream);
+int sw_decode_tc_pack_sizes(int* n_bf16, int* n_f32);
+
 /* Best-of-K error metrics.  Replaces train.py:587 and :602-607 of test().
  *   pred [K][N][T][4], gt [N][T][2] (normalised), ss = Scale.sx (train.py:121)
  *   out [N][4] = (avg-K ADE, avg-K FDE, min-K ADE, min-K FDE) per agent */

@@ -26,6 +26,8 @@ _PROTOTYPES = {
     "sw_pool_bwd": (_I, [_P] * 16 + [_I, _I, _P]),
     "sw_decode_fwd": (_I, [_P] * 12 + [_I, _I, _I, _I, _P]),
     "sw_decode_bwd": (_I, [_P] * 13 + [_I, _I, _I, _I, _P]),
+    "sw_decode_fwd_tc": (_I, [_P] * 8 + [_I, _I, _I, _I, _P]),
+    "sw_decode_tc_pack_sizes": (_I, [_P, _P]),
     "sw_bestofk_metrics": (_I, [_P, _P, _F, _I, _I, _I, _P, _P]),
 }
 

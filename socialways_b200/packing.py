@@ -48,3 +48,28 @@ def pool_agent_matrix(att_w, att_b, fc4_w, fc4_b):
     """[64, 65] matrix M and [65] offset m0 with  (u | beta) = h @ M + m0."""
     tail = torch.cat([fc4_w, fc4_b.unsqueeze(1)], dim=1)    # [64(n), 65]: Wh @ tail = (u | beta)
     return att_w.t() @ tail, att_b @ tail
+
+
+def _canonical_kmajor(w_nk):
+    """[N, K] (K % 8 == 0) -> canonical no-swizzle K-major UMMA operand: [K/8][N][8] (8-row x 16-byte core
+    matrices, SBO = 128 B, LBO = N * 16 B)."""
+    n, k = w_nk.shape
+    return w_nk.reshape(n, k // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
+
+
+def pack_decoder_tc(lstm_pack, dec_pack):
+    """Operands of the tcgen05 decode kernel (csrc/decode_fwd_tc.cu) from the fp32 packs:
+    bf16 section  W1 [160 n][160 k] | W2 [80][160] | W34 [16 (2 real)][80] | Whh [256 n'][64], each canonical;
+    fp32 section  Wx [4][256] | bL [256] | b1 [160] | b2 [80] | b34 [2] | pad -> 1536 floats."""
+    w1 = dec_pack[:25600].view(160, 160).t()
+    b1 = dec_pack[25600:25760]
+    w2 = dec_pack[25760:38560].view(160, 80).t()
+    b2 = dec_pack[38560:38640]
+    w34 = dec_pack[38640:38800].view(80, 2).t()
+    b34 = dec_pack[38800:38802]
+    w34p = torch.zeros(16, 80, device=dec_pack.device, dtype=dec_pack.dtype)
+    w34p[:2] = w34
+    whh = lstm_pack[4:68].t()
+    w16 = torch.cat([_canonical_kmajor(w1), _canonical_kmajor(w2), _canonical_kmajor(w34p), _canonical_kmajor(whh)])
+    f32 = torch.cat([lstm_pack[0:4].reshape(-1), lstm_pack[68], b1, b2, b34, b34.new_zeros(14)])
+    return w16.to(torch.bfloat16).contiguous(), f32.contiguous()

@@ -260,6 +260,7 @@ class Generator(nn.Module):
                 packs = dict(enc=self.encoder.packed(), dec=self.decoder.packed(),
                              pool=packing.pack_pool(fe[0].weight, fe[0].bias, fe[2].weight, fe[2].bias),
                              pool_m=m.contiguous(), pool_m0=m0.contiguous())
+                packs["tc_w16"], packs["tc_f32"] = packing.pack_decoder_tc(packs["enc"], packs["dec"])
             self._pack_cache = (key, packs)
         return self._pack_cache[1]
 
@@ -276,9 +277,10 @@ class Generator(nn.Module):
         return self._scene_cache[key]
 
     @torch.no_grad()
-    def predict_k(self, obsv_p, noise, n_next, sub_batches=(), out=None):
+    def predict_k(self, obsv_p, noise, n_next, sub_batches=(), out=None, precision="fp32"):
         """K-sample predict(): noise [K,N,32] -> [K,N,n_next,4].  The observation encoding and the
-        pooled social vector do not depend on the sample and are computed once."""
+        pooled social vector do not depend on the sample and are computed once.
+        precision="fp32": FFMA decode kernel (the parity mode); "bf16": tcgen05/TMEM decode kernel."""
         if not obsv_p.is_cuda:
             raise SocialWaysCudaError("predict() runs on CUDA tensors only (no CPU fallback)")
         pk = self.packs()
@@ -289,6 +291,10 @@ class Generator(nn.Module):
             scenes = self.scene_index(sub_batches, n, obsv_p.device)
             ub = torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])
             pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
+        if precision == "bf16":
+            return ops.decode_tc(pk["tc_w16"], pk["tc_f32"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
+        if precision != "fp32":
+            raise ValueError("precision must be 'fp32' or 'bf16'")
         return ops.decode(pk["enc"], pk["dec"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
 
     def predict(self, obsv_p, noise, n_next, sub_batches=()):
