@@ -120,6 +120,14 @@ int sw_decode_fwd_tc(const void* tc_w16, const float* tc_f32, const float* h0, c
                      int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 int sw_decode_tc_pack_sizes(int* n_bf16, int* n_f32);
 
+/* fp32-faithful tensor-core variant of sw_decode_fwd: tcgen05.mma on fp16 hi/lo split operands (x = hi + lo,
+ * A.B ~= Ahi.Bhi + Ahi.Blo + Alo.Bhi, fp32 accumulate in TMEM; a1/a2 live in TMEM as the A operand of the next
+ * layer).  Packs from packing.pack_decoder_tcx; sizes via sw_decode_tcx_pack_sizes. */
+int sw_decode_fwd_tcx(const void* tcx_w16, const void* tcx_wsz16, const float* tcx_f32, const float* h0,
+                      const float* c0, const float* pooled, const float* noise, const float* x_last, float* out,
+                      int n_agents, int n_samples, int n_next, int sm_count, void* stream);
+int sw_decode_tcx_pack_sizes(int* n_w16, int* n_wsz16, int* n_f32);
+
 /* Best-of-K error metrics.  Replaces train.py:587 and :602-607 of test().
  *   pred [K][N][T][4], gt [N][T][2] (normalised), ss = Scale.sx (train.py:121)
  *   out [N][4] = (avg-K ADE, avg-K FDE, min-K ADE, min-K FDE) per agent */

@@ -28,6 +28,8 @@ _PROTOTYPES = {
     "sw_decode_bwd": (_I, [_P] * 13 + [_I, _I, _I, _I, _P]),
     "sw_decode_fwd_tc": (_I, [_P] * 8 + [_I, _I, _I, _I, _P]),
     "sw_decode_tc_pack_sizes": (_I, [_P, _P]),
+    "sw_decode_fwd_tcx": (_I, [_P] * 9 + [_I, _I, _I, _I, _P]),
+    "sw_decode_tcx_pack_sizes": (_I, [_P, _P, _P]),
     "sw_bestofk_metrics": (_I, [_P, _P, _F, _I, _I, _I, _P, _P]),
 }
 

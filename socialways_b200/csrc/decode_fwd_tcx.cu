@@ -1,0 +1,342 @@
+// fp32-faithful tensor-core decode kernel: tcgen05.mma on FP16 hi/lo SPLIT operands.
+//
+// Same computation as decode_fwd.cu (the loop of predict(), reference train.py:418-430, for every
+// (sample, agent) row), but every dense layer runs on the 5th-gen tensor cores with each fp32 operand x
+// represented as two fp16 numbers  x = hi + lo,  hi = fp16(x), lo = fp16(x - hi)  (22 significant bits; the
+// operand ranges of this network -- |x| < ~1e2 -- sit well inside fp16), and each product evaluated as
+//     A.B  ~=  A_hi.B_hi + A_hi.B_lo + A_lo.B_hi        (3 MMAs, fp32 accumulation in TMEM)
+// which keeps the result within ~1e-6 of the fp32 FFMA kernel: the 1e-4 ADE/FDE parity bar holds.
+//
+// One CTA = one 128-row tile at a time (UMMA M = 128, cta_group::1), 512 threads, thread t owns row
+// 32*(warp%4)+lane (its TMEM lane) and column quarter warp/4.  Operand placement:
+//   weights  W1h, W2, W34, Whh as hi|lo fp16 in shared memory (163 KB), canonical K-major no-swizzle layout
+//   h        hi|lo fp16 in shared memory (32 KB), rewritten by the LSTM epilogue every step
+//   a1, a2   hi|lo fp16 written IN PLACE over their own fp32 accumulators in TMEM (tcgen05.st) and consumed
+//            as the TMEM A operand of the next layer -- they never touch shared memory
+//   c1       the step-invariant part of layer 1, [S ; z] . W1[S,z rows] (hoisted), computed
+//            once per tile by MMAs whose weights are streamed through a 20 KB staging buffer, and
+//            kept in 160 TMEM columns for the 12 steps
+//   (p, v)   fed back to the LSTM input projection in fp32 FMAs (never rounded)
+// TMEM columns: [0,160) c1 | [160,320) L1 acc -> a1 hi|lo ; later gates half 1 | [320,448) L2 acc -> a2 hi|lo,
+//               L34 acc ; later gates half 0.
+#include <cuda_fp16.h>
+
+#include "sw_common.cuh"
+#include "sw_umma.cuh"
+
+namespace sw {
+
+constexpr int X_ROWS = 128;
+constexpr int X_THREADS = 512;
+// fp16 weight section (elements), every matrix canonical [K/8][N][8], hi block then lo block
+constexpr int XW_W1H_HI = 0, XW_W1H_LO = 10240, XW_W2_HI = 20480, XW_W2_LO = 33280, XW_W34_HI = 46080,
+              XW_W34_LO = 47360, XW_WHH_HI = 48640, XW_WHH_LO = 65024, XW_TOTAL = 81408;
+// hoist weights in global memory: 3 chunks of K = 32 rows of W1[S,z]: [chunk][hi|lo][4][160][8]
+constexpr int XW_SZ_CHUNK = 2 * 4 * 160 * 8;      // 10240 halves = 20480 B
+// fp32 section: wx4[256][4] | bL[256] | b1[160] | b2[80] | b34[2] | pad
+constexpr int XF_WX4 = 0, XF_BL = 1024, XF_B1 = 1280, XF_B2 = 1440, XF_B34 = 1520, XF_TOTAL = 1536;
+constexpr uint32_t XC_C1 = 0, XC_R1 = 160, XC_RG = 320, XC_V = 400;
+constexpr uint32_t FMT_F16 = 0;
+
+struct TcxSmem {
+    __half w[XW_TOTAL];                    // 162 816 B
+    __half h[2][8 * X_ROWS * 8];           // h hi | lo : [8 chunks][128][8]  (32 768 B)
+    __half stage[XW_SZ_CHUNK];             // hoist weight chunk (20 480 B)
+    float f32[XF_TOTAL];
+    float x4[4 * X_ROWS];
+    unsigned long long bar[2];
+    uint32_t tmem_base;
+};
+
+// x -> (hi, lo) fp16 pair for two values at once: returns packed hi2, lo2
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h2 = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+
+// three-pass product with both operands in shared memory
+__device__ __forceinline__ void mma3_ss(uint32_t d, const __half* a_hi, const __half* a_lo, const __half* b_hi,
+                                        const __half* b_lo, int b_rows, int n, int kblocks) {
+    umma_ss(d, a_hi, b_hi, b_rows, n, kblocks, FMT_F16, false);
+    umma_ss(d, a_hi, b_lo, b_rows, n, kblocks, FMT_F16, true);
+    umma_ss(d, a_lo, b_hi, b_rows, n, kblocks, FMT_F16, true);
+}
+
+// three-pass product with the A operand (hi / lo column blocks) in TMEM
+__device__ __forceinline__ void mma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const __half* b_hi, const __half* b_lo,
+                                        int b_rows, int n, int kblocks, bool accumulate_first) {
+    umma_ts(d, a_hi, b_hi, b_rows, n, kblocks, FMT_F16, accumulate_first);
+    umma_ts(d, a_hi, b_lo, b_rows, n, kblocks, FMT_F16, true);
+    umma_ts(d, a_lo, b_hi, b_rows, n, kblocks, FMT_F16, true);
+}
+
+__global__ void __launch_bounds__(X_THREADS, 1)
+decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__ wsz16, const float* __restrict__ wf32,
+                      const float* __restrict__ h0, const float* __restrict__ c0, const float* __restrict__ pooled,
+                      const float* __restrict__ noise, const float* __restrict__ x_last, float* __restrict__ out,
+                      int n_agents, long long n_rows, int n_next, int n_tiles) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TcxSmem& s = *reinterpret_cast<TcxSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lq = warp & 3, cq = warp >> 2;
+    const int r = lq * 32 + lane;
+
+    for (int i = tid * 8; i < XW_TOTAL; i += X_THREADS * 8)
+        *reinterpret_cast<uint4*>(s.w + i) = __ldg(reinterpret_cast<const uint4*>(w16 + i));
+    for (int i = tid; i < XF_TOTAL; i += X_THREADS) s.f32[i] = __ldg(wf32 + i);
+    if (warp == 0) {
+        ptx::tcgen05_alloc(ptx::cta_group_1, &s.tmem_base, 512u);
+        ptx::tcgen05_relinquish_alloc_permit(ptx::cta_group_1);
+    }
+    if (tid == 0) {
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[0]), 1);
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[1]), 1);
+        ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
+    }
+    ptx::fence_proxy_async(ptx::space_shared);
+    ptx::tcgen05_fence_before_thread_sync();
+    __syncthreads();
+    ptx::tcgen05_fence_after_thread_sync();
+    const uint32_t tmem = s.tmem_base;
+    const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);       // this thread's lane, column 0
+    uint32_t ph0 = 0, ph1 = 0;
+    const float4* wx4 = reinterpret_cast<const float4*>(s.f32 + XF_WX4);
+    const float* bL = s.f32 + XF_BL;
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const long long row0 = (long long)tile * X_ROWS;
+        const bool valid = row0 + r < n_rows;
+        const int agent = valid ? (int)((row0 + r) % n_agents) : 0;
+        // ---------------- tile prologue ----------------
+        {   // h0 -> hi|lo operand chunks (columns 16cq .. 16cq+15 of this row)
+            float v[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 t = valid ? __ldg(reinterpret_cast<const float4*>(h0 + (size_t)agent * SW_H + cq * 16) + q)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split2(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1], hi[e], lo[e]);
+                const size_t off = ((size_t)(cq * 2 + j) * X_ROWS + r) * 8;
+                *reinterpret_cast<uint4*>(s.h[0] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(s.h[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+        }
+        float c[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 t = valid ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent * SW_H + cq * 16) + q)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            c[q * 4] = t.x; c[q * 4 + 1] = t.y; c[q * 4 + 2] = t.z; c[q * 4 + 3] = t.w;
+        }
+        float p0 = 0.f, p1 = 0.f;
+        if (cq == 0 && valid) {
+            const float2 t = __ldg(reinterpret_cast<const float2*>(x_last + (size_t)agent * 4));
+            p0 = t.x; p1 = t.y;
+        }
+        {   // [S ; z] (K = 96) -> hi|lo TMEM A operand in R1: hi columns [160,208), lo [208,256); this thread: K 24cq..24cq+23
+            uint32_t hi[12], lo[12];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                const int k = cq * 24 + 2 * e;        // even; S and z boundaries (64) are even too
+                float a = 0.f, b = 0.f;
+                if (valid) {
+                    if (k < 64) {
+                        if (pooled) { const float2 t = __ldg(reinterpret_cast<const float2*>(pooled + (size_t)agent * SW_H + k)); a = t.x; b = t.y; }
+                    } else {
+                        const float2 t = __ldg(reinterpret_cast<const float2*>(noise + (size_t)(row0 + r) * SW_Z + (k - 64)));
+                        a = t.x; b = t.y;
+                    }
+                }
+                split2(a, b, hi[e], lo[e]);
+            }
+            tmem_st<12>(tl + XC_R1 + cq * 12, hi);
+            tmem_st<12>(tl + XC_R1 + 48 + cq * 12, lo);
+            ptx::tcgen05_wait_st();
+        }
+        // c1 = [S ; z] . W1[S,z rows]^T accumulated into TMEM [0,160): three K = 32 chunks of streamed weights
+        for (int ch = 0; ch < 3; ++ch) {
+            for (int i = tid * 8; i < XW_SZ_CHUNK; i += X_THREADS * 8)
+                *reinterpret_cast<uint4*>(s.stage + i) = __ldg(reinterpret_cast<const uint4*>(wsz16 + (size_t)ch * XW_SZ_CHUNK + i));
+            ptx::fence_proxy_async(ptx::space_shared);
+            ptx::tcgen05_fence_before_thread_sync();
+            __syncthreads();
+            if (tid == 0) {
+                ptx::tcgen05_fence_after_thread_sync();
+                mma3_ts(tmem + XC_C1, tmem + XC_R1 + ch * 16, tmem + XC_R1 + 48 + ch * 16, s.stage, s.stage + XW_SZ_CHUNK / 2,
+                        160, 160, 2, ch > 0);
+                umma_commit(&s.bar[0]);
+            }
+            mbar_wait(&s.bar[0], ph0); ph0 ^= 1;       // staging buffer is free again / c1 complete
+            ptx::tcgen05_fence_after_thread_sync();
+        }
+        ptx::tcgen05_fence_before_thread_sync();
+        __syncthreads();
+
+        for (int t = 0; t < n_next; ++t) {
+            const bool feed_back = t + 1 < n_next;
+            // ---------------- layer 1: h (K = 64, smem) -> 160, accumulate in R1 ----------------
+            if (tid == 0) {
+                ptx::tcgen05_fence_after_thread_sync();
+                mma3_ss(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_W1H_HI, s.w + XW_W1H_LO, 160, 160, 4);
+                umma_commit(&s.bar[0]);
+            }
+            mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
+            ptx::tcgen05_fence_after_thread_sync();
+            {
+                uint32_t hi[20], lo[20];
+                const float* b1 = s.f32 + XF_B1 + cq * 40;
+#pragma unroll
+                for (int part = 0; part < 2; ++part) {           // two halves of 20 columns: bounds the live registers
+                    uint32_t acc[20], c1v[20];
+                    tmem_ld<20>(tl + XC_R1 + cq * 40 + part * 20, acc);
+                    tmem_ld<20>(tl + XC_C1 + cq * 40 + part * 20, c1v);
+                    ptx::tcgen05_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 10; ++e) {
+                        const int j = part * 20 + 2 * e;
+                        const float y0 = lrelu02(__uint_as_float(acc[2 * e]) + __uint_as_float(c1v[2 * e]) + b1[j]);
+                        const float y1 = lrelu02(__uint_as_float(acc[2 * e + 1]) + __uint_as_float(c1v[2 * e + 1]) + b1[j + 1]);
+                        split2(y0, y1, hi[part * 10 + e], lo[part * 10 + e]);
+                    }
+                }
+                ptx::tcgen05_fence_before_thread_sync();
+                __syncthreads();                       // every thread has read its accumulator columns
+                ptx::tcgen05_fence_after_thread_sync();
+                tmem_st<20>(tl + XC_R1 + cq * 20, hi);           // a1 hi : columns [160,240)
+                tmem_st<20>(tl + XC_R1 + 80 + cq * 20, lo);      // a1 lo : columns [240,320)
+                ptx::tcgen05_wait_st();
+            }
+            ptx::tcgen05_fence_before_thread_sync();
+            __syncthreads();
+            // ---------------- layer 2: a1 (K = 160, TMEM) -> 80, accumulate in [320,400) ----------------
+            if (tid == 0) {
+                ptx::tcgen05_fence_after_thread_sync();
+                mma3_ts(tmem + XC_RG, tmem + XC_R1, tmem + XC_R1 + 80, s.w + XW_W2_HI, s.w + XW_W2_LO, 80, 80, 10, false);
+                umma_commit(&s.bar[0]);
+            }
+            mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
+            ptx::tcgen05_fence_after_thread_sync();
+            {
+                uint32_t acc[20], hi[10], lo[10];
+                tmem_ld<20>(tl + XC_RG + cq * 20, acc);
+                ptx::tcgen05_wait_ld();
+                const float* b2 = s.f32 + XF_B2 + cq * 20;
+#pragma unroll
+                for (int e = 0; e < 10; ++e)
+                    split2(lrelu02(__uint_as_float(acc[2 * e]) + b2[2 * e]), lrelu02(__uint_as_float(acc[2 * e + 1]) + b2[2 * e + 1]),
+                           hi[e], lo[e]);
+                ptx::tcgen05_fence_before_thread_sync();
+                __syncthreads();
+                ptx::tcgen05_fence_after_thread_sync();
+                tmem_st<10>(tl + XC_RG + cq * 10, hi);           // a2 hi : columns [320,360)
+                tmem_st<10>(tl + XC_RG + 40 + cq * 10, lo);      // a2 lo : columns [360,400)
+                ptx::tcgen05_wait_st();
+            }
+            ptx::tcgen05_fence_before_thread_sync();
+            __syncthreads();
+            // ---------------- folded layers 3+4: a2 (K = 80, TMEM) -> 2 (N padded to 16), accumulate in [400,416) ----------------
+            if (tid == 0) {
+                ptx::tcgen05_fence_after_thread_sync();
+                mma3_ts(tmem + XC_V, tmem + XC_RG, tmem + XC_RG + 40, s.w + XW_W34_HI, s.w + XW_W34_LO, 16, 16, 5, false);
+                umma_commit(&s.bar[0]);
+            }
+            mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
+            ptx::tcgen05_fence_after_thread_sync();
+            if (cq == 0) {
+                uint32_t a[2];
+                tmem_ld<2>(tl + XC_V, a);
+                ptx::tcgen05_wait_ld();
+                const float v0 = __uint_as_float(a[0]) + s.f32[XF_B34], v1 = __uint_as_float(a[1]) + s.f32[XF_B34 + 1];
+                p0 += v0; p1 += v1;
+                s.x4[r] = p0; s.x4[X_ROWS + r] = p1; s.x4[2 * X_ROWS + r] = v0; s.x4[3 * X_ROWS + r] = v1;
+                if (valid)
+                    *reinterpret_cast<float4*>(out + ((size_t)(row0 + r) * n_next + t) * 4) = make_float4(p0, p1, v0, v1);
+            }
+            ptx::tcgen05_fence_before_thread_sync();
+            __syncthreads();
+            if (!feed_back) break;
+            // ---------------- LSTM gates: h (K = 64, smem) -> 256 in two N halves: [320,448) and [160,288) ----------------
+            if (tid == 0) {
+                ptx::tcgen05_fence_after_thread_sync();
+                mma3_ss(tmem + XC_RG, s.h[0], s.h[1], s.w + XW_WHH_HI, s.w + XW_WHH_LO, 256, 128, 4);
+                mma3_ss(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_WHH_HI + 128 * 8, s.w + XW_WHH_LO + 128 * 8, 256, 128, 4);
+                umma_commit(&s.bar[1]);
+            }
+            mbar_wait(&s.bar[1], ph1); ph1 ^= 1;
+            ptx::tcgen05_fence_after_thread_sync();
+            {
+                const float x0 = s.x4[r], x1 = s.x4[X_ROWS + r], x2 = s.x4[2 * X_ROWS + r], x3 = s.x4[3 * X_ROWS + r];
+                const uint32_t gbase = tl + ((cq < 2) ? XC_RG : XC_R1) + (cq & 1) * 64;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t a[32];
+                    tmem_ld<32>(gbase + half * 32, a);
+                    ptx::tcgen05_wait_ld();
+                    float hv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        float g[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int n = cq * 64 + half * 32 + u * 4 + q;
+                            const float4 w = wx4[n];
+                            g[q] = __uint_as_float(a[u * 4 + q]) + bL[n] + fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w * x3)));
+                        }
+                        const float gi = sigmoid_fast(g[0]), gf = sigmoid_fast(g[1]), gg = tanh_fast(g[2]), go = sigmoid_fast(g[3]);
+                        const int cu = half * 8 + u;
+                        c[cu] = fmaf(gf, c[cu], gi * gg);
+                        hv[u] = go * tanh_fast(c[cu]);
+                    }
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split2(hv[2 * e], hv[2 * e + 1], hi[e], lo[e]);
+                    const size_t off = ((size_t)(cq * 2 + half) * X_ROWS + r) * 8;
+                    *reinterpret_cast<uint4*>(s.h[0] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(s.h[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            ptx::fence_proxy_async(ptx::space_shared);
+            ptx::tcgen05_fence_before_thread_sync();
+            __syncthreads();
+        }
+    }
+    ptx::tcgen05_fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) ptx::tcgen05_dealloc(ptx::cta_group_1, tmem, 512u);
+}
+
+}  // namespace sw
+
+extern "C" int sw_decode_fwd_tcx(const void* tcx_w16, const void* tcx_wsz16, const float* tcx_f32, const float* h0,
+                                 const float* c0, const float* pooled, const float* noise, const float* x_last, float* out,
+                                 int n_agents, int n_samples, int n_next, int sm_count, void* stream) {
+    if (!tcx_w16 || !tcx_wsz16 || !tcx_f32 || !h0 || !c0 || !noise || !x_last || !out) return SW_ERR_ARG;
+    if (n_agents <= 0 || n_samples <= 0 || n_next <= 0 || sm_count <= 0) return SW_ERR_ARG;
+    const long long n_rows = (long long)n_agents * n_samples;
+    const long long tiles = (n_rows + sw::X_ROWS - 1) / sw::X_ROWS;
+    if (tiles > 0x7fffffffLL) return SW_ERR_UNSUPPORTED;
+    const int smem = (int)sizeof(sw::TcxSmem);
+    SW_CUDA_TRY(cudaFuncSetAttribute(sw::decode_fwd_tcx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    sw::decode_fwd_tcx_kernel<<<grid, sw::X_THREADS, smem, (cudaStream_t)stream>>>(
+        (const __half*)tcx_w16, (const __half*)tcx_wsz16, tcx_f32, h0, c0, pooled, noise, x_last, out, n_agents, n_rows,
+        n_next, (int)tiles);
+    SW_CUDA_TRY(cudaGetLastError());
+    return SW_OK;
+}
+
+extern "C" int sw_decode_tcx_pack_sizes(int* n_w16, int* n_wsz16, int* n_f32) {
+    if (!n_w16 || !n_wsz16 || !n_f32) return SW_ERR_ARG;
+    *n_w16 = sw::XW_TOTAL;
+    *n_wsz16 = 3 * sw::XW_SZ_CHUNK;
+    *n_f32 = sw::XF_TOTAL;
+    return SW_OK;
+}

@@ -177,6 +177,25 @@ def decode_tc(tc_w16, tc_f32, h0, c0, pooled, noise, x_last, n_next, out=None):
     return out
 
 
+def decode_tcx(w16, wsz16, f32, h0, c0, pooled, noise, x_last, n_next, out=None):
+    """sw_decode_fwd_tcx: tcgen05 decode kernel on fp16 hi/lo split operands (fp32-faithful)."""
+    noise = _f32(noise)
+    k, n, z = noise.shape
+    if z != Z or h0.shape != (n, H):
+        raise ValueError("decode_tcx: noise must be [K, N, 32] and h0 [N, 64]")
+    for t in (w16, wsz16):
+        if t.dtype != torch.float16 or not t.is_contiguous():
+            raise ValueError("decode_tcx: fp16 contiguous operand packs expected (packing.pack_decoder_tcx)")
+    if out is None:
+        out = torch.empty(k, n, n_next, 4, device=noise.device)
+    code = _lib.lib().sw_decode_fwd_tcx(w16.data_ptr(), wsz16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(_f32(h0)),
+                                        _lib.ptr(_f32(c0)), _lib.ptr(None if pooled is None else _f32(pooled)),
+                                        _lib.ptr(noise), _lib.ptr(_f32(x_last)), _lib.ptr(out), n, k, n_next,
+                                        sm_count(noise.device), _stream())
+    _lib.check(code, "sw_decode_fwd_tcx")
+    return out
+
+
 def decode_bwd(lstm_pack_t, dec_pack_t, c0, stash, d_out, n_agents, n_samples):
     """sw_decode_bwd.  d_out [K*N, T, 4] -> dict of gradient images + dh0/dc0 [K*N, 64]."""
     d_out = _f32(d_out)

@@ -73,3 +73,38 @@ def pack_decoder_tc(lstm_pack, dec_pack):
     w16 = torch.cat([_canonical_kmajor(w1), _canonical_kmajor(w2), _canonical_kmajor(w34p), _canonical_kmajor(whh)])
     f32 = torch.cat([lstm_pack[0:4].reshape(-1), lstm_pack[68], b1, b2, b34, b34.new_zeros(14)])
     return w16.to(torch.bfloat16).contiguous(), f32.contiguous()
+
+
+def _split_f16(w):
+    hi = w.to(torch.float16)
+    lo = (w - hi.to(torch.float32)).to(torch.float16)
+    return hi, lo
+
+
+def pack_decoder_tcx(lstm_pack, dec_pack):
+    """Operands of the fp16-split tcgen05 decode kernel (csrc/decode_fwd_tcx.cu):
+    w16   fp16 [81408]: for W1h [160 n][64 k], W2 [80][160], W34 [16 (2 real)][80], Whh [256 n'][64]:
+          canonical hi block then canonical lo block, x = hi + lo
+    wsz16 fp16 [3][2][4][160][8]: the hoisted rows of W1 (S: k 0..63, z: 64..95) in three K = 32 chunks, hi | lo
+    f32   [1536]: wx4 [256 n'][4] | bL [256] | b1 [160] | b2 [80] | b34 [2] | pad"""
+    w1 = dec_pack[:25600].view(160, 160).t()                  # [n, k], k order {h, S, z}
+    b1 = dec_pack[25600:25760]
+    w2 = dec_pack[25760:38560].view(160, 80).t()
+    b2 = dec_pack[38560:38640]
+    w34 = dec_pack[38640:38800].view(80, 2).t()
+    b34 = dec_pack[38800:38802]
+    w34p = torch.zeros(16, 80, device=dec_pack.device, dtype=dec_pack.dtype)
+    w34p[:2] = w34
+    whh = lstm_pack[4:68].t()
+    parts = []
+    for m in (w1[:, :64], w2, w34p, whh):
+        hi, lo = _split_f16(m.contiguous())
+        parts += [_canonical_kmajor(hi), _canonical_kmajor(lo)]
+    w16 = torch.cat(parts).contiguous()
+    chunks = []
+    for ch in range(3):
+        hi, lo = _split_f16(w1[:, 64 + 32 * ch:64 + 32 * (ch + 1)].contiguous())
+        chunks += [_canonical_kmajor(hi), _canonical_kmajor(lo)]
+    wsz16 = torch.cat(chunks).contiguous()
+    f32 = torch.cat([lstm_pack[0:4].t().reshape(-1), lstm_pack[68], b1, b2, b34, b34.new_zeros(14)]).contiguous()
+    return w16, wsz16, f32

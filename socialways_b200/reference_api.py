@@ -261,6 +261,7 @@ class Generator(nn.Module):
                              pool=packing.pack_pool(fe[0].weight, fe[0].bias, fe[2].weight, fe[2].bias),
                              pool_m=m.contiguous(), pool_m0=m0.contiguous())
                 packs["tc_w16"], packs["tc_f32"] = packing.pack_decoder_tc(packs["enc"], packs["dec"])
+                packs["tcx"] = packing.pack_decoder_tcx(packs["enc"], packs["dec"])
             self._pack_cache = (key, packs)
         return self._pack_cache[1]
 
@@ -280,7 +281,8 @@ class Generator(nn.Module):
     def predict_k(self, obsv_p, noise, n_next, sub_batches=(), out=None, precision="fp32"):
         """K-sample predict(): noise [K,N,32] -> [K,N,n_next,4].  The observation encoding and the
         pooled social vector do not depend on the sample and are computed once.
-        precision="fp32": FFMA decode kernel (the parity mode); "bf16": tcgen05/TMEM decode kernel."""
+        precision: "fp32" = FFMA decode kernel; "fp16x2" = tcgen05 kernel on fp16 hi/lo split operands
+        (fp32-faithful, ~1e-6); "bf16" = tcgen05 kernel on bf16 operands (fast mode, ~2e-3)."""
         if not obsv_p.is_cuda:
             raise SocialWaysCudaError("predict() runs on CUDA tensors only (no CPU fallback)")
         pk = self.packs()
@@ -293,8 +295,10 @@ class Generator(nn.Module):
             pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
         if precision == "bf16":
             return ops.decode_tc(pk["tc_w16"], pk["tc_f32"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
+        if precision == "fp16x2":
+            return ops.decode_tcx(*pk["tcx"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
         if precision != "fp32":
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+            raise ValueError("precision must be 'fp32', 'fp16x2' or 'bf16'")
         return ops.decode(pk["enc"], pk["dec"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
 
     def predict(self, obsv_p, noise, n_next, sub_batches=()):

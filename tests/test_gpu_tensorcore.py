@@ -75,3 +75,34 @@ def test_tc_decode_vs_bf16_emulation_and_oracle(sizes, k):
     last = obsv[:, -1].unsqueeze(0).unsqueeze(2).expand(k, -1, 1, -1)
     prev = torch.cat([last, got[:, :, :-1, :2]], 2)
     assert ((got[..., :2] - prev) - got[..., 2:]).abs().max().item() < 1e-6
+
+
+@pytest.mark.parametrize("sizes,k", [([8] * 16, 1), ([5, 1, 32, 2, 9], 3), ([8] * 40, 7), ([6] * 36, 2)])
+def test_tcx_fp16_split_decode_is_fp32_faithful(sizes, k):
+    """tcgen05 kernel on fp16 hi/lo split operands vs the fp32 oracle: operator tolerance 2e-5 (normalised),
+    best-of-K ADE/FDE within the 1e-4 bar of north_star."""
+    import socialways_b200 as sw
+    from socialways_b200 import ops
+    from oracle import socialways_oracle as so
+    P = so.init_weights(seed=6)
+    data = synthetic_scenes(sizes, seed=13)
+    sc = so.IsoScale(data["obsvs"], data["preds"])
+    obsv = torch.from_numpy(sc.normalize(data["obsvs"]))
+    pred = torch.from_numpy(sc.normalize(data["preds"]))
+    n = obsv.shape[0]
+    torch.manual_seed(4)
+    noise = torch.rand(k, n, 32)
+    gen = sw.Generator(use_social=True)
+    gen.load_state_dict({key: v for key, v in P.items() if not key.startswith("D.")})
+    gen = gen.cuda().requires_grad_(False)
+    for social in (True, False):
+        gen.use_social = social
+        got = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision="fp16x2")
+        want = torch.stack([so.predict(P, obsv, noise[i], 12, data["batches"], social, "closed") for i in range(k)])
+        err = (got.cpu() - want).abs().max().item()
+        print(f"fp16x2 tensor-core decode (use_social={social}): max |gpu - fp32 oracle| = {err:.2e}")
+        assert err < 2e-5, err
+        m = ops.bestofk_metrics(got, pred.cuda(), sc.sx).cpu()
+        e = (((want[..., :2] - pred) / sc.sx) ** 2).sum(-1).sqrt()
+        ref = torch.stack([e.mean(2).mean(0), e[:, :, -1].mean(0), e.mean(2).min(0)[0], e[:, :, -1].min(0)[0]], 1)
+        assert (m - ref).abs().max().item() < 1e-4
