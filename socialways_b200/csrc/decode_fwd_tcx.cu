@@ -17,8 +17,9 @@
 //            once per tile by MMAs whose weights are streamed through a 20 KB staging buffer, and
 //            kept in 160 TMEM columns for the 12 steps
 //   (p, v)   fed back to the LSTM input projection in fp32 FMAs (never rounded)
-// TMEM columns: [0,160) c1 | [160,320) L1 acc -> a1 hi|lo ; later gates half 1 | [320,448) L2 acc -> a2 hi|lo,
-//               L34 acc ; later gates half 0.
+// TMEM columns: [0,160) c1 | [160,320) L1 acc -> a1 hi|lo ; later gates half 1 | [320,448) L2 acc -> a2 hi|lo ;
+//               later gates half 0 | [448,464) L34 acc.  MMAs execute in issue order, so the gates MMAs are
+//               queued right behind the last reader of the region they overwrite and run under the epilogues.
 #include <cuda_fp16.h>
 
 #include "sw_common.cuh"
@@ -35,7 +36,7 @@ constexpr int XW_W1H_HI = 0, XW_W1H_LO = 10240, XW_W2_HI = 20480, XW_W2_LO = 332
 constexpr int XW_SZ_CHUNK = 2 * 4 * 160 * 8;      // 10240 halves = 20480 B
 // fp32 section: wx4[256][4] | bL[256] | b1[160] | b2[80] | b34[2] | pad
 constexpr int XF_WX4 = 0, XF_BL = 1024, XF_B1 = 1280, XF_B2 = 1440, XF_B34 = 1520, XF_TOTAL = 1536;
-constexpr uint32_t XC_C1 = 0, XC_R1 = 160, XC_RG = 320, XC_V = 400;
+constexpr uint32_t XC_C1 = 0, XC_R1 = 160, XC_RG = 320, XC_V = 448;
 constexpr uint32_t FMT_F16 = 0;
 
 struct TcxSmem {
@@ -44,7 +45,7 @@ struct TcxSmem {
     __half stage[XW_SZ_CHUNK];             // hoist weight chunk (20 480 B)
     float f32[XF_TOTAL];
     float x4[4 * X_ROWS];
-    unsigned long long bar[2];
+    unsigned long long bar[3];
     uint32_t tmem_base;
 };
 
@@ -94,6 +95,7 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
     if (tid == 0) {
         ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[0]), 1);
         ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[1]), 1);
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[2]), 1);
         ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
     }
     ptx::fence_proxy_async(ptx::space_shared);
@@ -221,6 +223,10 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
                 ptx::tcgen05_fence_after_thread_sync();
                 mma3_ts(tmem + XC_RG, tmem + XC_R1, tmem + XC_R1 + 80, s.w + XW_W2_HI, s.w + XW_W2_LO, 80, 80, 10, false);
                 umma_commit(&s.bar[0]);
+                if (feed_back) {   // gates, N half 1 -> [160,288): runs under the L2 / L34 epilogues
+                    mma3_ss(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_WHH_HI + 128 * 8, s.w + XW_WHH_LO + 128 * 8, 256, 128, 4);
+                    umma_commit(&s.bar[2]);
+                }
             }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
@@ -247,6 +253,10 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
                 ptx::tcgen05_fence_after_thread_sync();
                 mma3_ts(tmem + XC_V, tmem + XC_RG, tmem + XC_RG + 40, s.w + XW_W34_HI, s.w + XW_W34_LO, 16, 16, 5, false);
                 umma_commit(&s.bar[0]);
+                if (feed_back) {   // gates, N half 0 -> [320,448): queued behind L34, the last reader of a2
+                    mma3_ss(tmem + XC_RG, s.h[0], s.h[1], s.w + XW_WHH_HI, s.w + XW_WHH_LO, 256, 128, 4);
+                    umma_commit(&s.bar[1]);
+                }
             }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
@@ -263,14 +273,9 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
             if (!feed_back) break;
-            // ---------------- LSTM gates: h (K = 64, smem) -> 256 in two N halves: [320,448) and [160,288) ----------------
-            if (tid == 0) {
-                ptx::tcgen05_fence_after_thread_sync();
-                mma3_ss(tmem + XC_RG, s.h[0], s.h[1], s.w + XW_WHH_HI, s.w + XW_WHH_LO, 256, 128, 4);
-                mma3_ss(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_WHH_HI + 128 * 8, s.w + XW_WHH_LO + 128 * 8, 256, 128, 4);
-                umma_commit(&s.bar[1]);
-            }
-            mbar_wait(&s.bar[1], ph1); ph1 ^= 1;
+            // ---------------- LSTM cell on the two gate halves (column quarters 0,1 -> half 0; 2,3 -> half 1) ----------------
+            if (cq < 2) mbar_wait(&s.bar[1], ph1); else mbar_wait(&s.bar[2], ph1);
+            ph1 ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
             {
                 const float x0 = s.x4[r], x1 = s.x4[X_ROWS + r], x2 = s.x4[2 * X_ROWS + r], x3 = s.x4[3 * X_ROWS + r];
@@ -282,18 +287,18 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
                     ptx::tcgen05_wait_ld();
                     float hv[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        float g[4];
+                    for (int u = 0; u < 8; u += 2) {
+                        float g[2][4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int n = cq * 64 + half * 32 + u * 4 + q;
-                            const float4 w = wx4[n];
-                            g[q] = __uint_as_float(a[u * 4 + q]) + bL[n] + fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w * x3)));
-                        }
-                        const float gi = sigmoid_fast(g[0]), gf = sigmoid_fast(g[1]), gg = tanh_fast(g[2]), go = sigmoid_fast(g[3]);
-                        const int cu = half * 8 + u;
-                        c[cu] = fmaf(gf, c[cu], gi * gg);
-                        hv[u] = go * tanh_fast(c[cu]);
+                        for (int w2 = 0; w2 < 2; ++w2)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int n = cq * 64 + half * 32 + (u + w2) * 4 + q;
+                                const float4 w = wx4[n];
+                                g[w2][q] = __uint_as_float(a[(u + w2) * 4 + q]) + bL[n] +
+                                           fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w * x3)));
+                            }
+                        lstm_cell_pair(g[0], g[1], c[half * 8 + u], c[half * 8 + u + 1], hv[u], hv[u + 1]);
                     }
                     uint32_t hi[4], lo[4];
 #pragma unroll

@@ -110,4 +110,44 @@ __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f); }
 
+
+// e^{-x} for the logistic forms below, argument clamped so that products of two (1 + e) terms stay finite
+__device__ __forceinline__ float expneg_clamped(float x) { return ex2_approx(fminf(-1.4426950408889634f * x, 60.0f)); }
+
+// LSTM cell update of TWO hidden units with shared reciprocals: 1/(A.B) gives both 1/A and 1/B, so the 10
+// logistic/tanh evaluations cost 10 ex2 + 5 rcp MUFU operations instead of 10 + 10 (the MUFU pipe, 16
+// lanes/clk/SM, is what bounds the gate epilogue).  g = pre-activations (i, f, g, o); c updated in place.
+__device__ __forceinline__ void lstm_cell_pair(const float (&ga)[4], const float (&gb)[4], float& ca, float& cb,
+                                               float& ha, float& hb) {
+    float cn[2];
+    const float* gs[2] = {ga, gb};
+    const float cs[2] = {ca, cb};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float* g = gs[q];
+        const float ai = 1.0f + expneg_clamped(g[0]), ag = 1.0f + expneg_clamped(2.0f * g[2]);
+        const float r_ig = rcp_approx(ai * ag);
+        const float sig_i = ag * r_ig, tanh_g = fmaf(2.0f * ai, r_ig, -1.0f);
+        const float af = 1.0f + expneg_clamped(g[1]), ao = 1.0f + expneg_clamped(g[3]);
+        const float r_fo = rcp_approx(af * ao);
+        cn[q] = fmaf(ao * r_fo, cs[q], sig_i * tanh_g);              // sigma(f) = ao / (af.ao)
+        if (q == 0) ha = af * r_fo; else hb = af * r_fo;             // sigma(o), multiplied by tanh(c) below
+    }
+    const float a0 = 1.0f + expneg_clamped(2.0f * cn[0]), a1 = 1.0f + expneg_clamped(2.0f * cn[1]);
+    const float r = rcp_approx(a0 * a1);
+    ha *= fmaf(2.0f * a1, r, -1.0f);
+    hb *= fmaf(2.0f * a0, r, -1.0f);
+    ca = cn[0];
+    cb = cn[1];
+}
+
+// bf16-mode cell: hardware tanh (MUFU.TANH, rel. error 2^-11, below the bf16 operand rounding), 5 MUFU per unit
+__device__ __forceinline__ float tanh_hw(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void lstm_cell_hw(const float (&g)[4], float& c, float& h) {
+    const float si = fmaf(0.5f, tanh_hw(0.5f * g[0]), 0.5f), sf = fmaf(0.5f, tanh_hw(0.5f * g[1]), 0.5f);
+    const float so = fmaf(0.5f, tanh_hw(0.5f * g[3]), 0.5f);
+    c = fmaf(sf, c, si * tanh_hw(g[2]));
+    h = so * tanh_hw(c);
+}
+
 }  // namespace sw
