@@ -44,21 +44,9 @@ struct TcSmem {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ constexpr uint32_t umma_idesc_bf16(int n) { return umma_idesc(n, 1u); }
-
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&v);
-}
-
-// issue K/16 MMAs: D[128 x n] (+)= A[128 x K] . B[n x K]^T ; A chunks 2048 B apart, B chunks n*16 B apart
-__device__ __forceinline__ void issue_layer(uint32_t d_tmem, const __nv_bfloat16* a, const __nv_bfloat16* b, int n, int kblocks) {
-    const uint32_t idesc = umma_idesc_bf16(n);
-    for (int kb = 0; kb < kblocks; ++kb) {
-        const uint64_t ad = umma_desc(a + (size_t)kb * 2 * TC_ROWS * 8, TC_ROWS * 16, 128);
-        const uint64_t bd = umma_desc(b + (size_t)kb * 2 * n * 8, n * 16, 128);
-        ptx::tcgen05_mma(ptx::kind_f16, ptx::cta_group_1, d_tmem, ad, bd, idesc, kb > 0);
-    }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -71,6 +59,7 @@ decode_fwd_tc_kernel(const __nv_bfloat16* __restrict__ w16, const float* __restr
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lq = warp & 3, cq = warp >> 2;
     const int r = lq * 32 + lane;                          // row of the tile == TMEM lane
+    const bool leader = lane == 0;                         // lane of warp 0 that issues the MMAs
 
     // ---- one-time setup: weights -> smem, TMEM allocation, mbarriers ----
     for (int i = tid * 8; i < TW_TOTAL; i += TC_THREADS * 8)
@@ -151,13 +140,13 @@ decode_fwd_tc_kernel(const __nv_bfloat16* __restrict__ w16, const float* __restr
 
         for (int t = 0; t < n_next; ++t) {
             const bool feed_back = t + 1 < n_next;
-            if (tid == 0) {
+            if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
-                issue_layer(tmem + COL_L1, s.al1, s.w + TW_W1, 160, 10);
-                ptx::tcgen05_commit(ptx::cta_group_1, reinterpret_cast<uint64_t*>(&s.bar[0]));
+                umma_ss<160, 160, 10>(tmem + COL_L1, s.al1, s.w + TW_W1, 1u, false, leader);
+                umma_commit(&s.bar[0], leader);
                 if (feed_back) {
-                    issue_layer(tmem + COL_G, s.al1, s.w + TW_WHH, 256, 4);
-                    ptx::tcgen05_commit(ptx::cta_group_1, reinterpret_cast<uint64_t*>(&s.bar[1]));
+                    umma_ss<256, 256, 4>(tmem + COL_G, s.al1, s.w + TW_WHH, 1u, false, leader);
+                    umma_commit(&s.bar[1], leader);
                 }
             }
             // ---- L1 epilogue: +b1, LeakyReLU -> A1 (bf16) ----
@@ -183,10 +172,10 @@ decode_fwd_tc_kernel(const __nv_bfloat16* __restrict__ w16, const float* __restr
             ptx::fence_proxy_async(ptx::space_shared);
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
-                issue_layer(tmem + COL_L2, s.a12, s.w + TW_W2, 80, 10);
-                ptx::tcgen05_commit(ptx::cta_group_1, reinterpret_cast<uint64_t*>(&s.bar[0]));
+                umma_ss<80, 80, 10>(tmem + COL_L2, s.a12, s.w + TW_W2, 1u, false, leader);
+                umma_commit(&s.bar[0], leader);
             }
             // ---- L2 epilogue: +b2, LeakyReLU -> A2 (bf16, over the first 10 chunks of A1) ----
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
@@ -217,10 +206,10 @@ decode_fwd_tc_kernel(const __nv_bfloat16* __restrict__ w16, const float* __restr
             ptx::fence_proxy_async(ptx::space_shared);
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
-                issue_layer(tmem + COL_V, s.a12, s.w + TW_W34, 16, 5);
-                ptx::tcgen05_commit(ptx::cta_group_1, reinterpret_cast<uint64_t*>(&s.bar[0]));
+                umma_ss<16, 16, 5>(tmem + COL_V, s.a12, s.w + TW_W34, 1u, false, leader);
+                umma_commit(&s.bar[0], leader);
             }
             // ---- velocity, integration, emit, fp32 feedback state ----
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;

@@ -58,20 +58,22 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
     lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 
-// three-pass product with both operands in shared memory
+// three-pass product with both operands in shared memory (called by the whole issuing warp)
+template <int B_ROWS, int N, int KB>
 __device__ __forceinline__ void mma3_ss(uint32_t d, const __half* a_hi, const __half* a_lo, const __half* b_hi,
-                                        const __half* b_lo, int b_rows, int n, int kblocks) {
-    umma_ss(d, a_hi, b_hi, b_rows, n, kblocks, FMT_F16, false);
-    umma_ss(d, a_hi, b_lo, b_rows, n, kblocks, FMT_F16, true);
-    umma_ss(d, a_lo, b_hi, b_rows, n, kblocks, FMT_F16, true);
+                                        const __half* b_lo, bool leader) {
+    umma_ss<B_ROWS, N, KB>(d, a_hi, b_hi, FMT_F16, false, leader);
+    umma_ss<B_ROWS, N, KB>(d, a_hi, b_lo, FMT_F16, true, leader);
+    umma_ss<B_ROWS, N, KB>(d, a_lo, b_hi, FMT_F16, true, leader);
 }
 
 // three-pass product with the A operand (hi / lo column blocks) in TMEM
+template <int B_ROWS, int N, int KB>
 __device__ __forceinline__ void mma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const __half* b_hi, const __half* b_lo,
-                                        int b_rows, int n, int kblocks, bool accumulate_first) {
-    umma_ts(d, a_hi, b_hi, b_rows, n, kblocks, FMT_F16, accumulate_first);
-    umma_ts(d, a_hi, b_lo, b_rows, n, kblocks, FMT_F16, true);
-    umma_ts(d, a_lo, b_hi, b_rows, n, kblocks, FMT_F16, true);
+                                        bool accumulate_first, bool leader) {
+    umma_ts<B_ROWS, N, KB>(d, a_hi, b_hi, FMT_F16, accumulate_first, leader);
+    umma_ts<B_ROWS, N, KB>(d, a_hi, b_lo, FMT_F16, true, leader);
+    umma_ts<B_ROWS, N, KB>(d, a_lo, b_hi, FMT_F16, true, leader);
 }
 
 __global__ void __launch_bounds__(X_THREADS, 1)
@@ -84,6 +86,7 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lq = warp & 3, cq = warp >> 2;
     const int r = lq * 32 + lane;
+    const bool leader = lane == 0;          // lane of warp 0 that issues the MMAs
 
     for (int i = tid * 8; i < XW_TOTAL; i += X_THREADS * 8)
         *reinterpret_cast<uint4*>(s.w + i) = __ldg(reinterpret_cast<const uint4*>(w16 + i));
@@ -102,7 +105,7 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
     ptx::tcgen05_fence_before_thread_sync();
     __syncthreads();
     ptx::tcgen05_fence_after_thread_sync();
-    const uint32_t tmem = s.tmem_base;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0);   // warp-uniform for the compiler (uniform datapath)
     const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);       // this thread's lane, column 0
     uint32_t ph0 = 0, ph1 = 0;
     const float4* wx4 = reinterpret_cast<const float4*>(s.f32 + XF_WX4);
@@ -170,11 +173,11 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             ptx::fence_proxy_async(ptx::space_shared);
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
-            if (tid == 0) {
+            if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
-                mma3_ts(tmem + XC_C1, tmem + XC_R1 + ch * 16, tmem + XC_R1 + 48 + ch * 16, s.stage, s.stage + XW_SZ_CHUNK / 2,
-                        160, 160, 2, ch > 0);
-                umma_commit(&s.bar[0]);
+                mma3_ts<160, 160, 2>(tmem + XC_C1, tmem + XC_R1 + ch * 16, tmem + XC_R1 + 48 + ch * 16, s.stage,
+                                     s.stage + XW_SZ_CHUNK / 2, ch > 0, leader);
+                umma_commit(&s.bar[0], leader);
             }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;       // staging buffer is free again / c1 complete
             ptx::tcgen05_fence_after_thread_sync();
@@ -185,10 +188,10 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
         for (int t = 0; t < n_next; ++t) {
             const bool feed_back = t + 1 < n_next;
             // ---------------- layer 1: h (K = 64, smem) -> 160, accumulate in R1 ----------------
-            if (tid == 0) {
+            if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
-                mma3_ss(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_W1H_HI, s.w + XW_W1H_LO, 160, 160, 4);
-                umma_commit(&s.bar[0]);
+                mma3_ss<160, 160, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_W1H_HI, s.w + XW_W1H_LO, leader);
+                umma_commit(&s.bar[0], leader);
             }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
@@ -219,13 +222,13 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
             // ---------------- layer 2: a1 (K = 160, TMEM) -> 80, accumulate in [320,400) ----------------
-            if (tid == 0) {
+            if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
-                mma3_ts(tmem + XC_RG, tmem + XC_R1, tmem + XC_R1 + 80, s.w + XW_W2_HI, s.w + XW_W2_LO, 80, 80, 10, false);
-                umma_commit(&s.bar[0]);
+                mma3_ts<80, 80, 10>(tmem + XC_RG, tmem + XC_R1, tmem + XC_R1 + 80, s.w + XW_W2_HI, s.w + XW_W2_LO, false, leader);
+                umma_commit(&s.bar[0], leader);
                 if (feed_back) {   // gates, N half 1 -> [160,288): runs under the L2 / L34 epilogues
-                    mma3_ss(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_WHH_HI + 128 * 8, s.w + XW_WHH_LO + 128 * 8, 256, 128, 4);
-                    umma_commit(&s.bar[2]);
+                    mma3_ss<256, 128, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_WHH_HI + 128 * 8, s.w + XW_WHH_LO + 128 * 8, leader);
+                    umma_commit(&s.bar[2], leader);
                 }
             }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
@@ -249,13 +252,13 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
             // ---------------- folded layers 3+4: a2 (K = 80, TMEM) -> 2 (N padded to 16), accumulate in [400,416) ----------------
-            if (tid == 0) {
+            if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
-                mma3_ts(tmem + XC_V, tmem + XC_RG, tmem + XC_RG + 40, s.w + XW_W34_HI, s.w + XW_W34_LO, 16, 16, 5, false);
-                umma_commit(&s.bar[0]);
+                mma3_ts<16, 16, 5>(tmem + XC_V, tmem + XC_RG, tmem + XC_RG + 40, s.w + XW_W34_HI, s.w + XW_W34_LO, false, leader);
+                umma_commit(&s.bar[0], leader);
                 if (feed_back) {   // gates, N half 0 -> [320,448): queued behind L34, the last reader of a2
-                    mma3_ss(tmem + XC_RG, s.h[0], s.h[1], s.w + XW_WHH_HI, s.w + XW_WHH_LO, 256, 128, 4);
-                    umma_commit(&s.bar[1]);
+                    mma3_ss<256, 128, 4>(tmem + XC_RG, s.h[0], s.h[1], s.w + XW_WHH_HI, s.w + XW_WHH_LO, leader);
+                    umma_commit(&s.bar[1], leader);
                 }
             }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;

@@ -30,32 +30,52 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         if (spins > (1u << 24)) __trap();
 }
 
-__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
-    ptx::tcgen05_commit(ptx::cta_group_1, reinterpret_cast<uint64_t*>(bar));
+// MMA / commit issue.  Called by ALL 32 lanes of the issuing warp (convergent code: descriptors stay in uniform
+// registers); `leader` predicates the instruction itself so that exactly one lane issues it.
+__device__ __forceinline__ void umma_commit(unsigned long long* bar, bool leader) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+                 :: "r"(addr), "r"((uint32_t)leader) : "memory");
 }
 
-// D[128 x n] (+)= A[128 x 16*kblocks] . B[n x 16*kblocks]^T, both operands 16-bit in shared memory.
-// `a`: [K/8][128][8]; `b`: [K/8][b_rows][8] (the MMA uses n consecutive rows starting at `b`).
-template <typename T>
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, const T* a, const T* b, int b_rows, int n, int kblocks,
-                                        uint32_t ab_format, bool accumulate_first) {
-    const uint32_t idesc = umma_idesc(n, ab_format);
-    for (int kb = 0; kb < kblocks; ++kb) {
-        const uint64_t ad = umma_desc(a + (size_t)kb * 2 * 128 * 8, 128 * 16, 128);
-        const uint64_t bd = umma_desc(b + (size_t)kb * 2 * b_rows * 8, b_rows * 16, 128);
-        ptx::tcgen05_mma(ptx::kind_f16, ptx::cta_group_1, d_tmem, ad, bd, idesc, accumulate_first || kb > 0);
-    }
+__device__ __forceinline__ void umma_issue_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              bool accumulate, bool leader) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate), "r"((uint32_t)leader)
+                 : "memory");
+}
+
+__device__ __forceinline__ void umma_issue_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              bool accumulate, bool leader) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate), "r"((uint32_t)leader)
+                 : "memory");
+}
+
+// D[128 x N] (+)= A[128 x 16*KB] . B[N x 16*KB]^T, both operands 16-bit in shared memory.
+// `a`: [K/8][128][8]; `b`: [K/8][B_ROWS][8] (the MMA uses N consecutive rows starting at `b`).
+template <int B_ROWS, int N, int KB, typename T>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, const T* a, const T* b, uint32_t ab_format, bool accumulate_first,
+                                        bool leader) {
+    const uint32_t idesc = umma_idesc(N, ab_format);
+    const uint64_t ad = umma_desc(a, 128 * 16, 128), bd = umma_desc(b, B_ROWS * 16, 128);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)      // start-address field is in 16-byte units: one K block = 2 chunks of rows*16 B
+        umma_issue_ss(d_tmem, ad + (uint64_t)(kb * 2 * 128), bd + (uint64_t)(kb * 2 * B_ROWS), idesc, accumulate_first || kb > 0, leader);
 }
 
 // same with the A operand in TMEM (16-bit, 8 columns per K block)
-template <typename T>
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, const T* b, int b_rows, int n, int kblocks,
-                                        uint32_t ab_format, bool accumulate_first) {
-    const uint32_t idesc = umma_idesc(n, ab_format);
-    for (int kb = 0; kb < kblocks; ++kb) {
-        const uint64_t bd = umma_desc(b + (size_t)kb * 2 * b_rows * 8, b_rows * 16, 128);
-        ptx::tcgen05_mma_tmem_a(ptx::kind_f16, ptx::cta_group_1, d_tmem, a_tmem + kb * 8, bd, idesc, accumulate_first || kb > 0);
-    }
+template <int B_ROWS, int N, int KB, typename T>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, const T* b, uint32_t ab_format, bool accumulate_first,
+                                        bool leader) {
+    const uint32_t idesc = umma_idesc(N, ab_format);
+    const uint64_t bd = umma_desc(b, B_ROWS * 16, 128);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+        umma_issue_ts(d_tmem, a_tmem + kb * 8, bd + (uint64_t)(kb * 2 * B_ROWS), idesc, accumulate_first || kb > 0, leader);
 }
 
 // TMEM load / store of NCOLS consecutive 32-bit columns of the calling thread's lane (32x32b shape),
