@@ -1,0 +1,65 @@
+#!/usr/bin/env python
+"""Secondary benchmark: the GAN TRAINING step (train(), reference train.py:439-560) on the toy set scaled
+up (BASELINE.json configs[3]: 65 536 trajectories, n_per_batch = n_conditions so scenes keep 6 agents,
+SURVEY.md D6), obs 2 / pred 2, use_social=True, unroll 1.  Reports agents/s of one epoch per batch size,
+next to the CPU oracle port on a bounded sample.  Not the driver's contract (that is bench.py)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def toy(n):
+    from socialways_b200.toy import create_samples, pack_scenes
+    np.random.seed(30)
+    samples, ts = create_samples(n, 6, 3, n_per_batch=6)
+    o, p, t, b = pack_scenes(samples, ts)
+    return dict(obsvs=o, preds=p, times=t, batches=b)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=65536 // 6 * 6)
+    ap.add_argument("--batch-sizes", default="256,4096,49152")
+    ap.add_argument("--epochs", type=int, default=2)
+    ap.add_argument("--cpu-n", type=int, default=216)
+    args = ap.parse_args()
+    from socialways_b200.trainer import SocialWaysTrainer
+    data = toy(args.n)
+    out = {"metric": "train_agents_per_sec", "n_trajectories": args.n, "results": []}
+    for bs in [int(x) for x in args.batch_sizes.split(",")]:
+        tr = SocialWaysTrainer(data, batch_size=bs, use_social=True, n_unrolling_steps=1)
+        np.random.seed(0)
+        torch.manual_seed(0)
+        tr.train(verbose=False)                       # warm-up epoch
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.epochs):
+            ade, fde = tr.train(verbose=False)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.epochs
+        iters = len(tr.loss_log) // (args.epochs + 1)
+        out["results"].append({"batch_size": bs, "epoch_s": dt, "agents_per_s": tr.n_train_samples / dt,
+                               "iterations_per_epoch": iters, "ms_per_iteration": 1e3 * dt / iters,
+                               "train_ade": ade, "train_fde": fde})
+    # CPU oracle port of the same loop on a bounded sample
+    from oracle import socialways_oracle as so
+    torch.set_num_threads(os.cpu_count() or 1)
+    cpu = so.OracleTrainer(so.init_weights(n_next=2), toy(args.cpu_n), batch_size=64, use_social=True, pool="loop")
+    t0 = time.perf_counter()
+    cpu.train_epoch()
+    dt = time.perf_counter() - t0
+    out["cpu_baseline"] = {"agents_per_s": cpu.n_train / dt, "cores": torch.get_num_threads(), "kind": "port",
+                           "sample": f"toy {args.cpu_n}/6, batch 64, one epoch ({dt:.2f} s)"}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
