@@ -241,6 +241,8 @@ class Generator(nn.Module):
         self.attention = AttentionPooling(hidden_size, social_feature_size)                     # :372
         self.decoder = DecoderFC(hidden_size + social_feature_size + self.noise_len)            # :375
         self.use_social = use_social                                                            # :83 default False
+        # decode kernel of the no-grad path: "fp16x2" (tensor cores, fp32-faithful), "fp32" (FFMA) or "bf16" (fast)
+        self.inference_precision = "fp16x2"
         self._pack_cache = None
         self._scene_cache = {}
 
@@ -278,13 +280,14 @@ class Generator(nn.Module):
         return self._scene_cache[key]
 
     @torch.no_grad()
-    def predict_k(self, obsv_p, noise, n_next, sub_batches=(), out=None, precision="fp32"):
+    def predict_k(self, obsv_p, noise, n_next, sub_batches=(), out=None, precision=None):
         """K-sample predict(): noise [K,N,32] -> [K,N,n_next,4].  The observation encoding and the
         pooled social vector do not depend on the sample and are computed once.
         precision: "fp32" = FFMA decode kernel; "fp16x2" = tcgen05 kernel on fp16 hi/lo split operands
         (fp32-faithful, ~1e-6); "bf16" = tcgen05 kernel on bf16 operands (fast mode, ~2e-3)."""
         if not obsv_p.is_cuda:
             raise SocialWaysCudaError("predict() runs on CUDA tensors only (no CPU fallback)")
+        precision = precision or self.inference_precision
         pk = self.packs()
         n = obsv_p.shape[0]
         enc = ops.lstm_seq(pk["enc"], obsv_p, want_x_last=True)

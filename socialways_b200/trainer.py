@@ -82,6 +82,10 @@ class SocialWaysTrainer:
         self.D.load_state_dict({k[2:]: as_t(v) for k, v in weights.items() if k.startswith("D.")})
 
     def predict(self, obsv_p, noise, n_next, sub_batches=()):
+        """predict() inside train(): the no-grad passes use the same FFMA decode kernel as the autograd pass,
+        so the fake samples D sees and the ones G is trained on come from one arithmetic."""
+        if not torch.is_grad_enabled():
+            return self.generator.predict_k(obsv_p, noise.unsqueeze(0), n_next, sub_batches, precision="fp32")[0]
         return self.generator.predict(obsv_p, noise, n_next, sub_batches)
 
     # ------------------------------------------------------------------ train.py:439-560

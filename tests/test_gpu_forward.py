@@ -14,6 +14,14 @@ from golden_data import synthetic_scenes
 pytestmark = pytest.mark.gpu
 
 ATOL = 2e-5
+PRECISION = "fp32"      # set per test by the `precision` fixture: every test runs on both fp32-faithful decode kernels
+
+
+@pytest.fixture(autouse=True, params=["fp32", "fp16x2"])
+def precision(request):
+    global PRECISION
+    PRECISION = request.param
+    yield request.param
 
 
 def _generator(P, use_social=True):
@@ -21,6 +29,7 @@ def _generator(P, use_social=True):
     g = sw.Generator(use_social=use_social)
     sd = {k: v for k, v in P.items() if not k.startswith("D.")}
     g.load_state_dict(sd, strict=True)
+    g.inference_precision = PRECISION
     return g.cuda().requires_grad_(False)      # inference path; the autograd path has its own tests
 
 
