@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--batch-sizes", default="256,4096,49152")
     ap.add_argument("--epochs", type=int, default=2)
     ap.add_argument("--cpu-n", type=int, default=216)
+    ap.add_argument("--graph", action="store_true", help="also time train_graphed() (CUDA-graph replay per batch shape)")
     args = ap.parse_args()
     from socialways_b200.trainer import SocialWaysTrainer
     data = toy(args.n)
@@ -46,9 +47,27 @@ def main():
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / args.epochs
         iters = len(tr.loss_log) // (args.epochs + 1)
-        out["results"].append({"batch_size": bs, "epoch_s": dt, "agents_per_s": tr.n_train_samples / dt,
-                               "iterations_per_epoch": iters, "ms_per_iteration": 1e3 * dt / iters,
-                               "train_ade": ade, "train_fde": fde})
+        rec = {"batch_size": bs, "epoch_s": dt, "agents_per_s": tr.n_train_samples / dt,
+               "iterations_per_epoch": iters, "ms_per_iteration": 1e3 * dt / iters, "train_ade": ade, "train_fde": fde}
+        if args.graph:
+            try:
+                tg = SocialWaysTrainer(data, batch_size=bs, use_social=True, n_unrolling_steps=1, cuda_graph=True)
+                np.random.seed(0)
+                torch.manual_seed(0)
+                tg.train_graphed(verbose=False)           # eager pass + capture
+                tg.train_graphed(verbose=False)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(args.epochs):
+                    gade, gfde = tg.train_graphed(verbose=False)
+                torch.cuda.synchronize()
+                gdt = (time.perf_counter() - t0) / args.epochs
+                rec["cuda_graph"] = {"epoch_s": gdt, "agents_per_s": tg.n_train_samples / gdt,
+                                     "ms_per_iteration": 1e3 * gdt / iters, "train_ade": gade, "train_fde": gfde,
+                                     "graphs": len(tg._graphs)}
+            except Exception as e:                        # report, do not hide
+                rec["cuda_graph"] = {"error": repr(e)[:300]}
+        out["results"].append(rec)
     # CPU oracle port of the same loop on a bounded sample
     from oracle import socialways_oracle as so
     torch.set_num_threads(os.cpu_count() or 1)

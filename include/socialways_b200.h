@@ -128,6 +128,22 @@ int sw_decode_fwd_tcx(const void* tcx_w16, const void* tcx_wsz16, const float* t
                       int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 int sw_decode_tcx_pack_sizes(int* n_w16, int* n_wsz16, int* n_f32);
 
+/* Discriminator FC heads (train.py:281-292, 300-309), one thread per trajectory, all 8 Linear layers fused.
+ *   pack: sw_disc_heads_pack_floats(P, L) floats = Wo1[32][64] bo1 Wo2[32][32] bo2 Wp1[32][P] bp1 Wp2[32][32] bp2
+ *         Wc1[32][64] bc1 Wc2[1][32] bc2 Wl1[32][64] bl1 Wl2[L][32] bl2 (torch [out][in] layouts), P = n_next*4, L = 2
+ *   h [N][64] last hidden state of the observation LSTM, pred [N][P]; label [N] and code [N][L] out
+ *   xrec [N][257+P] out (or NULL): per-row record [h|o1|pred|p1|both|c1|l1|1] for the backward pass
+ * Backward: d_label [N], d_code [N][L] in (NULL = 0); d_h [N][64], d_pred [N][P] out (NULL = skip);
+ *   grec [N][193+L] out = [d_o1|d_oc|d_p1|d_pc|d_c1|d_label|d_l1|d_code]; every parameter gradient is a block of
+ *   the plain GEMM xrec^T . grec (sw_disc_heads_record_dims gives the two widths). */
+int sw_disc_heads_pack_floats(int pred_dim, int n_latent);
+int sw_disc_heads_record_dims(int pred_dim, int n_latent, int* x_dim, int* g_dim);
+int sw_disc_heads_fwd(const float* pack, const float* h, const float* pred, int pred_dim, int n_latent,
+                      int n_rows, float* label, float* code, float* xrec, void* stream);
+int sw_disc_heads_bwd(const float* pack, const float* xrec, int pred_dim, int n_latent, int n_rows,
+                      const float* d_label, const float* d_code, float* d_h, float* d_pred, float* grec,
+                      void* stream);
+
 /* Best-of-K error metrics.  Replaces train.py:587 and :602-607 of test().
  *   pred [K][N][T][4], gt [N][T][2] (normalised), ss = Scale.sx (train.py:121)
  *   out [N][4] = (avg-K ADE, avg-K FDE, min-K ADE, min-K FDE) per agent */

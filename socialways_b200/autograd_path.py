@@ -107,6 +107,37 @@ class DecodeFn(torch.autograd.Function):
         return d_enc, d_dec, g["dh0"], g["dc0"], d_pooled, None, None, None
 
 
+class DiscHeadsFn(torch.autograd.Function):
+    """(heads pack, h [N,64], pred [N,P]) -> (label [N,1], code [N,L]): the four FC blocks of the Discriminator
+    (train.py:281-292,300-309) in one forward and one backward launch; every parameter gradient is a block of
+    ONE GEMM  X^T . G  over the per-row records the kernels write."""
+
+    @staticmethod
+    def forward(ctx, pack, h, pred, n_latent):
+        label, code, xrec = ops.disc_heads_fwd(pack, h, pred, n_latent, record=True)
+        ctx.save_for_backward(pack, xrec)
+        ctx.p, ctx.n_latent = pred.shape[1], n_latent
+        ctx.need = (h.requires_grad, pred.requires_grad)
+        return label, code
+
+    @staticmethod
+    def backward(ctx, d_label, d_code):
+        pack, xrec = ctx.saved_tensors
+        p, L = ctx.p, ctx.n_latent
+        d_h, d_pred, g = ops.disc_heads_bwd(pack, xrec, p, d_label.contiguous(), d_code.contiguous(), L,
+                                            want_dh=ctx.need[0], want_dpred=ctx.need[1])
+        m = xrec.t() @ g                                     # [257 + P, 193 + L]
+        one = 256 + p
+        blocks = [(0, 64, 0, 32), (64, 96, 32, 64), (96, 96 + p, 64, 96), (96 + p, 128 + p, 96, 128),
+                  (128 + p, 192 + p, 128, 160), (192 + p, 224 + p, 160, 161), (128 + p, 192 + p, 161, 193),
+                  (224 + p, 256 + p, 193, 193 + L)]
+        parts = []
+        for r0, r1, c0, c1 in blocks:
+            parts.append(m[r0:r1, c0:c1].t().reshape(-1))   # dW [out][in]
+            parts.append(m[one, c0:c1])                      # db
+        return torch.cat(parts), d_h, d_pred, None
+
+
 def predict_with_grad(gen, obsv_p, noise, n_next, sub_batches=()):
     """predict() (train.py:392-432) with autograd: same three kernels as inference plus their stashes."""
     from . import packing

@@ -182,7 +182,7 @@ extern "C" int sw_decode_bwd(const float* lstm_pack_t, const float* dec_pack_t, 
     const long long tiles = (n_rows + SW_ROWS - 1) / SW_ROWS;
     if (tiles > 0x7fffffffLL) return SW_ERR_UNSUPPORTED;
     const int smem = (int)sizeof(sw::DecodeBwdSmem);
-    SW_CUDA_TRY(cudaFuncSetAttribute(sw::decode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SW_SET_MAX_SMEM(sw::decode_bwd_kernel, smem);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     sw::decode_bwd_kernel<<<grid, SW_THREADS, smem, (cudaStream_t)stream>>>(
         lstm_pack_t, dec_pack_t, c0, stash_gates, stash_a1, stash_a2, d_out, g_gates, g_a1, g_a2, g_v, dh0, dc0, n_agents,

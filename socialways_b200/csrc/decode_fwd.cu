@@ -191,7 +191,8 @@ extern "C" int sw_decode_fwd(const float* lstm_pack, const float* dec_pack, cons
     if (stash && (!stash_a1 || !stash_a2 || (n_next > 1 && !stash_gates))) return SW_ERR_ARG;
     const int smem = (int)sizeof(sw::DecodeSmem);
     auto kern = stash ? sw::decode_fwd_kernel<true> : sw::decode_fwd_kernel<false>;
-    SW_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SW_SET_MAX_SMEM(sw::decode_fwd_kernel<true>, smem);     // one static cache per call site: set both instantiations
+    SW_SET_MAX_SMEM(sw::decode_fwd_kernel<false>, smem);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     kern<<<grid, SW_THREADS, smem, (cudaStream_t)stream>>>(lstm_pack, dec_pack, h0, c0, pooled, noise, x_last, out, stash_xh,
                                                            stash_gates, stash_a1, stash_a2, n_agents, n_rows, n_next,

@@ -274,7 +274,7 @@ extern "C" int sw_decode_fwd_tc(const void* tc_w16, const float* tc_f32, const f
     const long long tiles = (n_rows + sw::TC_ROWS - 1) / sw::TC_ROWS;
     if (tiles > 0x7fffffffLL) return SW_ERR_UNSUPPORTED;
     const int smem = (int)sizeof(sw::TcSmem) + 128;
-    SW_CUDA_TRY(cudaFuncSetAttribute(sw::decode_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SW_SET_MAX_SMEM(sw::decode_fwd_tc_kernel, smem);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     sw::decode_fwd_tc_kernel<<<grid, sw::TC_THREADS, smem, (cudaStream_t)stream>>>(
         (const __nv_bfloat16*)tc_w16, tc_f32, h0, c0, pooled, noise, x_last, out, n_agents, n_rows, n_next, (int)tiles);

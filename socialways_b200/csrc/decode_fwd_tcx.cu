@@ -332,7 +332,7 @@ extern "C" int sw_decode_fwd_tcx(const void* tcx_w16, const void* tcx_wsz16, con
     const long long tiles = (n_rows + sw::X_ROWS - 1) / sw::X_ROWS;
     if (tiles > 0x7fffffffLL) return SW_ERR_UNSUPPORTED;
     const int smem = (int)sizeof(sw::TcxSmem);
-    SW_CUDA_TRY(cudaFuncSetAttribute(sw::decode_fwd_tcx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SW_SET_MAX_SMEM(sw::decode_fwd_tcx_kernel, smem);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     sw::decode_fwd_tcx_kernel<<<grid, sw::X_THREADS, smem, (cudaStream_t)stream>>>(
         (const __half*)tcx_w16, (const __half*)tcx_wsz16, tcx_f32, h0, c0, pooled, noise, x_last, out, n_agents, n_rows,

@@ -102,7 +102,7 @@ extern "C" int sw_lstm_seq_bwd(const float* lstm_pack_t, const float* stash_gate
     if (n_rows <= 0 || n_steps <= 0 || sm_count <= 0) return SW_ERR_ARG;
     const int tiles = (n_rows + SW_ROWS - 1) / SW_ROWS;
     const int smem = (int)sizeof(sw::SeqBwdSmem);
-    SW_CUDA_TRY(cudaFuncSetAttribute(sw::lstm_seq_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SW_SET_MAX_SMEM(sw::lstm_seq_bwd_kernel, smem);
     const int grid = tiles < 2 * sm_count ? tiles : 2 * sm_count;
     sw::lstm_seq_bwd_kernel<<<grid, SW_THREADS, smem, (cudaStream_t)stream>>>(lstm_pack_t, stash_gates, dh_last, dc_last,
                                                                               g_gates, dx, n_rows, n_steps, tiles);

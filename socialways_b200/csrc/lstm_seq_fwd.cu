@@ -119,7 +119,8 @@ extern "C" int sw_lstm_seq_fwd(const float* lstm_pack, const float* x, int in_di
     const int tiles = (n_rows + SW_ROWS - 1) / SW_ROWS;
     const int smem = (int)sizeof(sw::SeqSmem);
     auto kern = stash ? sw::lstm_seq_fwd_kernel<true> : sw::lstm_seq_fwd_kernel<false>;
-    SW_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    SW_SET_MAX_SMEM(sw::lstm_seq_fwd_kernel<true>, smem);     // one static cache per call site: set both instantiations
+    SW_SET_MAX_SMEM(sw::lstm_seq_fwd_kernel<false>, smem);
     // two CTAs fit per SM (104 KB each): let short grids spread over more SMs' worth of slots
     const int grid = tiles < 2 * sm_count ? tiles : 2 * sm_count;
     kern<<<grid, SW_THREADS, smem, (cudaStream_t)stream>>>(lstm_pack, x, in_dim, n_rows, n_steps, h_in, c_in, y_out, h_out, c_out, x_last,

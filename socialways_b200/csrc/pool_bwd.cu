@@ -187,8 +187,8 @@ extern "C" int sw_pool_bwd(const float* pool_pack, const float* x_last, const fl
     cudaStream_t st = (cudaStream_t)stream;
 #define SW_POOLB_LAUNCH(GG)                                                                                          \
     do {                                                                                                             \
-        SW_CUDA_TRY(cudaFuncSetAttribute(sw::pool_bwd_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                         (int)smem));                                                                \
+        SW_SET_MAX_SMEM(sw::pool_bwd_kernel<GG>, \
+                                         (int)smem);                                                                \
         sw::pool_bwd_kernel<GG><<<grid, SW_THREADS, smem, st>>>(pool_pack, x_last, h, ub, dS, tdot, attn,             \
                                                                  scene_offsets, agent_scene, pair_offsets, dub,      \
                                                                  dh_direct, st_a1, st_g2, st_g1, st_f, n_agents,     \

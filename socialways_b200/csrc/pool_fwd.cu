@@ -167,8 +167,8 @@ extern "C" int sw_pool_fwd(const float* pool_pack, const float* x_last, const fl
     cudaStream_t st = (cudaStream_t)stream;
 #define SW_POOL_LAUNCH(GG)                                                                                         \
     do {                                                                                                           \
-        SW_CUDA_TRY(cudaFuncSetAttribute(sw::pool_fwd_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                         (int)smem));                                                              \
+        SW_SET_MAX_SMEM(sw::pool_fwd_kernel<GG>, \
+                                         (int)smem);                                                              \
         sw::pool_fwd_kernel<GG><<<grid, SW_THREADS, smem, st>>>(pool_pack, x_last, h, ub, scene_offsets,            \
                                                                  agent_scene, pooled, attn, n_agents, a_cap, span_cap); \
     } while (0)

@@ -34,6 +34,19 @@
 
 void sw_set_last_cuda_error(int e);
 
+// Raise a kernel's dynamic shared-memory limit, once per call site and size (a function attribute, not a stream
+// operation; doing it only when the requested size grows keeps steady-state launches free of driver calls, which
+// also makes them capturable into CUDA graphs).
+#define SW_SET_MAX_SMEM(kernel, bytes)                                                                       \
+    do {                                                                                                     \
+        static int _sw_smem_set = -1;                                                                        \
+        const int _sw_want = (int)(bytes);                                                                   \
+        if (_sw_want > _sw_smem_set) {                                                                       \
+            SW_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, _sw_want)); \
+            _sw_smem_set = _sw_want;                                                                         \
+        }                                                                                                    \
+    } while (0)
+
 namespace sw {
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return __fdividef(1.0f, 1.0f + expf(-x)); }

@@ -218,6 +218,34 @@ def decode_bwd(lstm_pack_t, dec_pack_t, c0, stash, d_out, n_agents, n_samples):
     return dict(gates=g_gates[:t - 1], a1=g_a1, a2=g_a2, v=g_v, dh0=dh0, dc0=dc0)
 
 
+def disc_heads_fwd(pack, h, pred, n_latent=2, record=False):
+    """sw_disc_heads_fwd: h [N,64], pred [N,P] -> label [N,1], code [N,n_latent] (+ the activation record)."""
+    h, pred = _f32(h), _f32(pred)
+    n, p = pred.shape
+    dev = h.device
+    label = torch.empty(n, 1, device=dev)
+    code = torch.empty(n, n_latent, device=dev)
+    xrec = torch.empty(n, 257 + p, device=dev) if record else None
+    rc = _lib.lib().sw_disc_heads_fwd(_lib.ptr(_f32(pack)), _lib.ptr(h), _lib.ptr(pred), p, n_latent, n, _lib.ptr(label),
+                                      _lib.ptr(code), _lib.ptr(xrec), _stream())
+    _lib.check(rc, "sw_disc_heads_fwd")
+    return label, code, xrec
+
+
+def disc_heads_bwd(pack, xrec, pred_dim, d_label, d_code, n_latent=2, want_dh=True, want_dpred=True):
+    """sw_disc_heads_bwd -> (d_h [N,64] | None, d_pred [N,P] | None, gradient record G [N, 193 + n_latent])."""
+    n, dev = xrec.shape[0], xrec.device
+    d_h = torch.empty(n, H, device=dev) if want_dh else None
+    d_pred = torch.empty(n, pred_dim, device=dev) if want_dpred else None
+    grec = torch.empty(n, 193 + n_latent, device=dev)
+    rc = _lib.lib().sw_disc_heads_bwd(_lib.ptr(_f32(pack)), _lib.ptr(xrec), pred_dim, n_latent, n,
+                                      _lib.ptr(None if d_label is None else _f32(d_label)),
+                                      _lib.ptr(None if d_code is None else _f32(d_code)), _lib.ptr(d_h), _lib.ptr(d_pred),
+                                      _lib.ptr(grec), _stream())
+    _lib.check(rc, "sw_disc_heads_bwd")
+    return d_h, d_pred, grec
+
+
 def bestofk_metrics(pred, gt, ss):
     """sw_bestofk_metrics.  pred [K,N,T,4], gt [N,T,2] -> [N,4] (avg ADE, avg FDE, min ADE, min FDE)."""
     pred, gt = _f32(pred), _f32(gt)

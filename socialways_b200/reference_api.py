@@ -178,8 +178,8 @@ class DecoderLstm(nn.Module):
 
 
 class Discriminator(nn.Module):
-    """train.py:272-316.  The observation LSTM runs in sw_lstm_seq_fwd / sw_lstm_seq_bwd; the four
-    small FC heads (64->32->32, 48->32->32, 64->32->1, 64->32->2) are library GEMMs in this round."""
+    """train.py:272-316.  The observation LSTM runs in sw_lstm_seq_fwd / sw_lstm_seq_bwd, the four FC heads
+    (64->32->32, n_next*4->32->32, 64->32->1, 64->32->2) in sw_disc_heads_fwd / sw_disc_heads_bwd."""
 
     def __init__(self, n_next, hidden_dim, n_latent_code):
         super().__init__()
@@ -210,11 +210,23 @@ class Discriminator(nn.Module):
         with torch.no_grad():
             return ops.lstm_seq(self.packed_lstm(), obsv)["h"]
 
+    def packed_heads(self):
+        """Flat parameter pack of the 8 Linear layers, torch [out][in] layouts (csrc/disc_heads.cu)."""
+        mods = (self.obsv_encoder_fc[0], self.obsv_encoder_fc[2], self.pred_encoder[0], self.pred_encoder[2],
+                self.classifier[0], self.classifier[2], self.latent_decoder[0], self.latent_decoder[2])
+        return torch.cat([t.reshape(-1) for m in mods for t in (m.weight, m.bias)])
+
     def heads(self, obsv_h, pred):
-        obsv_code = self.obsv_encoder_fc(obsv_h)
-        pred_code = self.pred_encoder(pred.reshape(-1, self.n_next * 4))
-        both_codes = torch.cat([obsv_code, pred_code], dim=1)
-        return self.classifier(both_codes), self.latent_decoder(both_codes)
+        """FC heads (train.py:301-309) in the fused kernels; label [N,1], code_hat [N,n_latent]."""
+        pred2 = pred.reshape(-1, self.n_next * 4)
+        n_latent = self.latent_decoder[2].out_features
+        if torch.is_grad_enabled() and (pred2.requires_grad or obsv_h.requires_grad or
+                                        any(p.requires_grad for p in self.parameters())):
+            from .autograd_path import DiscHeadsFn
+            return DiscHeadsFn.apply(self.packed_heads(), obsv_h.contiguous(), pred2.contiguous(), n_latent)
+        with torch.no_grad():
+            label, code, _ = ops.disc_heads_fwd(self.packed_heads(), obsv_h, pred2, n_latent)
+        return label, code
 
     def forward(self, obsv, pred):
         return self.heads(self.encode_obsv(obsv), pred)

@@ -26,7 +26,7 @@ from .scale import Scale
 class SocialWaysTrainer:
     def __init__(self, data, batch_size=256, hidden_size=64, use_social=False, n_unrolling_steps=1,
                  lr_g=1e-4, lr_d=1e-3, device="cuda", weights=None, n_latent_codes=2,
-                 use_info_loss=True, loss_info_w=0.5, world=None):
+                 use_info_loss=True, loss_info_w=0.5, world=None, cuda_graph=False):
         self.device = torch.device(device)
         self.batch_size, self.n_unrolling_steps = batch_size, n_unrolling_steps
         self.use_info_loss, self.loss_info_w, self.n_latent_codes = use_info_loss, loss_info_w, n_latent_codes
@@ -62,8 +62,11 @@ class SocialWaysTrainer:
         self.generator.to(self.device)
         self.D.to(self.device)
         self.noise_len = hidden_size // 2
-        self.predictor_optimizer = opt.Adam(self.generator.optimizer_parameters(), lr=lr_g, betas=(0.9, 0.999))
-        self.D_optimizer = opt.Adam(self.D.parameters(), lr=lr_d, betas=(0.9, 0.999))
+        self.cuda_graph = cuda_graph
+        self._graphs = {}
+        extra = dict(capturable=True) if cuda_graph else {}
+        self.predictor_optimizer = opt.Adam(self.generator.optimizer_parameters(), lr=lr_g, betas=(0.9, 0.999), **extra)
+        self.D_optimizer = opt.Adam(self.D.parameters(), lr=lr_d, betas=(0.9, 0.999), **extra)
         self.mse_loss = nn.MSELoss()
         self.world_size, self.rank = swdist.world() if world is None else world
         self.epoch = 1
@@ -177,6 +180,112 @@ class SocialWaysTrainer:
         train_FDE /= self.n_train_samples
         toc = time.perf_counter()
         if verbose and self.rank == 0:
+            print(" Epc=%4d, Train ADE,FDE = (%.3f, %.3f) | time = %.1f" % (self.epoch, train_ADE, train_FDE, toc - tic))
+        return train_ADE, train_FDE
+
+    # ------------------------------------------------------------------ CUDA-graph variant of train()
+    def _graph_body(self, st):
+        """One iteration of train() (train.py:470-551) on static tensors, free of host synchronisation so that it
+        can be captured into a CUDA graph: no .item(), no host RNG, in-place D backup/rollback instead of
+        copy.deepcopy / .data rebinding (same values)."""
+        D, mse_loss, nl = self.D, self.mse_loss, self.n_latent_codes
+        obsv, pred, noise, zeros, ones, scenes = st["obsv"], st["pred"], st["noise"], st["zeros"], st["ones"], st["scenes"]
+        obsv_4d, pred_4d = get_traj_4d(obsv, pred)
+        lin = [p for m in D.modules() if isinstance(m, nn.Linear) for p in (m.weight, m.bias)]
+        for u in range(self.n_unrolling_steps + 1):
+            D.zero_grad(set_to_none=True)
+            with torch.no_grad():
+                pred_hat_4d = self.predict(obsv, noise, self.n_next, scenes)
+            obsv_h = D.encode_obsv(obsv_4d)
+            fake_labels, code_hat = D.heads(obsv_h, pred_hat_4d)
+            d_fake = mse_loss(fake_labels, zeros)
+            d_info = mse_loss(code_hat, noise[:, :nl])
+            real_labels, _ = D.heads(obsv_h, pred_4d)
+            d_real = mse_loss(real_labels, ones)
+            d_loss = d_fake + d_real + (self.loss_info_w * d_info if self.use_info_loss else 0.0)
+            d_loss.backward()
+            self.D_optimizer.step()
+            if u == 0 and self.n_unrolling_steps > 0:
+                with torch.no_grad():
+                    for b, p in zip(st["backup"], lin):
+                        b.copy_(p)
+        D.zero_grad(set_to_none=True)
+        self.predictor_optimizer.zero_grad(set_to_none=True)
+        pred_hat_4d = self.predict(obsv, noise, self.n_next, scenes)
+        with torch.no_grad():
+            obsv_h = D.encode_obsv(obsv_4d)
+        gen_labels, code_hat = D.heads(obsv_h, pred_hat_4d)
+        g_fool = mse_loss(gen_labels, ones)
+        g_info = mse_loss(code_hat, noise[:, :nl])
+        g_loss = g_fool + (self.loss_info_w * g_info if self.use_info_loss else 0.0)
+        g_loss.backward()
+        self.predictor_optimizer.step()
+        with torch.no_grad():
+            if self.n_unrolling_steps > 0:                                   # D.load(backup): Linear layers only
+                for b, p in zip(st["backup"], lin):
+                    p.copy_(b)
+            err_all = torch.pow((pred_hat_4d[:, :, :2] - pred) / self.ss, 2).sum(dim=2).sqrt()
+            st["stats"].copy_(torch.stack([err_all.sum() / self.n_next, err_all[:, -1].sum(), d_loss.detach(), d_fake.detach(),
+                                           d_real.detach(), d_info.detach(), g_fool.detach(), g_info.detach()]))
+
+    def train_graphed(self, verbose=True):
+        """train() with every mini-batch shape captured once into a CUDA graph and replayed (removes the
+        ~10 ms/iteration of Python + launch overhead that bounds small batches).  Needs optimisers built with
+        capturable=True (constructor flag cuda_graph=True) and world_size 1.  The first occurrence of a batch
+        shape runs eagerly (it also warms up the lazily-initialised optimiser state), the second is captured."""
+        if not self.cuda_graph or self.world_size != 1:
+            raise RuntimeError("construct the trainer with cuda_graph=True (single process) to use train_graphed()")
+        tic = time.perf_counter()
+        dev = self.device
+        stats_acc = torch.zeros(8, device=dev, dtype=torch.float64)
+        n_iter = 0
+        group, count = [], 0
+        for ii, batch_i in enumerate(self.train_batches):
+            count += int(batch_i[1] - batch_i[0])
+            group.append(batch_i)
+            if not (ii >= self.train_size - 1 or
+                    count + (self.the_batches[ii + 1][1] - self.the_batches[ii + 1][0]) > self.batch_size):
+                continue
+            lo, hi = int(group[0][0]), int(group[-1][1])
+            sub = np.asarray(group) - lo
+            key = (hi - lo, sub.tobytes())
+            ent = self._graphs.get(key)
+            if ent is None:
+                bs = hi - lo
+                lin_n = [p for m in self.D.modules() if isinstance(m, nn.Linear) for p in (m.weight, m.bias)]
+                st = dict(obsv=torch.empty(bs, self.n_past, 2, device=dev), pred=torch.empty(bs, self.n_next, 2, device=dev),
+                          noise=torch.empty(bs, self.noise_len, device=dev), zeros=torch.empty(bs, 1, device=dev),
+                          ones=torch.empty(bs, 1, device=dev), stats=torch.zeros(8, device=dev),
+                          backup=[torch.empty_like(p) for p in lin_n],
+                          scenes=self.generator.scene_index(sub, bs, dev))
+                _ = st["scenes"].pair_offsets                                 # build every lazy device index up front
+                ent = self._graphs[key] = dict(st=st, graph=None, seen=0)
+            st = ent["st"]
+            st["obsv"].copy_(self.dataset_obsv[lo:hi])
+            st["pred"].copy_(self.dataset_pred[lo:hi])
+            st["zeros"].fill_(float(np.random.uniform(0, 0.1)))               # train.py:471
+            st["ones"].fill_(float(np.random.uniform(0.9, 1.0)))              # train.py:472
+            st["noise"].copy_(torch.rand(hi - lo, self.noise_len))            # train.py:473 (CPU RNG)
+            if ent["graph"] is None and ent["seen"] >= 1:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._graph_body(st)
+                ent["graph"] = g
+            if ent["graph"] is not None:
+                ent["graph"].replay()
+            else:
+                self._graph_body(st)
+            ent["seen"] += 1
+            stats_acc += st["stats"]
+            n_iter += 1
+            group, count = [], 0
+        vals = stats_acc.tolist()
+        train_ADE, train_FDE = vals[0] / self.n_train_samples, vals[1] / self.n_train_samples
+        self.last_epoch_mean_losses = dict(zip(("d_loss", "d_fake", "d_real", "d_info", "g_fool", "g_info"),
+                                               [v / max(1, n_iter) for v in vals[2:]]))
+        toc = time.perf_counter()
+        if verbose:
             print(" Epc=%4d, Train ADE,FDE = (%.3f, %.3f) | time = %.1f" % (self.epoch, train_ADE, train_FDE, toc - tic))
         return train_ADE, train_FDE
 

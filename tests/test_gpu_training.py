@@ -172,3 +172,25 @@ def test_sharded_training_matches_single_gpu():
                         "--master-addr", "127.0.0.1", "--master-port", "29517",
                         os.path.join(here, "multigpu_train_check.py")], capture_output=True, text=True, timeout=600)
     assert "MULTIGPU_TRAIN_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_cuda_graph_training_matches_eager():
+    """train_graphed(): capture + replay of the whole GAN iteration vs the eager train() from the same seeds.
+    (capturable Adam computes its bias corrections on the device: weights agree to fp32 rounding, not bit for bit.)"""
+    from oracle import socialways_oracle as so
+    from socialways_b200.trainer import SocialWaysTrainer
+    data = so.toy_samples(216, 6)
+    W = so.init_weights(seed=9, n_next=2)
+    runs = {}
+    for graph in (False, True):
+        tr = SocialWaysTrainer(data, batch_size=64, use_social=True, n_unrolling_steps=1, weights=W, cuda_graph=graph)
+        np.random.seed(3)
+        torch.manual_seed(3)
+        res = [(tr.train_graphed if graph else tr.train)(verbose=False) for _ in range(3)]
+        runs[graph] = (res, tr.reference_weights())
+        if graph:
+            assert any(e["graph"] is not None for e in tr._graphs.values()), "no batch shape was captured"
+    for (a0, f0), (a1, f1) in zip(runs[False][0], runs[True][0]):
+        assert abs(a0 - a1) < 1e-4 and abs(f0 - f1) < 1e-4
+    for k, v in runs[False][1].items():
+        assert (v - runs[True][1][k]).abs().max().item() < 5e-5, k

