@@ -40,6 +40,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 A_PER_SCENE, N_PAST, N_NEXT, K_SAMPLES = 8, 8, 12, 20
 FLOPS_PER_TRAJ = 1_726_848          # 12 x DecoderFC (83 360) + 11 x encoder step (66 048)
 FLOPS_PER_TRAJ_EXECUTED = 12 * 2 * (64 * 160 + 160 * 80 + 80 * 2) + 11 * 2 * 68 * 256 + 2 * 96 * 160
+# dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of each decode kernel, divided by the
+# trajectories of that launch (655 360): profiles/r1_decode_tcx.txt, r1_decode_fp32_ffma.txt, r1_decode_tc_bf16_v1.txt.
+# Algorithmic: 128 B noise in + 192 B (p, v) x 12 out = 320 B per trajectory.
+NCU_DRAM_BYTES_PER_TRAJ = {"fp16x2": (112.097024e6 + 93.687808e6) / 655360, "fp32": (114.652672e6 + 91.719424e6) / 655360,
+                           "bf16": None}
 
 
 KERNEL_OF = {"fp32": "decode_fwd_kernel", "fp16x2": "decode_fwd_tcx_kernel", "bf16": "decode_fwd_tc_kernel"}
@@ -329,7 +334,11 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"kernel": KERNEL_OF[args.precision],
                          "bound": "tensor", "achieved": ach, "peak": peak,
-                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": ach / peak,
+                         "traffic": (NCU_DRAM_BYTES_PER_TRAJ[args.precision] * traj_per_step
+                                     if NCU_DRAM_BYTES_PER_TRAJ[args.precision] else None),
+                         "traffic_note": "bytes per launch = ncu DRAM bytes per trajectory (profiles/) x trajectories of this "
+                                         "launch; algorithmic 320 B/trajectory",
                          "peak_source": f"bf16_tflops_sustained ({pk_['src']})",
                          "kernel_ms": dec_ms, "kernel_share_of_step": dec_ms / (ms / args.steps),
                          "flops_per_traj_algorithmic": FLOPS_PER_TRAJ,

@@ -195,3 +195,24 @@ def test_full_size_properties_eth_config():
     want = torch.stack([so.predict(P, obsv[lo:hi], noise[i, lo:hi], 12, data["batches"][1000:1003] - lo, True, "closed")
                         for i in (0, 7, 19)])
     np.testing.assert_allclose(out[[0, 7, 19], lo:hi].cpu().numpy(), want.numpy(), atol=ATOL, rtol=0)
+
+
+def test_config5_dense_crowd_k128():
+    """BASELINE config 5 shape: 256 agents per scene, K = 128 samples (65 536 decode rows for 2 scenes).
+    Full-size run through the public API; oracle comparison on 3 of the 128 samples; sample-independence and
+    finiteness on all of them."""
+    from oracle import socialways_oracle as so
+    P = so.init_weights(seed=8)
+    data = synthetic_scenes([256, 256], seed=17)
+    sc = so.IsoScale(data["obsvs"], data["preds"])
+    obsv = torch.from_numpy(sc.normalize(data["obsvs"]))
+    n, k = obsv.shape[0], 128
+    noise = torch.rand(k, n, 32, generator=torch.Generator().manual_seed(5))
+    noise[100] = noise[3]
+    gen = _generator(P)
+    out = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"])
+    assert out.shape == (k, n, 12, 4) and torch.isfinite(out).all()
+    assert torch.equal(out[100], out[3])
+    for i in (0, 64, 127):
+        want = so.predict(P, obsv, noise[i], 12, data["batches"], True, "closed")
+        np.testing.assert_allclose(out[i].cpu().numpy(), want.numpy(), atol=ATOL, rtol=0)

@@ -106,3 +106,28 @@ def test_tcx_fp16_split_decode_is_fp32_faithful(sizes, k):
         e = (((want[..., :2] - pred) / sc.sx) ** 2).sum(-1).sqrt()
         ref = torch.stack([e.mean(2).mean(0), e[:, :, -1].mean(0), e.mean(2).min(0)[0], e[:, :, -1].min(0)[0]], 1)
         assert (m - ref).abs().max().item() < 1e-4
+
+
+def test_config3_zara_shape_bf16_fast_mode():
+    """BASELINE config 3: ~32 agents per scene, K = 20, bf16 fast mode.  Stated tolerance of that mode (it is NOT
+    the fp32 parity mode): positions within 5e-3 (normalised) of the fp32 oracle, best-of-K ADE/FDE within 2 %."""
+    import socialways_b200 as sw
+    from socialways_b200 import ops
+    from oracle import socialways_oracle as so
+    P = so.init_weights(seed=10)
+    data = synthetic_scenes([32, 31, 33, 32], seed=19)
+    sc = so.IsoScale(data["obsvs"], data["preds"])
+    obsv = torch.from_numpy(sc.normalize(data["obsvs"]))
+    pred = torch.from_numpy(sc.normalize(data["preds"]))
+    n, k = obsv.shape[0], 20
+    noise = torch.rand(k, n, 32, generator=torch.Generator().manual_seed(6))
+    gen = sw.Generator(use_social=True)
+    gen.load_state_dict({key: v for key, v in P.items() if not key.startswith("D.")})
+    gen = gen.cuda().requires_grad_(False)
+    got = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision="bf16")
+    want = torch.stack([so.predict(P, obsv, noise[i], 12, data["batches"], True, "closed") for i in range(k)])
+    assert (got.cpu() - want).abs().max().item() < 5e-3
+    m = ops.bestofk_metrics(got, pred.cuda(), sc.sx).cpu().sum(0)
+    e = (((want[..., :2] - pred) / sc.sx) ** 2).sum(-1).sqrt()
+    ref = torch.stack([e.mean(2).mean(0), e[:, :, -1].mean(0), e.mean(2).min(0)[0], e[:, :, -1].min(0)[0]], 1).sum(0)
+    assert ((m - ref).abs() / ref).max().item() < 0.02
