@@ -11,8 +11,12 @@
 // 32*(warp%4)+lane (its TMEM lane) and column quarter warp/4.  Operand placement:
 //   weights  W1h, W2, W34, Whh as hi|lo fp16 in shared memory (163 KB), canonical K-major no-swizzle layout
 //   h        hi|lo fp16 in shared memory (32 KB), rewritten by the LSTM epilogue every step
-//   a1, a2   hi|lo fp16 written IN PLACE over their own fp32 accumulators in TMEM (tcgen05.st) and consumed
-//            as the TMEM A operand of the next layer -- they never touch shared memory
+//   a1, a2   hi|lo fp16 written IN PLACE over their own fp32 accumulators in TMEM (tcgen05.st): the 16 accumulator
+//            columns of a K block become 8 hi + 8 lo columns, written by the very thread that read them (no
+//            barrier in between), and are consumed as the TMEM A operand of the next layer -- they never touch
+//            shared memory.  (Issuing L1 / L2 as two N groups to overlap epilogue and MMA was measured SLOWER: every
+//            tcgen05.mma carries a fixed cost of the order of 60 clk, so fewer, wider MMAs win.)  The folded 80 -> 2
+//            output layer runs as fp32 FMAs inside the layer-2 epilogue (no MMA round trip for 160 MACs per row).
 //   c1       the step-invariant part of layer 1, [S ; z] . W1[S,z rows] (hoisted), computed
 //            once per tile by MMAs whose weights are streamed through a 20 KB staging buffer, and
 //            kept in 160 TMEM columns for the 12 steps
@@ -34,8 +38,8 @@ constexpr int XW_W1H_HI = 0, XW_W1H_LO = 10240, XW_W2_HI = 20480, XW_W2_LO = 332
               XW_W34_LO = 47360, XW_WHH_HI = 48640, XW_WHH_LO = 65024, XW_TOTAL = 81408;
 // hoist weights in global memory: 3 chunks of K = 32 rows of W1[S,z]: [chunk][hi|lo][4][160][8]
 constexpr int XW_SZ_CHUNK = 2 * 4 * 160 * 8;      // 10240 halves = 20480 B
-// fp32 section: wx4[256][4] | bL[256] | b1[160] | b2[80] | b34[2] | pad
-constexpr int XF_WX4 = 0, XF_BL = 1024, XF_B1 = 1280, XF_B2 = 1440, XF_B34 = 1520, XF_TOTAL = 1536;
+// fp32 section: wx4[256][4] | bL[256] | b1[160] | b2[80] | b34[2] | pad | W34[80][2]
+constexpr int XF_WX4 = 0, XF_BL = 1024, XF_B1 = 1280, XF_B2 = 1440, XF_B34 = 1520, XF_W34 = 1536, XF_TOTAL = 1536 + 160;
 constexpr uint32_t XC_C1 = 0, XC_R1 = 160, XC_RG = 320, XC_V = 448;
 constexpr uint32_t FMT_F16 = 0;
 
@@ -45,6 +49,7 @@ struct TcxSmem {
     __half stage[XW_SZ_CHUNK];             // hoist weight chunk (20 480 B)
     float f32[XF_TOTAL];
     float x4[4 * X_ROWS];
+    float vpart[8 * X_ROWS];                // partial velocities [quarter][component][row]
     unsigned long long bar[3];
     uint32_t tmem_base;
 };
@@ -68,12 +73,54 @@ __device__ __forceinline__ void mma3_ss(uint32_t d, const __half* a_hi, const __
 }
 
 // three-pass product with the A operand (hi / lo column blocks) in TMEM
-template <int B_ROWS, int N, int KB>
+template <int B_ROWS, int N, int KB, int A_STRIDE = 8>
 __device__ __forceinline__ void mma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const __half* b_hi, const __half* b_lo,
                                         bool accumulate_first, bool leader) {
-    umma_ts<B_ROWS, N, KB>(d, a_hi, b_hi, FMT_F16, accumulate_first, leader);
-    umma_ts<B_ROWS, N, KB>(d, a_hi, b_lo, FMT_F16, true, leader);
-    umma_ts<B_ROWS, N, KB>(d, a_lo, b_hi, FMT_F16, true, leader);
+    umma_ts<B_ROWS, N, KB, A_STRIDE>(d, a_hi, b_hi, FMT_F16, accumulate_first, leader);
+    umma_ts<B_ROWS, N, KB, A_STRIDE>(d, a_hi, b_lo, FMT_F16, true, leader);
+    umma_ts<B_ROWS, N, KB, A_STRIDE>(d, a_lo, b_hi, FMT_F16, true, leader);
+}
+
+// Epilogue of a hidden layer, NKB K-blocks (16 output features each) of this thread: y = lrelu(acc [+ c1] + bias), then the
+// hi|lo fp16 pieces of each block are written IN PLACE over the 16 accumulator columns that produced them
+// (hi -> columns +0..7, lo -> +8..15), i.e. only over columns this thread itself has just read: no barrier between
+// the read and the write, and the next layer addresses K block kb at column 16*kb (hi) / 16*kb + 8 (lo).
+template <int NKB, bool WITH_C1>
+__device__ __forceinline__ void hidden_epilogue(uint32_t t_acc, uint32_t t_c1, const float* __restrict__ bias) {
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb) {
+        uint32_t acc[16], c1v[16], pc[16];
+        tmem_ld<16>(t_acc + kb * 16, acc);
+        if (WITH_C1) tmem_ld<16>(t_c1 + kb * 16, c1v);
+        ptx::tcgen05_wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float y0 = __uint_as_float(acc[2 * e]) + bias[kb * 16 + 2 * e], y1 = __uint_as_float(acc[2 * e + 1]) + bias[kb * 16 + 2 * e + 1];
+            if (WITH_C1) { y0 += __uint_as_float(c1v[2 * e]); y1 += __uint_as_float(c1v[2 * e + 1]); }
+            split2(lrelu02(y0), lrelu02(y1), pc[e], pc[8 + e]);
+        }
+        tmem_st<16>(t_acc + kb * 16, pc);
+    }
+    ptx::tcgen05_wait_st();
+}
+
+// Epilogue of layer 2 fused with the folded 80 -> 2 output layer: y = lrelu(acc + b2) stays in registers and is
+// contracted with W34 in fp32 FMAs (2 per column); the per-quarter partial velocities meet in shared memory.
+// No a2 operand, no extra MMA round trip for a 160-MAC-per-row layer.
+template <int NKB>
+__device__ __forceinline__ void output_epilogue(uint32_t t_acc, const float* __restrict__ bias, const float2* __restrict__ w34,
+                                                float& v0, float& v1) {
+    v0 = 0.0f; v1 = 0.0f;
+    uint32_t acc[NKB * 16];
+    tmem_ld<NKB * 16>(t_acc, acc);
+    ptx::tcgen05_wait_ld();
+#pragma unroll
+    for (int j = 0; j < NKB * 16; ++j) {
+        const float y = lrelu02(__uint_as_float(acc[j]) + bias[j]);
+        const float2 w = w34[j];
+        v0 = fmaf(y, w.x, v0);
+        v1 = fmaf(y, w.y, v1);
+    }
 }
 
 __global__ void __launch_bounds__(X_THREADS, 1)
@@ -107,7 +154,7 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
     ptx::tcgen05_fence_after_thread_sync();
     const uint32_t tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0);   // warp-uniform for the compiler (uniform datapath)
     const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);       // this thread's lane, column 0
-    uint32_t ph0 = 0, ph1 = 0;
+    uint32_t ph0 = 0, ph1 = 0;              // parities: bar0 (hoist, L1, L2) | bar1 / bar2 (gate halves)
     const float4* wx4 = reinterpret_cast<const float4*>(s.f32 + XF_WX4);
     const float* bL = s.f32 + XF_BL;
 
@@ -142,7 +189,7 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             c[q * 4] = t.x; c[q * 4 + 1] = t.y; c[q * 4 + 2] = t.z; c[q * 4 + 3] = t.w;
         }
         float p0 = 0.f, p1 = 0.f;
-        if (cq == 0 && valid) {
+        if (cq == 1 && valid) {
             const float2 t = __ldg(reinterpret_cast<const float2*>(x_last + (size_t)agent * 4));
             p0 = t.x; p1 = t.y;
         }
@@ -187,7 +234,7 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
 
         for (int t = 0; t < n_next; ++t) {
             const bool feed_back = t + 1 < n_next;
-            // ---------------- layer 1: h (K = 64, smem) -> 160, accumulate in R1 ----------------
+            // ---------------- layer 1: h (K = 64, smem) -> 160 in R1; column quarters own 3, 3, 2, 2 K-blocks of a1 ----------------
             if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
                 mma3_ss<160, 160, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_W1H_HI, s.w + XW_W1H_LO, leader);
@@ -196,35 +243,16 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
             {
-                uint32_t hi[20], lo[20];
-                const float* b1 = s.f32 + XF_B1 + cq * 40;
-#pragma unroll
-                for (int part = 0; part < 2; ++part) {           // two halves of 20 columns: bounds the live registers
-                    uint32_t acc[20], c1v[20];
-                    tmem_ld<20>(tl + XC_R1 + cq * 40 + part * 20, acc);
-                    tmem_ld<20>(tl + XC_C1 + cq * 40 + part * 20, c1v);
-                    ptx::tcgen05_wait_ld();
-#pragma unroll
-                    for (int e = 0; e < 10; ++e) {
-                        const int j = part * 20 + 2 * e;
-                        const float y0 = lrelu02(__uint_as_float(acc[2 * e]) + __uint_as_float(c1v[2 * e]) + b1[j]);
-                        const float y1 = lrelu02(__uint_as_float(acc[2 * e + 1]) + __uint_as_float(c1v[2 * e + 1]) + b1[j + 1]);
-                        split2(y0, y1, hi[part * 10 + e], lo[part * 10 + e]);
-                    }
-                }
-                ptx::tcgen05_fence_before_thread_sync();
-                __syncthreads();                       // every thread has read its accumulator columns
-                ptx::tcgen05_fence_after_thread_sync();
-                tmem_st<20>(tl + XC_R1 + cq * 20, hi);           // a1 hi : columns [160,240)
-                tmem_st<20>(tl + XC_R1 + 80 + cq * 20, lo);      // a1 lo : columns [240,320)
-                ptx::tcgen05_wait_st();
+                const int col0 = (cq < 2) ? cq * 48 : 96 + (cq - 2) * 32;
+                if (cq < 2) hidden_epilogue<3, true>(tl + XC_R1 + col0, tl + XC_C1 + col0, s.f32 + XF_B1 + col0);
+                else        hidden_epilogue<2, true>(tl + XC_R1 + col0, tl + XC_C1 + col0, s.f32 + XF_B1 + col0);
             }
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
-            // ---------------- layer 2: a1 (K = 160, TMEM) -> 80, accumulate in [320,400) ----------------
+            // ---------------- layer 2: a1 (K = 160, TMEM, K block kb at column 16 kb) -> 80 in [320,400) ----------------
             if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
-                mma3_ts<80, 80, 10>(tmem + XC_RG, tmem + XC_R1, tmem + XC_R1 + 80, s.w + XW_W2_HI, s.w + XW_W2_LO, false, leader);
+                mma3_ts<80, 80, 10, 16>(tmem + XC_RG, tmem + XC_R1, tmem + XC_R1 + 8, s.w + XW_W2_HI, s.w + XW_W2_LO, false, leader);
                 umma_commit(&s.bar[0], leader);
                 if (feed_back) {   // gates, N half 1 -> [160,288): runs under the L2 / L34 epilogues
                     mma3_ss<256, 128, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_WHH_HI + 128 * 8, s.w + XW_WHH_LO + 128 * 8, leader);
@@ -233,47 +261,31 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
-            {
-                uint32_t acc[20], hi[10], lo[10];
-                tmem_ld<20>(tl + XC_RG + cq * 20, acc);
-                ptx::tcgen05_wait_ld();
-                const float* b2 = s.f32 + XF_B2 + cq * 20;
-#pragma unroll
-                for (int e = 0; e < 10; ++e)
-                    split2(lrelu02(__uint_as_float(acc[2 * e]) + b2[2 * e]), lrelu02(__uint_as_float(acc[2 * e + 1]) + b2[2 * e + 1]),
-                           hi[e], lo[e]);
-                ptx::tcgen05_fence_before_thread_sync();
-                __syncthreads();
-                ptx::tcgen05_fence_after_thread_sync();
-                tmem_st<10>(tl + XC_RG + cq * 10, hi);           // a2 hi : columns [320,360)
-                tmem_st<10>(tl + XC_RG + 40 + cq * 10, lo);      // a2 lo : columns [360,400)
-                ptx::tcgen05_wait_st();
+            {   // layer-2 epilogue + folded layers 3+4 (80 -> 2) on CUDA cores: partial velocity of this column quarter
+                const int col0 = (cq == 0) ? 0 : 16 + cq * 16;
+                const float2* w34 = reinterpret_cast<const float2*>(s.f32 + XF_W34) + col0;
+                float v0, v1;
+                if (cq == 0) output_epilogue<2>(tl + XC_RG + col0, s.f32 + XF_B2 + col0, w34, v0, v1);
+                else         output_epilogue<1>(tl + XC_RG + col0, s.f32 + XF_B2 + col0, w34, v0, v1);
+                s.vpart[(cq * 2 + 0) * X_ROWS + r] = v0;
+                s.vpart[(cq * 2 + 1) * X_ROWS + r] = v1;
             }
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
-            // ---------------- folded layers 3+4: a2 (K = 80, TMEM) -> 2 (N padded to 16), accumulate in [400,416) ----------------
-            if (warp == 0) {
+            // ---------------- gates, N half 0 -> [320,448) (the layer-2 accumulator is consumed); velocity, integration, emit --------
+            if (warp == 0 && feed_back) {
                 ptx::tcgen05_fence_after_thread_sync();
-                mma3_ts<16, 16, 5>(tmem + XC_V, tmem + XC_RG, tmem + XC_RG + 40, s.w + XW_W34_HI, s.w + XW_W34_LO, false, leader);
-                umma_commit(&s.bar[0], leader);
-                if (feed_back) {   // gates, N half 0 -> [320,448): queued behind L34, the last reader of a2
-                    mma3_ss<256, 128, 4>(tmem + XC_RG, s.h[0], s.h[1], s.w + XW_WHH_HI, s.w + XW_WHH_LO, leader);
-                    umma_commit(&s.bar[1], leader);
-                }
+                mma3_ss<256, 128, 4>(tmem + XC_RG, s.h[0], s.h[1], s.w + XW_WHH_HI, s.w + XW_WHH_LO, leader);
+                umma_commit(&s.bar[1], leader);
             }
-            mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
-            ptx::tcgen05_fence_after_thread_sync();
-            if (cq == 0) {
-                uint32_t a[2];
-                tmem_ld<2>(tl + XC_V, a);
-                ptx::tcgen05_wait_ld();
-                const float v0 = __uint_as_float(a[0]) + s.f32[XF_B34], v1 = __uint_as_float(a[1]) + s.f32[XF_B34 + 1];
+            if (cq == 1) {      // quarter 1 finishes the row (warp 0 of quarter 0 is busy issuing the gate MMAs)
+                const float v0 = s.vpart[0 * X_ROWS + r] + s.vpart[2 * X_ROWS + r] + s.vpart[4 * X_ROWS + r] + s.vpart[6 * X_ROWS + r] + s.f32[XF_B34];
+                const float v1 = s.vpart[1 * X_ROWS + r] + s.vpart[3 * X_ROWS + r] + s.vpart[5 * X_ROWS + r] + s.vpart[7 * X_ROWS + r] + s.f32[XF_B34 + 1];
                 p0 += v0; p1 += v1;
                 s.x4[r] = p0; s.x4[X_ROWS + r] = p1; s.x4[2 * X_ROWS + r] = v0; s.x4[3 * X_ROWS + r] = v1;
                 if (valid)
                     *reinterpret_cast<float4*>(out + ((size_t)(row0 + r) * n_next + t) * 4) = make_float4(p0, p1, v0, v1);
             }
-            ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
             if (!feed_back) break;
             // ---------------- LSTM cell on the two gate halves (column quarters 0,1 -> half 0; 2,3 -> half 1) ----------------

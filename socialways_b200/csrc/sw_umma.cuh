@@ -18,6 +18,15 @@ __device__ __forceinline__ uint64_t umma_desc(const void* smem_ptr, uint32_t lbo
            (1ull << 46);   // version = 1 (sm_100), base_offset = 0, layout_type = SWIZZLE_NONE
 }
 
+// Same descriptor, but broadcast from lane 0 with a shuffle: the compiler then KNOWS the value is warp-uniform, keeps
+// it (and every "+ k-block offset" derived from it) in uniform registers and feeds UTCHMMA without the
+// ELECT / R2UR.BROADCAST "waterfall" loop it otherwise emits per MMA.  Call from convergent code (all 32 lanes).
+__device__ __forceinline__ uint64_t umma_desc_uniform(const void* smem_ptr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    const uint64_t d = umma_desc(smem_ptr, lbo_bytes, sbo_bytes);
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)d, 0), hi = __shfl_sync(0xffffffffu, (uint32_t)(d >> 32), 0);
+    return ((uint64_t)hi << 32) | lo;
+}
+
 // instruction descriptor: FP32 accumulate (c_format 1 @4), a/b format @7/@10 (0 = F16, 1 = BF16), K-major A and B,
 // N >> 3 @17, M = 128 (>> 4) @24
 __device__ __forceinline__ constexpr uint32_t umma_idesc(int n, uint32_t ab_format) {
@@ -61,21 +70,21 @@ template <int B_ROWS, int N, int KB, typename T>
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, const T* a, const T* b, uint32_t ab_format, bool accumulate_first,
                                         bool leader) {
     const uint32_t idesc = umma_idesc(N, ab_format);
-    const uint64_t ad = umma_desc(a, 128 * 16, 128), bd = umma_desc(b, B_ROWS * 16, 128);
+    const uint64_t ad = umma_desc_uniform(a, 128 * 16, 128), bd = umma_desc_uniform(b, B_ROWS * 16, 128);
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb)      // start-address field is in 16-byte units: one K block = 2 chunks of rows*16 B
         umma_issue_ss(d_tmem, ad + (uint64_t)(kb * 2 * 128), bd + (uint64_t)(kb * 2 * B_ROWS), idesc, accumulate_first || kb > 0, leader);
 }
 
-// same with the A operand in TMEM (16-bit, 8 columns per K block)
-template <int B_ROWS, int N, int KB, typename T>
+// same with the A operand in TMEM (16-bit: one K block = 8 columns; consecutive K blocks A_STRIDE columns apart)
+template <int B_ROWS, int N, int KB, int A_STRIDE = 8, typename T>
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, const T* b, uint32_t ab_format, bool accumulate_first,
                                         bool leader) {
     const uint32_t idesc = umma_idesc(N, ab_format);
-    const uint64_t bd = umma_desc(b, B_ROWS * 16, 128);
+    const uint64_t bd = umma_desc_uniform(b, B_ROWS * 16, 128);
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb)
-        umma_issue_ts(d_tmem, a_tmem + kb * 8, bd + (uint64_t)(kb * 2 * B_ROWS), idesc, accumulate_first || kb > 0, leader);
+        umma_issue_ts(d_tmem, a_tmem + kb * A_STRIDE, bd + (uint64_t)(kb * 2 * B_ROWS), idesc, accumulate_first || kb > 0, leader);
 }
 
 // TMEM load / store of NCOLS consecutive 32-bit columns of the calling thread's lane (32x32b shape),
@@ -138,7 +147,7 @@ __device__ __forceinline__ float expneg_clamped(float x) { return ex2_approx(fmi
 // logistic/tanh evaluations cost 10 ex2 + 5 rcp MUFU operations instead of 10 + 10 (the MUFU pipe, 16
 // lanes/clk/SM, is what bounds the gate epilogue).  g = pre-activations (i, f, g, o); c updated in place.
 __device__ __forceinline__ void lstm_cell_pair(const float (&ga)[4], const float (&gb)[4], float& ca, float& cb,
-                                               float& ha, float& hb) {
+                                                  float& ha, float& hb) {
     float cn[2];
     const float* gs[2] = {ga, gb};
     const float cs[2] = {ca, cb};
@@ -150,8 +159,8 @@ __device__ __forceinline__ void lstm_cell_pair(const float (&ga)[4], const float
         const float sig_i = ag * r_ig, tanh_g = fmaf(2.0f * ai, r_ig, -1.0f);
         const float af = 1.0f + expneg_clamped(g[1]), ao = 1.0f + expneg_clamped(g[3]);
         const float r_fo = rcp_approx(af * ao);
-        cn[q] = fmaf(ao * r_fo, cs[q], sig_i * tanh_g);              // sigma(f) = ao / (af.ao)
-        if (q == 0) ha = af * r_fo; else hb = af * r_fo;             // sigma(o), multiplied by tanh(c) below
+        cn[q] = fmaf(ao * r_fo, cs[q], sig_i * tanh_g);
+        if (q == 0) ha = af * r_fo; else hb = af * r_fo;
     }
     const float a0 = 1.0f + expneg_clamped(2.0f * cn[0]), a1 = 1.0f + expneg_clamped(2.0f * cn[1]);
     const float r = rcp_approx(a0 * a1);

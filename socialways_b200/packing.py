@@ -86,7 +86,8 @@ def pack_decoder_tcx(lstm_pack, dec_pack):
     w16   fp16 [81408]: for W1h [160 n][64 k], W2 [80][160], W34 [16 (2 real)][80], Whh [256 n'][64]:
           canonical hi block then canonical lo block, x = hi + lo
     wsz16 fp16 [3][2][4][160][8]: the hoisted rows of W1 (S: k 0..63, z: 64..95) in three K = 32 chunks, hi | lo
-    f32   [1536]: wx4 [256 n'][4] | bL [256] | b1 [160] | b2 [80] | b34 [2] | pad"""
+    f32   [1696]: wx4 [256 n'][4] | bL [256] | b1 [160] | b2 [80] | b34 [2] | pad | W34 [80 k][2] (fp32: the folded
+          80 -> 2 output layer runs as FMAs inside the layer-2 epilogue)"""
     w1 = dec_pack[:25600].view(160, 160).t()                  # [n, k], k order {h, S, z}
     b1 = dec_pack[25600:25760]
     w2 = dec_pack[25760:38560].view(160, 80).t()
@@ -106,5 +107,6 @@ def pack_decoder_tcx(lstm_pack, dec_pack):
         hi, lo = _split_f16(w1[:, 64 + 32 * ch:64 + 32 * (ch + 1)].contiguous())
         chunks += [_canonical_kmajor(hi), _canonical_kmajor(lo)]
     wsz16 = torch.cat(chunks).contiguous()
-    f32 = torch.cat([lstm_pack[0:4].t().reshape(-1), lstm_pack[68], b1, b2, b34, b34.new_zeros(14)]).contiguous()
+    f32 = torch.cat([lstm_pack[0:4].t().reshape(-1), lstm_pack[68], b1, b2, b34, b34.new_zeros(14),
+                     dec_pack[38640:38800]]).contiguous()
     return w16, wsz16, f32
