@@ -21,9 +21,9 @@
 //            once per tile by MMAs whose weights are streamed through a 20 KB staging buffer, and
 //            kept in 160 TMEM columns for the 12 steps
 //   (p, v)   fed back to the LSTM input projection in fp32 FMAs (never rounded)
-// TMEM columns: [0,160) c1 | [160,320) L1 acc -> a1 hi|lo ; later gates half 1 | [320,448) L2 acc -> a2 hi|lo ;
-//               later gates half 0 | [448,464) L34 acc.  MMAs execute in issue order, so the gates MMAs are
-//               queued right behind the last reader of the region they overwrite and run under the epilogues.
+// TMEM columns: [0,160) c1 | [160,320) L1 acc -> a1 hi|lo ; later gates half 1 | [320,448) L2 acc [320,400) ;
+//               later gates half 0.  MMAs execute in issue order, so the gates MMAs are queued right behind the
+//               last reader of the region they overwrite and run under the epilogues.
 #include <cuda_fp16.h>
 
 #include "sw_common.cuh"
@@ -40,7 +40,7 @@ constexpr int XW_W1H_HI = 0, XW_W1H_LO = 10240, XW_W2_HI = 20480, XW_W2_LO = 332
 constexpr int XW_SZ_CHUNK = 2 * 4 * 160 * 8;      // 10240 halves = 20480 B
 // fp32 section: wx4[256][4] | bL[256] | b1[160] | b2[80] | b34[2] | pad | W34[80][2]
 constexpr int XF_WX4 = 0, XF_BL = 1024, XF_B1 = 1280, XF_B2 = 1440, XF_B34 = 1520, XF_W34 = 1536, XF_TOTAL = 1536 + 160;
-constexpr uint32_t XC_C1 = 0, XC_R1 = 160, XC_RG = 320, XC_V = 448;
+constexpr uint32_t XC_C1 = 0, XC_R1 = 160, XC_RG = 320;
 constexpr uint32_t FMT_F16 = 0;
 
 struct TcxSmem {
