@@ -205,7 +205,10 @@ def run_ours(args):
     def step_resident(timed, precision=None, events=None):
         precision = precision or args.precision
         events = dec_events if events is None else events
-        enc = ops.lstm_seq(pk["enc"], obsv_d, want_x_last=True)
+        if precision == "fp16x2":
+            enc = ops.lstm_seq_tcx(*pk["enc_tcx"], obsv_d)
+        else:
+            enc = ops.lstm_seq(pk["enc"], obsv_d, want_x_last=True)
         ub = torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])
         pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
         if timed:

@@ -54,6 +54,12 @@ int sw_lstm_seq_fwd(const float* lstm_pack, const float* x, int in_dim, int n_ro
                     const float* h_in, const float* c_in, float* y_out, float* h_out, float* c_out,
                     float* x_last, float* stash_gates, float* stash_xh, int sm_count, void* stream);
 
+/* Tensor-core variant of sw_lstm_seq_fwd for the inference path (zero initial state, no stash, no y_out): the recurrent
+ * projection h . Whh^T as tcgen05.mma on fp16 hi/lo split operands (fp32 accumulate in TMEM), Wx . x4 + b as fp32 FMAs.
+ * enc_w16 / enc_f32 from packing.pack_encoder_tcx: Whh hi | lo fp16 canonical [2][8][256][8]; wx4 [256][4] | bL [256]. */
+int sw_lstm_seq_fwd_tcx(const void* enc_w16, const float* enc_f32, const float* x, int in_dim, int n_rows,
+                        int n_steps, float* h_out, float* c_out, float* x_last, int sm_count, void* stream);
+
 /* Backward of sw_lstm_seq_fwd from a zero initial state.  Replaces autograd through nn.LSTM
  * (train.py:254,268 for the generator, :278,299 for D) as walked by d_loss.backward() / g_loss.backward()
  * (train.py:495,538).  Tile-image layout = [..][tiles = ceil(N/32)][k][32 rows].

@@ -34,16 +34,19 @@
 
 void sw_set_last_cuda_error(int e);
 
-// Raise a kernel's dynamic shared-memory limit, once per call site and size (a function attribute, not a stream
-// operation; doing it only when the requested size grows keeps steady-state launches free of driver calls, which
-// also makes them capturable into CUDA graphs).
+// Raise a kernel's dynamic shared-memory limit, once per call site, device and size (a per-device function
+// attribute, not a stream operation; doing it only when the requested size grows keeps steady-state launches free of
+// driver calls, which also makes them capturable into CUDA graphs).
+#define SW_MAX_DEVICES 64
 #define SW_SET_MAX_SMEM(kernel, bytes)                                                                       \
     do {                                                                                                     \
-        static int _sw_smem_set = -1;                                                                        \
+        static int _sw_smem_set[SW_MAX_DEVICES];                                                             \
+        int _sw_dev = 0;                                                                                     \
+        SW_CUDA_TRY(cudaGetDevice(&_sw_dev));                                                                \
         const int _sw_want = (int)(bytes);                                                                   \
-        if (_sw_want > _sw_smem_set) {                                                                       \
+        if (_sw_dev < 0 || _sw_dev >= SW_MAX_DEVICES || _sw_want > _sw_smem_set[_sw_dev]) {                  \
             SW_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, _sw_want)); \
-            _sw_smem_set = _sw_want;                                                                         \
+            if (_sw_dev >= 0 && _sw_dev < SW_MAX_DEVICES) _sw_smem_set[_sw_dev] = _sw_want;                  \
         }                                                                                                    \
     } while (0)
 

@@ -92,6 +92,20 @@ def lstm_seq(lstm_pack, x, h_in=None, c_in=None, want_y=False, want_x_last=False
     return dict(h=h, c=c, y=y, x_last=xl, stash_gates=sg, stash_xh=sx)
 
 
+def lstm_seq_tcx(enc_w16, enc_f32, x):
+    """sw_lstm_seq_fwd_tcx: tensor-core observation encoder (zero initial state, inference only)."""
+    x = _f32(x)
+    n, t, d = x.shape
+    dev = x.device
+    if enc_w16.dtype != torch.float16 or not enc_w16.is_contiguous():
+        raise ValueError("lstm_seq_tcx: fp16 contiguous weight pack expected (packing.pack_encoder_tcx)")
+    h, c, xl = torch.empty(n, H, device=dev), torch.empty(n, H, device=dev), torch.empty(n, 4, device=dev)
+    code = _lib.lib().sw_lstm_seq_fwd_tcx(enc_w16.data_ptr(), _lib.ptr(_f32(enc_f32)), _lib.ptr(x), d, n, t, _lib.ptr(h),
+                                          _lib.ptr(c), _lib.ptr(xl), sm_count(dev), _stream())
+    _lib.check(code, "sw_lstm_seq_fwd_tcx")
+    return dict(h=h, c=c, x_last=xl)
+
+
 def lstm_seq_bwd(lstm_pack_t, stash_gates, dh_last, dc_last, n_rows, want_dx=False):
     """sw_lstm_seq_bwd -> gate gradients [T, tiles, 256, 32] (and dL/dx [N,T,4] if asked)."""
     t = stash_gates.shape[0]

@@ -110,3 +110,12 @@ def pack_decoder_tcx(lstm_pack, dec_pack):
     f32 = torch.cat([lstm_pack[0:4].t().reshape(-1), lstm_pack[68], b1, b2, b34, b34.new_zeros(14),
                      dec_pack[38640:38800]]).contiguous()
     return w16, wsz16, f32
+
+
+def pack_encoder_tcx(lstm_pack):
+    """Operands of the tensor-core observation encoder (csrc/lstm_seq_fwd_tcx.cu): Whh [256 n'][64 k] as canonical
+    hi | lo fp16 blocks (x = hi + lo), and fp32 [1280] = wx4 [256 n'][4] | bL [256]."""
+    hi, lo = _split_f16(lstm_pack[4:68].t().contiguous())
+    w16 = torch.cat([_canonical_kmajor(hi), _canonical_kmajor(lo)]).contiguous()
+    f32 = torch.cat([lstm_pack[0:4].t().reshape(-1), lstm_pack[68]]).contiguous()
+    return w16, f32

@@ -276,6 +276,7 @@ class Generator(nn.Module):
                              pool_m=m.contiguous(), pool_m0=m0.contiguous())
                 packs["tc_w16"], packs["tc_f32"] = packing.pack_decoder_tc(packs["enc"], packs["dec"])
                 packs["tcx"] = packing.pack_decoder_tcx(packs["enc"], packs["dec"])
+                packs["enc_tcx"] = packing.pack_encoder_tcx(packs["enc"])
             self._pack_cache = (key, packs)
         return self._pack_cache[1]
 
@@ -302,7 +303,10 @@ class Generator(nn.Module):
         precision = precision or self.inference_precision
         pk = self.packs()
         n = obsv_p.shape[0]
-        enc = ops.lstm_seq(pk["enc"], obsv_p, want_x_last=True)
+        if precision == "fp16x2":           # both recurrent kernels on the tensor cores (fp16 hi/lo split operands)
+            enc = ops.lstm_seq_tcx(*pk["enc_tcx"], obsv_p)
+        else:
+            enc = ops.lstm_seq(pk["enc"], obsv_p, want_x_last=True)
         pooled = None
         if self.use_social:                                                    # train.py:408-413
             scenes = self.scene_index(sub_batches, n, obsv_p.device)
