@@ -162,15 +162,34 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
         const long long row0 = (long long)tile * X_ROWS;
         const bool valid = row0 + r < n_rows;
         const int agent = valid ? (int)((row0 + r) % n_agents) : 0;
-        // ---------------- tile prologue ----------------
-        {   // h0 -> hi|lo operand chunks (columns 16cq .. 16cq+15 of this row)
-            float v[16];
+        // ---------------- tile prologue: every global load of the tile is issued up front (one exposed latency, not five),
+        //                  and the hoist weight chunk ch+1 is in flight while the MMAs of chunk ch run ----------------
+        float4 hq[4], cq4[4];
+        float2 szv[12], xl = make_float2(0.f, 0.f);
+        uint4 wreg[3];
+        const uint4* wsz4 = reinterpret_cast<const uint4*>(wsz16);
+        constexpr int CHUNK_U4 = XW_SZ_CHUNK / 8;                         // 1280 uint4 per chunk: 2.5 per thread
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 t = valid ? __ldg(reinterpret_cast<const float4*>(h0 + (size_t)agent * SW_H + cq * 16) + q)
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-                v[q * 4] = t.x; v[q * 4 + 1] = t.y; v[q * 4 + 2] = t.z; v[q * 4 + 3] = t.w;
+        for (int q = 0; q < 3; ++q)
+            if (tid + q * X_THREADS < CHUNK_U4) wreg[q] = __ldg(wsz4 + tid + q * X_THREADS);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            hq[q] = valid ? __ldg(reinterpret_cast<const float4*>(h0 + (size_t)agent * SW_H + cq * 16) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+            cq4[q] = valid ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent * SW_H + cq * 16) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int e = 0; e < 12; ++e) {                                    // [S ; z] (K = 96): this thread owns K 24cq .. 24cq+23
+            const int k = cq * 24 + 2 * e;                                // even; the S | z boundary (64) is even too
+            szv[e] = make_float2(0.f, 0.f);
+            if (valid) {
+                if (k < 64) { if (pooled) szv[e] = __ldg(reinterpret_cast<const float2*>(pooled + (size_t)agent * SW_H + k)); }
+                else szv[e] = __ldg(reinterpret_cast<const float2*>(noise + (size_t)(row0 + r) * SW_Z + (k - 64)));
             }
+        }
+        if (cq == 1 && valid) xl = __ldg(reinterpret_cast<const float2*>(x_last + (size_t)agent * 4));
+        {   // h0 -> hi|lo operand chunks (columns 16cq .. 16cq+15 of this row)
+            const float v[16] = {hq[0].x, hq[0].y, hq[0].z, hq[0].w, hq[1].x, hq[1].y, hq[1].z, hq[1].w,
+                                 hq[2].x, hq[2].y, hq[2].z, hq[2].w, hq[3].x, hq[3].y, hq[3].z, hq[3].w};
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
                 uint32_t hi[4], lo[4];
@@ -181,45 +200,30 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
                 *reinterpret_cast<uint4*>(s.h[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
         }
-        float c[16];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 t = valid ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent * SW_H + cq * 16) + q)
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
-            c[q * 4] = t.x; c[q * 4 + 1] = t.y; c[q * 4 + 2] = t.z; c[q * 4 + 3] = t.w;
-        }
-        float p0 = 0.f, p1 = 0.f;
-        if (cq == 1 && valid) {
-            const float2 t = __ldg(reinterpret_cast<const float2*>(x_last + (size_t)agent * 4));
-            p0 = t.x; p1 = t.y;
-        }
-        {   // [S ; z] (K = 96) -> hi|lo TMEM A operand in R1: hi columns [160,208), lo [208,256); this thread: K 24cq..24cq+23
+        float c[16] = {cq4[0].x, cq4[0].y, cq4[0].z, cq4[0].w, cq4[1].x, cq4[1].y, cq4[1].z, cq4[1].w,
+                       cq4[2].x, cq4[2].y, cq4[2].z, cq4[2].w, cq4[3].x, cq4[3].y, cq4[3].z, cq4[3].w};
+        float p0 = xl.x, p1 = xl.y;
+        {   // [S ; z] -> hi|lo TMEM A operand in R1: hi columns [160,208), lo [208,256)
             uint32_t hi[12], lo[12];
 #pragma unroll
-            for (int e = 0; e < 12; ++e) {
-                const int k = cq * 24 + 2 * e;        // even; S and z boundaries (64) are even too
-                float a = 0.f, b = 0.f;
-                if (valid) {
-                    if (k < 64) {
-                        if (pooled) { const float2 t = __ldg(reinterpret_cast<const float2*>(pooled + (size_t)agent * SW_H + k)); a = t.x; b = t.y; }
-                    } else {
-                        const float2 t = __ldg(reinterpret_cast<const float2*>(noise + (size_t)(row0 + r) * SW_Z + (k - 64)));
-                        a = t.x; b = t.y;
-                    }
-                }
-                split2(a, b, hi[e], lo[e]);
-            }
+            for (int e = 0; e < 12; ++e) split2(szv[e].x, szv[e].y, hi[e], lo[e]);
             tmem_st<12>(tl + XC_R1 + cq * 12, hi);
             tmem_st<12>(tl + XC_R1 + 48 + cq * 12, lo);
             ptx::tcgen05_wait_st();
         }
         // c1 = [S ; z] . W1[S,z rows]^T accumulated into TMEM [0,160): three K = 32 chunks of streamed weights
         for (int ch = 0; ch < 3; ++ch) {
-            for (int i = tid * 8; i < XW_SZ_CHUNK; i += X_THREADS * 8)
-                *reinterpret_cast<uint4*>(s.stage + i) = __ldg(reinterpret_cast<const uint4*>(wsz16 + (size_t)ch * XW_SZ_CHUNK + i));
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (tid + q * X_THREADS < CHUNK_U4) reinterpret_cast<uint4*>(s.stage)[tid + q * X_THREADS] = wreg[q];
             ptx::fence_proxy_async(ptx::space_shared);
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
+            if (ch < 2) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    if (tid + q * X_THREADS < CHUNK_U4) wreg[q] = __ldg(wsz4 + (size_t)(ch + 1) * CHUNK_U4 + tid + q * X_THREADS);
+            }
             if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
                 mma3_ts<160, 160, 2>(tmem + XC_C1, tmem + XC_R1 + ch * 16, tmem + XC_R1 + 48 + ch * 16, s.stage,
