@@ -202,15 +202,28 @@ def run_ours(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     dec_events = []
 
+    stage_events = []
+
     def step_resident(timed, precision=None, events=None):
         precision = precision or args.precision
+        headline = events is None
         events = dec_events if events is None else events
+        if timed and headline:
+            s0, s1, s2, s3 = ev(), ev(), ev(), ev()
+            s0.record()
         if precision == "fp16x2":
             enc = ops.lstm_seq_tcx(*pk["enc_tcx"], obsv_d)
         else:
             enc = ops.lstm_seq(pk["enc"], obsv_d, want_x_last=True)
+        if timed and headline:
+            s1.record()
         ub = torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])
+        if timed and headline:
+            s2.record()
         pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
+        if timed and headline:
+            s3.record()
+            stage_events.append((s0, s1, s2, s3))
         if timed:
             e0, e1 = ev(), ev()
             e0.record()
@@ -245,6 +258,8 @@ def run_ours(args):
     barrier()
     ms = t0.elapsed_time(t1)
     dec_ms = sum(a.elapsed_time(b) for a, b in dec_events) / len(dec_events)
+    enc_ms = sum(a.elapsed_time(b) for a, b, _, _ in stage_events) / len(stage_events)
+    pool_ms = sum(c.elapsed_time(d) for _, _, c, d in stage_events) / len(stage_events)
     metrics_sum = m.sum(0).cpu().numpy() / n
 
     # ---------------- the other decode kernels, same inputs, reported beside the headline ----------------
@@ -347,6 +362,18 @@ def run_ours(args):
                          "flops_per_traj_algorithmic": FLOPS_PER_TRAJ,
                          "flops_per_traj_executed": FLOPS_PER_TRAJ_EXECUTED,
                          "note": NOTE_OF[args.precision]},
+            # the other kernels of the step, live CUDA-event times (north_star asks for the pairwise kernel's HBM figure;
+            # it is compute-bound -- SURVEY.md D9 -- so the fraction is small by construction)
+            "secondary_kernels": {
+                "pool_fwd_kernel": {"kernel_ms": pool_ms, "bound": "hbm (as asked; actually compute-bound)",
+                                    "algorithmic_bytes": n * 788, "achieved_gbs": n * 788 / (pool_ms * 1e-3) / 1e9,
+                                    "peak_gbs": pk_["hbm_gbs"], "frac_of_hbm": n * 788 / (pool_ms * 1e-3) / 1e9 / pk_["hbm_gbs"],
+                                    "achieved_tflops_fp32": n * A_PER_SCENE * 4544 / (pool_ms * 1e-3) / 1e12,
+                                    "note": "788 B/agent = x_last 16 + h 256 + (u|beta) 260 read, S 256 written"},
+                "encoder": {"kernel": "lstm_seq_fwd_tcx_kernel" if args.precision == "fp16x2" else "lstm_seq_fwd_kernel",
+                            "kernel_ms": enc_ms,
+                            "achieved_tflops": n * 528384 / (enc_ms * 1e-3) / 1e12,
+                            "frac_of_tensor_peak": n * 528384 / (enc_ms * 1e-3) / 1e12 / peak}},
             "other_precisions": {
                 k: {"kernel": KERNEL_OF[k], "value": world * traj_per_step * args.steps / (o["ms"] * 1e-3), "unit": "traj/s",
                     "ms_per_step": o["ms"] / args.steps, "kernel_ms": o["dec_ms"],
