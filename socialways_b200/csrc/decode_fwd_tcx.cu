@@ -21,7 +21,7 @@
 //            once per tile by MMAs whose weights are streamed through a 20 KB staging buffer, and
 //            kept in 160 TMEM columns for the 12 steps
 //   (p, v)   fed back to the LSTM input projection in fp32 FMAs (never rounded)
-// TMEM columns: [0,160) c1 | [160,320) L1 acc -> a1 hi|lo ; later gates half 1 | [320,448) L2 acc [320,400) ;
+// TMEM columns: [0,160) c1 | [160,320) L1 acc -> a1 hi|lo ; later gates half 1 | [320,480) L2 acc (hi | lo weight halves) ;
 //               later gates half 0.  MMAs execute in issue order, so the gates MMAs are queued right behind the
 //               last reader of the region they overwrite and run under the epilogues.
 #include <cuda_fp16.h>
@@ -34,7 +34,7 @@ namespace sw {
 constexpr int X_ROWS = 128;
 constexpr int X_THREADS = 512;
 // fp16 weight section (elements), every matrix canonical [K/8][N][8], hi block then lo block
-constexpr int XW_W1H_HI = 0, XW_W1H_LO = 10240, XW_W2_HI = 20480, XW_W2_LO = 33280, XW_W34_HI = 46080,
+constexpr int XW_W1H_HI = 0, XW_W1H_LO = 10240, XW_W2_CAT = 20480 /* [20][160 = hi|lo][8] */, XW_W34_HI = 46080,
               XW_W34_LO = 47360, XW_WHH_HI = 48640, XW_WHH_LO = 65024, XW_TOTAL = 81408;
 // hoist weights in global memory: 3 chunks of K = 32 rows of W1[S,z]: [chunk][hi|lo][4][160][8]
 constexpr int XW_SZ_CHUNK = 2 * 4 * 160 * 8;      // 10240 halves = 20480 B
@@ -111,12 +111,13 @@ template <int NKB>
 __device__ __forceinline__ void output_epilogue(uint32_t t_acc, const float* __restrict__ bias, const float2* __restrict__ w34,
                                                 float& v0, float& v1) {
     v0 = 0.0f; v1 = 0.0f;
-    uint32_t acc[NKB * 16];
-    tmem_ld<NKB * 16>(t_acc, acc);
+    uint32_t acc[NKB * 16], acc2[NKB * 16];
+    tmem_ld<NKB * 16>(t_acc, acc);               // a1_hi.W2_hi + a1_lo.W2_hi
+    tmem_ld<NKB * 16>(t_acc + 80, acc2);         // a1_hi.W2_lo
     ptx::tcgen05_wait_ld();
 #pragma unroll
     for (int j = 0; j < NKB * 16; ++j) {
-        const float y = lrelu02(__uint_as_float(acc[j]) + bias[j]);
+        const float y = lrelu02(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]) + bias[j]);
         const float2 w = w34[j];
         v0 = fmaf(y, w.x, v0);
         v1 = fmaf(y, w.y, v1);
@@ -256,7 +257,11 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             // ---------------- layer 2: a1 (K = 160, TMEM, K block kb at column 16 kb) -> 80 in [320,400) ----------------
             if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
-                mma3_ts<80, 80, 10, 16>(tmem + XC_RG, tmem + XC_R1, tmem + XC_R1 + 8, s.w + XW_W2_HI, s.w + XW_W2_LO, false, leader);
+                // W2 hi and lo rows are stacked along N ([20 chunks][hi 80 | lo 80 rows][8]): one N = 160 pass yields a1_hi.W2_hi
+                // in columns [0,80) and a1_hi.W2_lo in [80,160); a1_lo.W2_hi accumulates into [0,80).  20 MMAs instead of 30
+                // (every tcgen05.mma carries a fixed cost); the epilogue adds the two column halves.
+                umma_ts<160, 160, 10, 16>(tmem + XC_RG, tmem + XC_R1, s.w + XW_W2_CAT, FMT_F16, false, leader);
+                umma_ts<160, 80, 10, 16>(tmem + XC_RG, tmem + XC_R1 + 8, s.w + XW_W2_CAT, FMT_F16, true, leader);
                 umma_commit(&s.bar[0], leader);
                 if (feed_back) {   // gates, N half 1 -> [160,288): runs under the L2 / L34 epilogues
                     mma3_ss<256, 128, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_WHH_HI + 128 * 8, s.w + XW_WHH_LO + 128 * 8, leader);

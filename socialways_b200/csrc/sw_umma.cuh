@@ -143,24 +143,28 @@ __device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.0f, rcp_appr
 // e^{-x} for the logistic forms below, argument clamped so that products of two (1 + e) terms stay finite
 __device__ __forceinline__ float expneg_clamped(float x) { return ex2_approx(fminf(-1.4426950408889634f * x, 60.0f)); }
 
-// LSTM cell update of TWO hidden units with shared reciprocals: 1/(A.B) gives both 1/A and 1/B, so the 10
-// logistic/tanh evaluations cost 10 ex2 + 5 rcp MUFU operations instead of 10 + 10 (the MUFU pipe, 16
-// lanes/clk/SM, is what bounds the gate epilogue).  g = pre-activations (i, f, g, o); c updated in place.
+// LSTM cell update of TWO hidden units with SHARED reciprocals: the gate epilogue is bound by the MUFU pipe (16 lanes/clk/SM),
+// so the four logistic denominators of a unit share ONE reciprocal, 1/(A.B.C.D), from which 1/A .. 1/D follow by
+// multiplications, and the two tanh(c) of the unit pair share another: 10 ex2 + 3 rcp per 2 units instead of 10 + 10.
+// Exponents are clamped at 2^30 so that the 4-fold product stays finite (sigma(x) floors at 2^-30 ~ 1e-9: far below
+// fp32 resolution of the cell update).  g = pre-activations (i, f, g, o); c updated in place.
+__device__ __forceinline__ float expneg30(float x) { return ex2_approx(fminf(-1.4426950408889634f * x, 30.0f)); }
 __device__ __forceinline__ void lstm_cell_pair(const float (&ga)[4], const float (&gb)[4], float& ca, float& cb,
-                                                  float& ha, float& hb) {
+                                               float& ha, float& hb) {
     float cn[2];
     const float* gs[2] = {ga, gb};
     const float cs[2] = {ca, cb};
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
         const float* g = gs[q];
-        const float ai = 1.0f + expneg_clamped(g[0]), ag = 1.0f + expneg_clamped(2.0f * g[2]);
-        const float r_ig = rcp_approx(ai * ag);
+        const float ai = 1.0f + expneg30(g[0]), af = 1.0f + expneg30(g[1]);
+        const float ag = 1.0f + expneg30(2.0f * g[2]), ao = 1.0f + expneg30(g[3]);
+        const float p_ig = ai * ag, p_fo = af * ao;
+        const float r = rcp_approx(p_ig * p_fo);
+        const float r_ig = r * p_fo, r_fo = r * p_ig;            // 1/(ai.ag), 1/(af.ao)
         const float sig_i = ag * r_ig, tanh_g = fmaf(2.0f * ai, r_ig, -1.0f);
-        const float af = 1.0f + expneg_clamped(g[1]), ao = 1.0f + expneg_clamped(g[3]);
-        const float r_fo = rcp_approx(af * ao);
-        cn[q] = fmaf(ao * r_fo, cs[q], sig_i * tanh_g);
-        if (q == 0) ha = af * r_fo; else hb = af * r_fo;
+        cn[q] = fmaf(ao * r_fo, cs[q], sig_i * tanh_g);          // sigma(f) = ao / (af.ao)
+        if (q == 0) ha = af * r_fo; else hb = af * r_fo;         // sigma(o), multiplied by tanh(c) below
     }
     const float a0 = 1.0f + expneg_clamped(2.0f * cn[0]), a1 = 1.0f + expneg_clamped(2.0f * cn[1]);
     const float r = rcp_approx(a0 * a1);

@@ -83,8 +83,8 @@ def _split_f16(w):
 
 def pack_decoder_tcx(lstm_pack, dec_pack):
     """Operands of the fp16-split tcgen05 decode kernel (csrc/decode_fwd_tcx.cu):
-    w16   fp16 [81408]: for W1h [160 n][64 k], W2 [80][160], W34 [16 (2 real)][80], Whh [256 n'][64]:
-          canonical hi block then canonical lo block, x = hi + lo
+    w16   fp16 [81408]: for W1h [160 n][64 k], W34 [16 (2 real)][80], Whh [256 n'][64]: canonical hi block then canonical
+          lo block (x = hi + lo); W2 [80][160]: ONE canonical block of 160 rows = hi rows then lo rows
     wsz16 fp16 [3][2][4][160][8]: the hoisted rows of W1 (S: k 0..63, z: 64..95) in three K = 32 chunks, hi | lo
     f32   [1696]: wx4 [256 n'][4] | bL [256] | b1 [160] | b2 [80] | b34 [2] | pad | W34 [80 k][2] (fp32: the folded
           80 -> 2 output layer runs as FMAs inside the layer-2 epilogue)"""
@@ -98,9 +98,12 @@ def pack_decoder_tcx(lstm_pack, dec_pack):
     w34p[:2] = w34
     whh = lstm_pack[4:68].t()
     parts = []
-    for m in (w1[:, :64], w2, w34p, whh):
+    for name, m in (("w1h", w1[:, :64]), ("w2", w2), ("w34", w34p), ("whh", whh)):
         hi, lo = _split_f16(m.contiguous())
-        parts += [_canonical_kmajor(hi), _canonical_kmajor(lo)]
+        if name == "w2":        # hi and lo rows stacked along N: one N = 160 MMA pass covers a1.W2_hi and a1.W2_lo
+            parts.append(_canonical_kmajor(torch.cat([hi, lo], dim=0)))
+        else:
+            parts += [_canonical_kmajor(hi), _canonical_kmajor(lo)]
     w16 = torch.cat(parts).contiguous()
     chunks = []
     for ch in range(3):
