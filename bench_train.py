@@ -24,6 +24,42 @@ def toy(n):
     return dict(obsvs=o, preds=p, times=t, batches=b)
 
 
+def main_distributed(args):
+    """torchrun: BASELINE config 4 -- the toy set scaled to 65 532 trajectories, scenes sharded over the ranks, one
+    flat-buffer NCCL all-reduce per optimiser step (3 per iteration with unroll 1).  Rank 0 prints one JSON line."""
+    import torch.distributed as dist
+    from socialways_b200.trainer import SocialWaysTrainer
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world, rank = dist.get_world_size(), dist.get_rank()
+    data = toy(args.n)
+    res = []
+    for bs in [int(x) for x in args.batch_sizes.split(",")]:
+        tr = SocialWaysTrainer(data, batch_size=bs, use_social=True, n_unrolling_steps=1, device=f"cuda:{local}")
+        np.random.seed(0)
+        torch.manual_seed(0)
+        tr.train(verbose=False)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.epochs):
+            ade, fde = tr.train(verbose=False)
+        torch.cuda.synchronize()
+        dist.barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / args.epochs], device="cuda", dtype=torch.float64)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        iters = len(tr.loss_log) // (args.epochs + 1)
+        rec = {"global_batch_size": bs, "epoch_s": dt.item(), "agents_per_s": tr.n_train_samples / dt.item(),
+               "iterations_per_epoch": iters, "ms_per_iteration": 1e3 * dt.item() / iters, "train_ade": ade, "train_fde": fde}
+        res.append(rec)
+    if rank == 0:
+        print(json.dumps({"metric": "train_agents_per_sec", "n_gpus": world, "n_trajectories": args.n,
+                          "parallelism": f"scenes of every mini-batch sharded x{world}, flat-buffer NCCL all-reduce per optimiser step",
+                          "results": res}))
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=65536 // 6 * 6)
@@ -32,6 +68,8 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=216)
     ap.add_argument("--graph", action="store_true", help="also time train_graphed() (CUDA-graph replay per batch shape)")
     args = ap.parse_args()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return main_distributed(args)
     from socialways_b200.trainer import SocialWaysTrainer
     data = toy(args.n)
     out = {"metric": "train_agents_per_sec", "n_trajectories": args.n, "results": []}

@@ -188,8 +188,12 @@ class SocialWaysTrainer:
         """One iteration of train() (train.py:470-551) on static tensors, free of host synchronisation so that it
         can be captured into a CUDA graph: no .item(), no host RNG, in-place D backup/rollback instead of
         copy.deepcopy / .data rebinding (same values)."""
-        D, mse_loss, nl = self.D, self.mse_loss, self.n_latent_codes
+        D, nl = self.D, self.n_latent_codes
         obsv, pred, noise, zeros, ones, scenes = st["obsv"], st["pred"], st["noise"], st["zeros"], st["ones"], st["scenes"]
+        if self.world_size > 1:       # this rank's share of nn.MSELoss over the GLOBAL mini-batch (SURVEY.md §8e)
+            mse_loss = lambda a, b, _bs=st["global_bs"]: swdist.global_mse(a, b, _bs * max(1, a.numel() // max(1, a.shape[0])))
+        else:
+            mse_loss = self.mse_loss
         obsv_4d, pred_4d = get_traj_4d(obsv, pred)
         lin = [p for m in D.modules() if isinstance(m, nn.Linear) for p in (m.weight, m.bias)]
         for u in range(self.n_unrolling_steps + 1):
@@ -204,6 +208,7 @@ class SocialWaysTrainer:
             d_real = mse_loss(real_labels, ones)
             d_loss = d_fake + d_real + (self.loss_info_w * d_info if self.use_info_loss else 0.0)
             d_loss.backward()
+            swdist.allreduce_grads(D.parameters(), self.world_size)
             self.D_optimizer.step()
             if u == 0 and self.n_unrolling_steps > 0:
                 with torch.no_grad():
@@ -219,6 +224,7 @@ class SocialWaysTrainer:
         g_info = mse_loss(code_hat, noise[:, :nl])
         g_loss = g_fool + (self.loss_info_w * g_info if self.use_info_loss else 0.0)
         g_loss.backward()
+        swdist.allreduce_grads(list(self.generator.optimizer_parameters()), self.world_size)
         self.predictor_optimizer.step()
         with torch.no_grad():
             if self.n_unrolling_steps > 0:                                   # D.load(backup): Linear layers only
@@ -234,7 +240,9 @@ class SocialWaysTrainer:
         capturable=True (constructor flag cuda_graph=True) and world_size 1.  The first occurrence of a batch
         shape runs eagerly (it also warms up the lazily-initialised optimiser state), the second is captured."""
         if not self.cuda_graph or self.world_size != 1:
-            raise RuntimeError("construct the trainer with cuda_graph=True (single process) to use train_graphed()")
+            # capturing the NCCL all-reduces of the sharded step was tried (torch 2.11 / NCCL 2.28) and hung in capture;
+            # multi-GPU training uses the eager train() until that is resolved
+            raise RuntimeError("train_graphed() needs cuda_graph=True and a single process; use train() for multi-GPU runs")
         tic = time.perf_counter()
         dev = self.device
         stats_acc = torch.zeros(8, device=dev, dtype=torch.float64)
@@ -248,7 +256,13 @@ class SocialWaysTrainer:
                 continue
             lo, hi = int(group[0][0]), int(group[-1][1])
             sub = np.asarray(group) - lo
-            key = (hi - lo, sub.tobytes())
+            global_bs, g_lo = hi - lo, lo
+            if self.world_size > 1:       # this rank's contiguous block of scenes (the NCCL all-reduces are captured too)
+                s_lo, s_hi, sub = swdist.shard_scenes(sub, self.world_size, self.rank)
+                if s_hi <= s_lo:
+                    raise RuntimeError("train_graphed(): a rank received no scene of this mini-batch; use train()")
+                lo, hi = g_lo + s_lo, g_lo + s_hi
+            key = (global_bs, hi - lo, lo - g_lo, sub.tobytes())
             ent = self._graphs.get(key)
             if ent is None:
                 bs = hi - lo
@@ -256,7 +270,7 @@ class SocialWaysTrainer:
                 st = dict(obsv=torch.empty(bs, self.n_past, 2, device=dev), pred=torch.empty(bs, self.n_next, 2, device=dev),
                           noise=torch.empty(bs, self.noise_len, device=dev), zeros=torch.empty(bs, 1, device=dev),
                           ones=torch.empty(bs, 1, device=dev), stats=torch.zeros(8, device=dev),
-                          backup=[torch.empty_like(p) for p in lin_n],
+                          backup=[torch.empty_like(p) for p in lin_n], global_bs=global_bs,
                           scenes=self.generator.scene_index(sub, bs, dev))
                 _ = st["scenes"].pair_offsets                                 # build every lazy device index up front
                 ent = self._graphs[key] = dict(st=st, graph=None, seen=0)
@@ -265,7 +279,7 @@ class SocialWaysTrainer:
             st["pred"].copy_(self.dataset_pred[lo:hi])
             st["zeros"].fill_(float(np.random.uniform(0, 0.1)))               # train.py:471
             st["ones"].fill_(float(np.random.uniform(0.9, 1.0)))              # train.py:472
-            st["noise"].copy_(torch.rand(hi - lo, self.noise_len))            # train.py:473 (CPU RNG)
+            st["noise"].copy_(torch.rand(global_bs, self.noise_len)[lo - g_lo:hi - g_lo])   # train.py:473 (CPU RNG, global batch)
             if ent["graph"] is None and ent["seen"] >= 1:
                 g = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize()
@@ -280,12 +294,15 @@ class SocialWaysTrainer:
             stats_acc += st["stats"]
             n_iter += 1
             group, count = [], 0
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(stats_acc, op=dist.ReduceOp.SUM)
         vals = stats_acc.tolist()
         train_ADE, train_FDE = vals[0] / self.n_train_samples, vals[1] / self.n_train_samples
         self.last_epoch_mean_losses = dict(zip(("d_loss", "d_fake", "d_real", "d_info", "g_fool", "g_info"),
                                                [v / max(1, n_iter) for v in vals[2:]]))
         toc = time.perf_counter()
-        if verbose:
+        if verbose and self.rank == 0:
             print(" Epc=%4d, Train ADE,FDE = (%.3f, %.3f) | time = %.1f" % (self.epoch, train_ADE, train_FDE, toc - tic))
         return train_ADE, train_FDE
 

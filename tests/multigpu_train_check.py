@@ -28,12 +28,12 @@ def main():
     data = synthetic_scenes(list(rng.randint(1, 9, size=60)), seed=8)
     W = so.init_weights(seed=2)
 
-    def run(w):
+    def run(w, graph=False):
         tr = SocialWaysTrainer(data, batch_size=64, use_social=True, n_unrolling_steps=1, weights=W,
-                               device=f"cuda:{local}", world=w)
+                               device=f"cuda:{local}", world=w, cuda_graph=graph)
         np.random.seed(5)
         torch.manual_seed(5)
-        ade, fde = tr.train(verbose=False)
+        ade, fde = (tr.train_graphed if graph else tr.train)(verbose=False)
         return tr.reference_weights(), ade, fde
 
     w_n, ade_n, fde_n = run((world, rank))
