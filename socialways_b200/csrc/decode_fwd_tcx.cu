@@ -20,7 +20,11 @@
 //   c1       the step-invariant part of layer 1, [S ; z] . W1[S,z rows] (hoisted), computed
 //            once per tile by MMAs whose weights are streamed through a 20 KB staging buffer, and
 //            kept in 160 TMEM columns for the 12 steps
-//   (p, v)   fed back to the LSTM input projection in fp32 FMAs (never rounded)
+//   (p, v)   fed back to the LSTM as ONE extra K block of the gate MMA: A row = [x_hi(4) | x_lo(4) | x_hi(4) | 1 | 1 | 0 0],
+//            B row n' = [Wx_hi | Wx_hi | Wx_lo | b_hi | b_lo | 0 0], i.e. the same three-product split plus the bias, so the
+//            gate accumulator IS the pre-activation (the gate epilogue was issue-bound: 37 % of its instructions were
+//            this 4-term projection + bias on CUDA cores).  The gate rows of Whh / Wx / b are pre-scaled on the host by
+//            -log2(e) (i, f, o) and -2 log2(e) (g), so the accumulator is directly the ex2 argument of the logistic forms.
 // TMEM columns: [0,160) c1 | [160,320) L1 acc -> a1 hi|lo ; later gates half 1 | [320,480) L2 acc (hi | lo weight halves) ;
 //               later gates half 0.  MMAs execute in issue order, so the gates MMAs are queued right behind the
 //               last reader of the region they overwrite and run under the epilogues.
@@ -34,12 +38,12 @@ namespace sw {
 constexpr int X_ROWS = 128;
 constexpr int X_THREADS = 512;
 // fp16 weight section (elements), every matrix canonical [K/8][N][8], hi block then lo block
-constexpr int XW_W1H_HI = 0, XW_W1H_LO = 10240, XW_W2_CAT = 20480 /* [20][160 = hi|lo][8] */, XW_W34_HI = 46080,
-              XW_W34_LO = 47360, XW_WHH_HI = 48640, XW_WHH_LO = 65024, XW_TOTAL = 81408;
+constexpr int XW_W1H_HI = 0, XW_W1H_LO = 10240, XW_W2_CAT = 20480 /* [20][160 = hi|lo][8] */, XW_WHH_HI = 46080,
+              XW_WHH_LO = 62464, XW_WXK = 78848 /* x-feedback K block [2][256][8] */, XW_TOTAL = 82944;
 // hoist weights in global memory: 3 chunks of K = 32 rows of W1[S,z]: [chunk][hi|lo][4][160][8]
 constexpr int XW_SZ_CHUNK = 2 * 4 * 160 * 8;      // 10240 halves = 20480 B
-// fp32 section: wx4[256][4] | bL[256] | b1[160] | b2[80] | b34[2] | pad | W34[80][2]
-constexpr int XF_WX4 = 0, XF_BL = 1024, XF_B1 = 1280, XF_B2 = 1440, XF_B34 = 1520, XF_W34 = 1536, XF_TOTAL = 1536 + 160;
+// fp32 section: b1[160] | b2[80] | b34[2] | pad | W34[80][2]
+constexpr int XF_B1 = 0, XF_B2 = 160, XF_B34 = 240, XF_W34 = 256, XF_TOTAL = 256 + 160;
 constexpr uint32_t XC_C1 = 0, XC_R1 = 160, XC_RG = 320;
 constexpr uint32_t FMT_F16 = 0;
 
@@ -47,8 +51,8 @@ struct TcxSmem {
     __half w[XW_TOTAL];                    // 162 816 B
     __half h[2][8 * X_ROWS * 8];           // h hi | lo : [8 chunks][128][8]  (32 768 B)
     __half stage[XW_SZ_CHUNK];             // hoist weight chunk (20 480 B)
+    __half xk[2 * X_ROWS * 8];             // x-feedback A operand, one K block: [2 chunks][128][8]  (4 096 B)
     float f32[XF_TOTAL];
-    float x4[4 * X_ROWS];
     float vpart[8 * X_ROWS];                // partial velocities [quarter][component][row]
     unsigned long long bar[3];
     uint32_t tmem_base;
@@ -81,26 +85,38 @@ __device__ __forceinline__ void mma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo
     umma_ts<B_ROWS, N, KB, A_STRIDE>(d, a_lo, b_hi, FMT_F16, true, leader);
 }
 
-// Epilogue of a hidden layer, NKB K-blocks (16 output features each) of this thread: y = lrelu(acc [+ c1] + bias), then the
-// hi|lo fp16 pieces of each block are written IN PLACE over the 16 accumulator columns that produced them
+// Epilogue of layer 1, NKB K-blocks (16 output features each) of this thread: y = lrelu(acc + c1) (c1 carries the bias),
+// then the hi|lo fp16 pieces of each block are written IN PLACE over the 16 accumulator columns that produced them
 // (hi -> columns +0..7, lo -> +8..15), i.e. only over columns this thread itself has just read: no barrier between
 // the read and the write, and the next layer addresses K block kb at column 16*kb (hi) / 16*kb + 8 (lo).
-template <int NKB, bool WITH_C1>
-__device__ __forceinline__ void hidden_epilogue(uint32_t t_acc, uint32_t t_c1, const float* __restrict__ bias) {
+template <int NKB>
+__device__ __forceinline__ void hidden_epilogue(uint32_t t_acc, uint32_t t_c1) {
 #pragma unroll
     for (int kb = 0; kb < NKB; ++kb) {
         uint32_t acc[16], c1v[16], pc[16];
         tmem_ld<16>(t_acc + kb * 16, acc);
-        if (WITH_C1) tmem_ld<16>(t_c1 + kb * 16, c1v);
+        tmem_ld<16>(t_c1 + kb * 16, c1v);
         ptx::tcgen05_wait_ld();
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            float y0 = __uint_as_float(acc[2 * e]) + bias[kb * 16 + 2 * e], y1 = __uint_as_float(acc[2 * e + 1]) + bias[kb * 16 + 2 * e + 1];
-            if (WITH_C1) { y0 += __uint_as_float(c1v[2 * e]); y1 += __uint_as_float(c1v[2 * e + 1]); }
+            const float y0 = __uint_as_float(acc[2 * e]) + __uint_as_float(c1v[2 * e]);
+            const float y1 = __uint_as_float(acc[2 * e + 1]) + __uint_as_float(c1v[2 * e + 1]);
             split2(lrelu02(y0), lrelu02(y1), pc[e], pc[8 + e]);
         }
         tmem_st<16>(t_acc + kb * 16, pc);
     }
+    ptx::tcgen05_wait_st();
+}
+
+// c1 += b1 for this thread's NKB K-blocks, once per tile (instead of one bias add per value per step)
+template <int NKB>
+__device__ __forceinline__ void fold_bias_into_c1(uint32_t t_c1, const float* __restrict__ bias) {
+    uint32_t v[NKB * 16];
+    tmem_ld<NKB * 16>(t_c1, v);
+    ptx::tcgen05_wait_ld();
+#pragma unroll
+    for (int j = 0; j < NKB * 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + bias[j]);
+    tmem_st<NKB * 16>(t_c1, v);
     ptx::tcgen05_wait_st();
 }
 
@@ -156,8 +172,6 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
     const uint32_t tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0);   // warp-uniform for the compiler (uniform datapath)
     const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);       // this thread's lane, column 0
     uint32_t ph0 = 0, ph1 = 0;              // parities: bar0 (hoist, L1, L2) | bar1 / bar2 (gate halves)
-    const float4* wx4 = reinterpret_cast<const float4*>(s.f32 + XF_WX4);
-    const float* bL = s.f32 + XF_BL;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row0 = (long long)tile * X_ROWS;
@@ -234,6 +248,11 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;       // staging buffer is free again / c1 complete
             ptx::tcgen05_fence_after_thread_sync();
         }
+        {   // b1 joins c1 (the columns this thread reads back in the layer-1 epilogue)
+            const int col0 = (cq < 2) ? cq * 48 : 96 + (cq - 2) * 32;
+            if (cq < 2) fold_bias_into_c1<3>(tl + XC_C1 + col0, s.f32 + XF_B1 + col0);
+            else        fold_bias_into_c1<2>(tl + XC_C1 + col0, s.f32 + XF_B1 + col0);
+        }
         ptx::tcgen05_fence_before_thread_sync();
         __syncthreads();
 
@@ -249,8 +268,8 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             ptx::tcgen05_fence_after_thread_sync();
             {
                 const int col0 = (cq < 2) ? cq * 48 : 96 + (cq - 2) * 32;
-                if (cq < 2) hidden_epilogue<3, true>(tl + XC_R1 + col0, tl + XC_C1 + col0, s.f32 + XF_B1 + col0);
-                else        hidden_epilogue<2, true>(tl + XC_R1 + col0, tl + XC_C1 + col0, s.f32 + XF_B1 + col0);
+                if (cq < 2) hidden_epilogue<3>(tl + XC_R1 + col0, tl + XC_C1 + col0);
+                else        hidden_epilogue<2>(tl + XC_R1 + col0, tl + XC_C1 + col0);
             }
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
@@ -263,10 +282,9 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
                 umma_ts<160, 160, 10, 16>(tmem + XC_RG, tmem + XC_R1, s.w + XW_W2_CAT, FMT_F16, false, leader);
                 umma_ts<160, 80, 10, 16>(tmem + XC_RG, tmem + XC_R1 + 8, s.w + XW_W2_CAT, FMT_F16, true, leader);
                 umma_commit(&s.bar[0], leader);
-                if (feed_back) {   // gates, N half 1 -> [160,288): runs under the L2 / L34 epilogues
+                if (feed_back)     // gates, N half 1, h part -> [160,288): runs under the L2 / L34 epilogues (its x block and
+                                   // commit follow once the velocity exists)
                     mma3_ss<256, 128, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_WHH_HI + 128 * 8, s.w + XW_WHH_LO + 128 * 8, leader);
-                    umma_commit(&s.bar[2], leader);
-                }
             }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
@@ -281,28 +299,39 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             }
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
-            // ---------------- gates, N half 0 -> [320,448) (the layer-2 accumulator is consumed); velocity, integration, emit --------
-            if (warp == 0 && feed_back) {
-                ptx::tcgen05_fence_after_thread_sync();
-                mma3_ss<256, 128, 4>(tmem + XC_RG, s.h[0], s.h[1], s.w + XW_WHH_HI, s.w + XW_WHH_LO, leader);
-                umma_commit(&s.bar[1], leader);
-            }
-            if (cq == 1) {      // quarter 1 finishes the row (warp 0 of quarter 0 is busy issuing the gate MMAs)
+            // ---------------- velocity, integration, emit; (p, v) -> hi|lo x block of the gate MMA ----------------
+            if (cq == 1) {      // quarter 1 finishes the row
                 const float v0 = s.vpart[0 * X_ROWS + r] + s.vpart[2 * X_ROWS + r] + s.vpart[4 * X_ROWS + r] + s.vpart[6 * X_ROWS + r] + s.f32[XF_B34];
                 const float v1 = s.vpart[1 * X_ROWS + r] + s.vpart[3 * X_ROWS + r] + s.vpart[5 * X_ROWS + r] + s.vpart[7 * X_ROWS + r] + s.f32[XF_B34 + 1];
                 p0 += v0; p1 += v1;
-                s.x4[r] = p0; s.x4[X_ROWS + r] = p1; s.x4[2 * X_ROWS + r] = v0; s.x4[3 * X_ROWS + r] = v1;
+                if (feed_back) {
+                    uint32_t hp, lp, hv, lv;
+                    split2(p0, p1, hp, lp);
+                    split2(v0, v1, hv, lv);
+                    *reinterpret_cast<uint4*>(s.xk + (size_t)r * 8) = make_uint4(hp, hv, lp, lv);                      // k 0..7
+                    *reinterpret_cast<uint4*>(s.xk + (size_t)(X_ROWS + r) * 8) = make_uint4(hp, hv, 0x3C003C00u, 0u);  // k 8..15
+                }
                 if (valid)
                     *reinterpret_cast<float4*>(out + ((size_t)(row0 + r) * n_next + t) * 4) = make_float4(p0, p1, v0, v1);
             }
+            if (!feed_back) { __syncthreads(); break; }
+            ptx::fence_proxy_async(ptx::space_shared);
             __syncthreads();
-            if (!feed_back) break;
+            // ---------------- gates: x block of half 1 (its h part ran under the epilogues) -> bar2; half 0 (h part + x block)
+            //                  -> [320,448) (the layer-2 accumulator is consumed) -> bar1.  Quarters 2,3 start their cell update
+            //                  while the tensor pipe works on half 0. ----------------
+            if (warp == 0) {
+                ptx::tcgen05_fence_after_thread_sync();
+                umma_ss<256, 128, 1>(tmem + XC_R1, s.xk, s.w + XW_WXK + 128 * 8, FMT_F16, true, leader);
+                umma_commit(&s.bar[2], leader);
+                mma3_ss<256, 128, 4>(tmem + XC_RG, s.h[0], s.h[1], s.w + XW_WHH_HI, s.w + XW_WHH_LO, leader);
+                umma_ss<256, 128, 1>(tmem + XC_RG, s.xk, s.w + XW_WXK, FMT_F16, true, leader);
+                umma_commit(&s.bar[1], leader);
+            }
             // ---------------- LSTM cell on the two gate halves (column quarters 0,1 -> half 0; 2,3 -> half 1) ----------------
             if (cq < 2) mbar_wait(&s.bar[1], ph1); else mbar_wait(&s.bar[2], ph1);
-            ph1 ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
             {
-                const float x0 = s.x4[r], x1 = s.x4[X_ROWS + r], x2 = s.x4[2 * X_ROWS + r], x3 = s.x4[3 * X_ROWS + r];
                 const uint32_t gbase = tl + ((cq < 2) ? XC_RG : XC_R1) + (cq & 1) * 64;
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
@@ -316,22 +345,21 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
 #pragma unroll
                         for (int w2 = 0; w2 < 2; ++w2)
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int n = cq * 64 + half * 32 + (u + w2) * 4 + q;
-                                const float4 w = wx4[n];
-                                g[w2][q] = __uint_as_float(a[(u + w2) * 4 + q]) + bL[n] +
-                                           fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w * x3)));
-                            }
-                        lstm_cell_pair(g[0], g[1], c[half * 8 + u], c[half * 8 + u + 1], hv[u], hv[u + 1]);
+                            for (int q = 0; q < 4; ++q) g[w2][q] = __uint_as_float(a[(u + w2) * 4 + q]);
+                        lstm_cell_pair_prescaled(g[0], g[1], c[half * 8 + u], c[half * 8 + u + 1], hv[u], hv[u + 1]);
                     }
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) split2(hv[2 * e], hv[2 * e + 1], hi[e], lo[e]);
+                    // h is an operand of the half-0 gate MMAs: quarters 2,3 (released by bar2) must not overwrite it before
+                    // those MMAs have completed (bar1; long done by now -- the wait is a formality that closes the race)
+                    if (half == 0 && cq >= 2) mbar_wait(&s.bar[1], ph1);
                     const size_t off = ((size_t)(cq * 2 + half) * X_ROWS + r) * 8;
                     *reinterpret_cast<uint4*>(s.h[0] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<uint4*>(s.h[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
+            ph1 ^= 1;
             ptx::fence_proxy_async(ptx::space_shared);
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();

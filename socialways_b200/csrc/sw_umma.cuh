@@ -174,6 +174,33 @@ __device__ __forceinline__ void lstm_cell_pair(const float (&ga)[4], const float
     cb = cn[1];
 }
 
+// Same cell with PRE-SCALED pre-activations: e = (-log2 e . x_i, -log2 e . x_f, -2 log2 e . x_g, -log2 e . x_o), i.e. the ex2
+// arguments themselves (the scale lives in the packed gate weights, packing.pack_decoder_tcx) -- 4 multiplies per unit less.
+__device__ __forceinline__ void lstm_cell_pair_prescaled(const float (&ea)[4], const float (&eb)[4], float& ca, float& cb,
+                                                         float& ha, float& hb) {
+    float cn[2];
+    const float* es[2] = {ea, eb};
+    const float cs[2] = {ca, cb};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float* e = es[q];
+        const float ai = 1.0f + ex2_approx(fminf(e[0], 30.0f)), af = 1.0f + ex2_approx(fminf(e[1], 30.0f));
+        const float ag = 1.0f + ex2_approx(fminf(e[2], 30.0f)), ao = 1.0f + ex2_approx(fminf(e[3], 30.0f));
+        const float p_ig = ai * ag, p_fo = af * ao;
+        const float r = rcp_approx(p_ig * p_fo);
+        const float r_ig = r * p_fo, r_fo = r * p_ig;            // 1/(ai.ag), 1/(af.ao)
+        const float sig_i = ag * r_ig, tanh_g = fmaf(2.0f * ai, r_ig, -1.0f);
+        cn[q] = fmaf(ao * r_fo, cs[q], sig_i * tanh_g);          // sigma(f) = ao / (af.ao)
+        if (q == 0) ha = af * r_fo; else hb = af * r_fo;         // sigma(o), multiplied by tanh(c) below
+    }
+    const float a0 = 1.0f + expneg_clamped(2.0f * cn[0]), a1 = 1.0f + expneg_clamped(2.0f * cn[1]);
+    const float r = rcp_approx(a0 * a1);
+    ha *= fmaf(2.0f * a1, r, -1.0f);
+    hb *= fmaf(2.0f * a0, r, -1.0f);
+    ca = cn[0];
+    cb = cn[1];
+}
+
 // bf16-mode cell: hardware tanh (MUFU.TANH, rel. error 2^-11, below the bf16 operand rounding), 5 MUFU per unit
 __device__ __forceinline__ float tanh_hw(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void lstm_cell_hw(const float (&g)[4], float& c, float& h) {

@@ -191,6 +191,20 @@ def decode_tc(tc_w16, tc_f32, h0, c0, pooled, noise, x_last, n_next, out=None):
     return out
 
 
+_TCX_SIZES = None
+
+
+def _tcx_pack_sizes():
+    global _TCX_SIZES
+    if _TCX_SIZES is None:
+        import ctypes
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(_lib.lib().sw_decode_tcx_pack_sizes(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)),
+                   "sw_decode_tcx_pack_sizes")
+        _TCX_SIZES = (a.value, b.value, c.value)
+    return _TCX_SIZES
+
+
 def decode_tcx(w16, wsz16, f32, h0, c0, pooled, noise, x_last, n_next, out=None):
     """sw_decode_fwd_tcx: tcgen05 decode kernel on fp16 hi/lo split operands (fp32-faithful)."""
     noise = _f32(noise)
@@ -200,6 +214,9 @@ def decode_tcx(w16, wsz16, f32, h0, c0, pooled, noise, x_last, n_next, out=None)
     for t in (w16, wsz16):
         if t.dtype != torch.float16 or not t.is_contiguous():
             raise ValueError("decode_tcx: fp16 contiguous operand packs expected (packing.pack_decoder_tcx)")
+    if (w16.numel(), wsz16.numel(), f32.numel()) != _tcx_pack_sizes():
+        raise ValueError(f"decode_tcx: pack sizes {(w16.numel(), wsz16.numel(), f32.numel())} do not match the kernel's "
+                         f"{_tcx_pack_sizes()} (packing.pack_decoder_tcx / sw_decode_tcx_pack_sizes)")
     if out is None:
         out = torch.empty(k, n, n_next, 4, device=noise.device)
     code = _lib.lib().sw_decode_fwd_tcx(w16.data_ptr(), wsz16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(_f32(h0)),

@@ -81,37 +81,51 @@ def _split_f16(w):
     return hi, lo
 
 
+LOG2E = 1.4426950408889634
+
+
+def _gate_prescale(device, dtype):
+    """[256] scale of the gate-interleaved rows n' = 4*unit + gate: -log2(e) for i, f, o and -2 log2(e) for g, so that the
+    gate accumulator is directly the ex2 argument of  sigma(x) = 1/(1 + 2^(-log2e x)),  tanh(x) = 2/(1 + 2^(-2 log2e x)) - 1."""
+    return torch.tensor([-LOG2E, -LOG2E, -2.0 * LOG2E, -LOG2E], device=device, dtype=dtype).repeat(64)
+
+
 def pack_decoder_tcx(lstm_pack, dec_pack):
     """Operands of the fp16-split tcgen05 decode kernel (csrc/decode_fwd_tcx.cu):
-    w16   fp16 [81408]: for W1h [160 n][64 k], W34 [16 (2 real)][80], Whh [256 n'][64]: canonical hi block then canonical
-          lo block (x = hi + lo); W2 [80][160]: ONE canonical block of 160 rows = hi rows then lo rows
+    w16   fp16 [82944]: W1h [160 n][64 k] and Whh [256 n'][64] as canonical hi block then canonical lo block (x = hi + lo);
+          W2 [80][160]: ONE canonical block of 160 rows = hi rows then lo rows; then the x-feedback K block of the gate MMA
+          [2 chunks][256 n'][8]: k 0..3 Wx_hi, 4..7 Wx_hi, 8..11 Wx_lo, 12 b_hi, 13 b_lo, 14..15 zero (the kernel's A row is
+          [x_hi | x_lo | x_hi | 1 | 1 | 0 0]).  The gate rows (Whh, Wx, b) carry the ex2 prescale (`_gate_prescale`).
     wsz16 fp16 [3][2][4][160][8]: the hoisted rows of W1 (S: k 0..63, z: 64..95) in three K = 32 chunks, hi | lo
-    f32   [1696]: wx4 [256 n'][4] | bL [256] | b1 [160] | b2 [80] | b34 [2] | pad | W34 [80 k][2] (fp32: the folded
-          80 -> 2 output layer runs as FMAs inside the layer-2 epilogue)"""
+    f32   [416]: b1 [160] | b2 [80] | b34 [2] | pad | W34 [80 k][2] (fp32: the folded 80 -> 2 output layer runs as FMAs
+          inside the layer-2 epilogue)"""
     w1 = dec_pack[:25600].view(160, 160).t()                  # [n, k], k order {h, S, z}
     b1 = dec_pack[25600:25760]
     w2 = dec_pack[25760:38560].view(160, 80).t()
     b2 = dec_pack[38560:38640]
-    w34 = dec_pack[38640:38800].view(80, 2).t()
     b34 = dec_pack[38800:38802]
-    w34p = torch.zeros(16, 80, device=dec_pack.device, dtype=dec_pack.dtype)
-    w34p[:2] = w34
-    whh = lstm_pack[4:68].t()
+    scale = _gate_prescale(lstm_pack.device, lstm_pack.dtype)
+    whh = lstm_pack[4:68].t() * scale[:, None]                # [256 n', 64]
+    wx = lstm_pack[0:4].t() * scale[:, None]                  # [256 n', 4]
+    bl = lstm_pack[68] * scale                                # [256]
     parts = []
-    for name, m in (("w1h", w1[:, :64]), ("w2", w2), ("w34", w34p), ("whh", whh)):
+    for name, m in (("w1h", w1[:, :64]), ("w2", w2), ("whh", whh)):
         hi, lo = _split_f16(m.contiguous())
         if name == "w2":        # hi and lo rows stacked along N: one N = 160 MMA pass covers a1.W2_hi and a1.W2_lo
             parts.append(_canonical_kmajor(torch.cat([hi, lo], dim=0)))
         else:
             parts += [_canonical_kmajor(hi), _canonical_kmajor(lo)]
+    wx_hi, wx_lo = _split_f16(wx.contiguous())
+    bl_hi, bl_lo = _split_f16(bl.contiguous())
+    zero = torch.zeros(256, 2, device=wx.device, dtype=torch.float16)
+    parts.append(_canonical_kmajor(torch.cat([wx_hi, wx_hi, wx_lo, bl_hi[:, None], bl_lo[:, None], zero], dim=1)))
     w16 = torch.cat(parts).contiguous()
     chunks = []
     for ch in range(3):
         hi, lo = _split_f16(w1[:, 64 + 32 * ch:64 + 32 * (ch + 1)].contiguous())
         chunks += [_canonical_kmajor(hi), _canonical_kmajor(lo)]
     wsz16 = torch.cat(chunks).contiguous()
-    f32 = torch.cat([lstm_pack[0:4].t().reshape(-1), lstm_pack[68], b1, b2, b34, b34.new_zeros(14),
-                     dec_pack[38640:38800]]).contiguous()
+    f32 = torch.cat([b1, b2, b34, b34.new_zeros(14), dec_pack[38640:38800]]).contiguous()
     return w16, wsz16, f32
 
 
