@@ -176,56 +176,94 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row0 = (long long)tile * X_ROWS;
         const bool valid = row0 + r < n_rows;
-        const int agent = valid ? (int)((row0 + r) % n_agents) : 0;
-        // ---------------- tile prologue: every global load of the tile is issued up front (one exposed latency, not five),
-        //                  and the hoist weight chunk ch+1 is in flight while the MMAs of chunk ch run ----------------
-        float4 hq[4], cq4[4];
-        float2 szv[12], xl = make_float2(0.f, 0.f);
+        const int abase = (int)(row0 % n_agents);               // agent of tile row j = (abase + j) % n_agents (32-bit)
+        const int agent = valid ? (abase + r) % n_agents : 0;
+        // ---------------- tile prologue.  Every global load of the tile is issued up front, and every load is COALESCED:
+        //   a warp instruction reads whole 128-byte lines (the row-per-lane loads of the first version cost 32 L1 tag
+        //   lookups per instruction -- 10 K of the 18 K clk of this prologue).  [S ; z] goes through shared memory (S in the
+        //   not-yet-used h operand region, z in the hoist staging buffer, 16-byte pieces XOR-swizzled by row so that both the
+        //   row-contiguous writes and the row-per-lane reads are conflict-free) to reach the thread that owns the row's
+        //   TMEM lane; h0 is loaded as (row, 8-column chunk) items, 8 rows x 128 B per instruction.  c0 is loaded last and
+        //   first used at the end of step 0: its latency and tag traffic hide under the hoist and step-0 MMAs. --------------
         uint4 wreg[3];
         const uint4* wsz4 = reinterpret_cast<const uint4*>(wsz16);
         constexpr int CHUNK_U4 = XW_SZ_CHUNK / 8;                         // 1280 uint4 per chunk: 2.5 per thread
 #pragma unroll
         for (int q = 0; q < 3; ++q)
             if (tid + q * X_THREADS < CHUNK_U4) wreg[q] = __ldg(wsz4 + tid + q * X_THREADS);
+        float4 sreg[4], zreg[2], hreg[2][2];
+        float2 xl = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            hq[q] = valid ? __ldg(reinterpret_cast<const float4*>(h0 + (size_t)agent * SW_H + cq * 16) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            cq4[q] = valid ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent * SW_H + cq * 16) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) {                                     // S tile [128][16 pieces]: piece g = tid + 512 i
+            const int g = tid + i * X_THREADS, row = g >> 4, piece = g & 15;
+            sreg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pooled && row0 + row < n_rows)
+                sreg[i] = __ldg(reinterpret_cast<const float4*>(pooled + (size_t)((abase + row) % n_agents) * SW_H) + piece);
         }
 #pragma unroll
-        for (int e = 0; e < 12; ++e) {                                    // [S ; z] (K = 96): this thread owns K 24cq .. 24cq+23
-            const int k = cq * 24 + 2 * e;                                // even; the S | z boundary (64) is even too
-            szv[e] = make_float2(0.f, 0.f);
-            if (valid) {
-                if (k < 64) { if (pooled) szv[e] = __ldg(reinterpret_cast<const float2*>(pooled + (size_t)agent * SW_H + k)); }
-                else szv[e] = __ldg(reinterpret_cast<const float2*>(noise + (size_t)(row0 + r) * SW_Z + (k - 64)));
+        for (int i = 0; i < 2; ++i) {                                     // z tile [128][8 pieces]
+            const int g = tid + i * X_THREADS, row = g >> 3, piece = g & 7;
+            zreg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + row < n_rows) zreg[i] = __ldg(reinterpret_cast<const float4*>(noise + (size_t)(row0 + row) * SW_Z) + piece);
+        }
+        const int hrow = warp * 8 + (lane & 7);                           // h0 items: (row, chunk = (lane >> 3) + 4 i)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            hreg[i][0] = hreg[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + hrow < n_rows) {
+                const float4* src = reinterpret_cast<const float4*>(h0 + (size_t)((abase + hrow) % n_agents) * SW_H) + ((lane >> 3) + 4 * i) * 2;
+                hreg[i][0] = __ldg(src);
+                hreg[i][1] = __ldg(src + 1);
             }
         }
         if (cq == 1 && valid) xl = __ldg(reinterpret_cast<const float2*>(x_last + (size_t)agent * 4));
-        {   // h0 -> hi|lo operand chunks (columns 16cq .. 16cq+15 of this row)
-            const float v[16] = {hq[0].x, hq[0].y, hq[0].z, hq[0].w, hq[1].x, hq[1].y, hq[1].z, hq[1].w,
-                                 hq[2].x, hq[2].y, hq[2].z, hq[2].w, hq[3].x, hq[3].y, hq[3].z, hq[3].w};
+        {
+            float4* sS = reinterpret_cast<float4*>(s.h);                  // [128 rows][16 pieces], piece' = piece ^ (row & 7)
+            float4* sZ = reinterpret_cast<float4*>(s.stage);              // [128 rows][8 pieces],  piece' = piece ^ (row & 7)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) split2(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1], hi[e], lo[e]);
-                const size_t off = ((size_t)(cq * 2 + j) * X_ROWS + r) * 8;
-                *reinterpret_cast<uint4*>(s.h[0] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(s.h[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int i = 0; i < 4; ++i) {
+                const int g = tid + i * X_THREADS, row = g >> 4, piece = g & 15;
+                sS[row * 16 + (piece ^ (row & 7))] = sreg[i];
             }
-        }
-        float c[16] = {cq4[0].x, cq4[0].y, cq4[0].z, cq4[0].w, cq4[1].x, cq4[1].y, cq4[1].z, cq4[1].w,
-                       cq4[2].x, cq4[2].y, cq4[2].z, cq4[2].w, cq4[3].x, cq4[3].y, cq4[3].z, cq4[3].w};
-        float p0 = xl.x, p1 = xl.y;
-        {   // [S ; z] -> hi|lo TMEM A operand in R1: hi columns [160,208), lo [208,256)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int g = tid + i * X_THREADS, row = g >> 3, piece = g & 7;
+                sZ[row * 8 + (piece ^ (row & 7))] = zreg[i];
+            }
+            __syncthreads();
+            // [S ; z] (K = 96): this thread owns K 24cq .. 24cq+23 of its row = pieces 6cq .. 6cq+5 (S: 0..15, z: 16..23)
+            // -> hi|lo TMEM A operand in R1: hi columns [160,208), lo [208,256)
             uint32_t hi[12], lo[12];
 #pragma unroll
-            for (int e = 0; e < 12; ++e) split2(szv[e].x, szv[e].y, hi[e], lo[e]);
+            for (int e = 0; e < 6; ++e) {
+                const int piece = cq * 6 + e;
+                const float4 v = piece < 16 ? sS[r * 16 + (piece ^ (r & 7))] : sZ[r * 8 + ((piece - 16) ^ (r & 7))];
+                split2(v.x, v.y, hi[2 * e], lo[2 * e]);
+                split2(v.z, v.w, hi[2 * e + 1], lo[2 * e + 1]);
+            }
             tmem_st<12>(tl + XC_R1 + cq * 12, hi);
             tmem_st<12>(tl + XC_R1 + 48 + cq * 12, lo);
             ptx::tcgen05_wait_st();
+            __syncthreads();                                              // the h region / staging buffer get their real contents now
         }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                                     // h0 -> hi|lo operand chunks [chunk][row][8]
+            uint32_t hi[4], lo[4];
+            split2(hreg[i][0].x, hreg[i][0].y, hi[0], lo[0]);
+            split2(hreg[i][0].z, hreg[i][0].w, hi[1], lo[1]);
+            split2(hreg[i][1].x, hreg[i][1].y, hi[2], lo[2]);
+            split2(hreg[i][1].z, hreg[i][1].w, hi[3], lo[3]);
+            const size_t off = ((size_t)((lane >> 3) + 4 * i) * X_ROWS + hrow) * 8;
+            *reinterpret_cast<uint4*>(s.h[0] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(s.h[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        float4 cq4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            cq4[q] = valid ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent * SW_H + cq * 16) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float c[16] = {cq4[0].x, cq4[0].y, cq4[0].z, cq4[0].w, cq4[1].x, cq4[1].y, cq4[1].z, cq4[1].w,
+                       cq4[2].x, cq4[2].y, cq4[2].z, cq4[2].w, cq4[3].x, cq4[3].y, cq4[3].z, cq4[3].w};
+        float p0 = xl.x, p1 = xl.y;
         // c1 = [S ; z] . W1[S,z rows]^T accumulated into TMEM [0,160): three K = 32 chunks of streamed weights
         for (int ch = 0; ch < 3; ++ch) {
 #pragma unroll
