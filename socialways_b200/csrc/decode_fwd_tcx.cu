@@ -70,8 +70,8 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 // three-pass product with both operands in shared memory (called by the whole issuing warp)
 template <int B_ROWS, int N, int KB>
 __device__ __forceinline__ void mma3_ss(uint32_t d, const __half* a_hi, const __half* a_lo, const __half* b_hi,
-                                        const __half* b_lo, bool leader) {
-    umma_ss<B_ROWS, N, KB>(d, a_hi, b_hi, FMT_F16, false, leader);
+                                        const __half* b_lo, bool leader, bool accumulate_first = false) {
+    umma_ss<B_ROWS, N, KB>(d, a_hi, b_hi, FMT_F16, accumulate_first, leader);
     umma_ss<B_ROWS, N, KB>(d, a_hi, b_lo, FMT_F16, true, leader);
     umma_ss<B_ROWS, N, KB>(d, a_lo, b_hi, FMT_F16, true, leader);
 }
@@ -259,8 +259,9 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
         }
         float4 cq4[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-            cq4[q] = valid ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent * SW_H + cq * 16) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int q = 0; q < 4; ++q)     // cell state of this thread's units: c[0..7] = units 32 + 8cq .. (round 0), c[8..15] = units 8cq ..
+            cq4[q] = valid ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent * SW_H + (q < 2 ? 32 : 0) + cq * 8) + (q & 1))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
         float c[16] = {cq4[0].x, cq4[0].y, cq4[0].z, cq4[0].w, cq4[1].x, cq4[1].y, cq4[1].z, cq4[1].w,
                        cq4[2].x, cq4[2].y, cq4[2].z, cq4[2].w, cq4[3].x, cq4[3].y, cq4[3].z, cq4[3].w};
         float p0 = xl.x, p1 = xl.y;
@@ -293,15 +294,15 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
         }
         ptx::tcgen05_fence_before_thread_sync();
         __syncthreads();
+        if (warp == 0) {    // layer 1 of step 0 (the later steps' layer-1 MMAs are issued from inside the previous gate epilogue)
+            ptx::tcgen05_fence_after_thread_sync();
+            mma3_ss<160, 160, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_W1H_HI, s.w + XW_W1H_LO, leader);
+            umma_commit(&s.bar[0], leader);
+        }
 
         for (int t = 0; t < n_next; ++t) {
             const bool feed_back = t + 1 < n_next;
             // ---------------- layer 1: h (K = 64, smem) -> 160 in R1; column quarters own 3, 3, 2, 2 K-blocks of a1 ----------------
-            if (warp == 0) {
-                ptx::tcgen05_fence_after_thread_sync();
-                mma3_ss<160, 160, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_W1H_HI, s.w + XW_W1H_LO, leader);
-                umma_commit(&s.bar[0], leader);
-            }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
             {
@@ -312,6 +313,8 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
             // ---------------- layer 2: a1 (K = 160, TMEM, K block kb at column 16 kb) -> 80 in [320,400) ----------------
+            // (Issuing these MMAs per K block from inside the layer-1 epilogue, so that layer 2 runs under it, was measured: no
+            //  gain -- 0.812 vs 0.806 ms per step -- the TMEM-operand MMAs and the epilogue's tcgen05.ld/st share the TMEM ports.)
             if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
                 // W2 hi and lo rows are stacked along N ([20 chunks][hi 80 | lo 80 rows][8]): one N = 160 pass yields a1_hi.W2_hi
@@ -366,41 +369,48 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
                 umma_ss<256, 128, 1>(tmem + XC_RG, s.xk, s.w + XW_WXK, FMT_F16, true, leader);
                 umma_commit(&s.bar[1], leader);
             }
-            // ---------------- LSTM cell on the two gate halves (column quarters 0,1 -> half 0; 2,3 -> half 1) ----------------
-            if (cq < 2) mbar_wait(&s.bar[1], ph1); else mbar_wait(&s.bar[2], ph1);
-            ptx::tcgen05_fence_after_thread_sync();
-            {
-                const uint32_t gbase = tl + ((cq < 2) ? XC_RG : XC_R1) + (cq & 1) * 64;
+            // ---------------- LSTM cell.  EVERY quarter first updates 8 units of gate half 1 (units 32 + 8cq .., ready early:
+            //                  its h part ran under the epilogues) while the tensor pipe works on half 0, then 8 units of half 0
+            //                  (units 8cq ..).  After each round the finished half of h (K blocks 2,3 / 0,1) goes straight into the
+            //                  NEXT step's layer-1 MMAs, so half of layer 1 runs under the second round. ----------------
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t a[32];
-                    tmem_ld<32>(gbase + half * 32, a);
-                    ptx::tcgen05_wait_ld();
-                    float hv[8];
+            for (int round = 0; round < 2; ++round) {
+                if (round == 0) mbar_wait(&s.bar[2], ph1); else mbar_wait(&s.bar[1], ph1);
+                ptx::tcgen05_fence_after_thread_sync();
+                uint32_t a[32];
+                tmem_ld<32>(tl + (round == 0 ? XC_R1 : XC_RG) + cq * 32, a);
+                ptx::tcgen05_wait_ld();
+                float hv[8];
 #pragma unroll
-                    for (int u = 0; u < 8; u += 2) {
-                        float g[2][4];
+                for (int u = 0; u < 8; u += 2) {
+                    float g[2][4];
 #pragma unroll
-                        for (int w2 = 0; w2 < 2; ++w2)
+                    for (int w2 = 0; w2 < 2; ++w2)
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) g[w2][q] = __uint_as_float(a[(u + w2) * 4 + q]);
-                        lstm_cell_pair_prescaled(g[0], g[1], c[half * 8 + u], c[half * 8 + u + 1], hv[u], hv[u + 1]);
-                    }
-                    uint32_t hi[4], lo[4];
+                        for (int q = 0; q < 4; ++q) g[w2][q] = __uint_as_float(a[(u + w2) * 4 + q]);
+                    lstm_cell_pair_prescaled(g[0], g[1], c[round * 8 + u], c[round * 8 + u + 1], hv[u], hv[u + 1]);
+                }
+                uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) split2(hv[2 * e], hv[2 * e + 1], hi[e], lo[e]);
-                    // h is an operand of the half-0 gate MMAs: quarters 2,3 (released by bar2) must not overwrite it before
-                    // those MMAs have completed (bar1; long done by now -- the wait is a formality that closes the race)
-                    if (half == 0 && cq >= 2) mbar_wait(&s.bar[1], ph1);
-                    const size_t off = ((size_t)(cq * 2 + half) * X_ROWS + r) * 8;
-                    *reinterpret_cast<uint4*>(s.h[0] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(s.h[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                for (int e = 0; e < 4; ++e) split2(hv[2 * e], hv[2 * e + 1], hi[e], lo[e]);
+                // h is an operand of the half-0 gate MMAs: nothing may overwrite it before they have completed (bar1; done
+                // long before round 0 has finished its arithmetic -- the wait closes the race, it does not cost time)
+                if (round == 0) mbar_wait(&s.bar[1], ph1);
+                const size_t off = ((size_t)((round == 0 ? 4 : 0) + cq) * X_ROWS + r) * 8;
+                *reinterpret_cast<uint4*>(s.h[0] + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                *reinterpret_cast<uint4*>(s.h[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                ptx::fence_proxy_async(ptx::space_shared);
+                ptx::tcgen05_fence_before_thread_sync();
+                __syncthreads();
+                if (warp == 0) {   // next step's layer 1, the two K blocks whose h chunks are complete
+                    ptx::tcgen05_fence_after_thread_sync();
+                    const int kb0 = round == 0 ? 2 : 0;
+                    mma3_ss<160, 160, 2>(tmem + XC_R1, s.h[0] + kb0 * 2 * X_ROWS * 8, s.h[1] + kb0 * 2 * X_ROWS * 8,
+                                         s.w + XW_W1H_HI + kb0 * 2 * 160 * 8, s.w + XW_W1H_LO + kb0 * 2 * 160 * 8, leader, round == 1);
+                    if (round == 1) umma_commit(&s.bar[0], leader);
                 }
             }
             ph1 ^= 1;
-            ptx::fence_proxy_async(ptx::space_shared);
-            ptx::tcgen05_fence_before_thread_sync();
-            __syncthreads();
         }
     }
     ptx::tcgen05_fence_before_thread_sync();
