@@ -123,16 +123,16 @@ __device__ __forceinline__ void fold_bias_into_c1(uint32_t t_c1, const float* __
 // Epilogue of layer 2 fused with the folded 80 -> 2 output layer: y = lrelu(acc + b2) stays in registers and is
 // contracted with W34 in fp32 FMAs (2 per column); the per-quarter partial velocities meet in shared memory.
 // No a2 operand, no extra MMA round trip for a 160-MAC-per-row layer.
-template <int NKB>
+template <int NC>
 __device__ __forceinline__ void output_epilogue(uint32_t t_acc, const float* __restrict__ bias, const float2* __restrict__ w34,
                                                 float& v0, float& v1) {
     v0 = 0.0f; v1 = 0.0f;
-    uint32_t acc[NKB * 16], acc2[NKB * 16];
-    tmem_ld<NKB * 16>(t_acc, acc);               // a1_hi.W2_hi + a1_lo.W2_hi
-    tmem_ld<NKB * 16>(t_acc + 80, acc2);         // a1_hi.W2_lo
+    uint32_t acc[NC], acc2[NC];
+    tmem_ld<NC>(t_acc, acc);                     // a1_hi.W2_hi + a1_lo.W2_hi
+    tmem_ld<NC>(t_acc + 80, acc2);               // a1_hi.W2_lo
     ptx::tcgen05_wait_ld();
 #pragma unroll
-    for (int j = 0; j < NKB * 16; ++j) {
+    for (int j = 0; j < NC; ++j) {
         const float y = lrelu02(__uint_as_float(acc[j]) + __uint_as_float(acc2[j]) + bias[j]);
         const float2 w = w34[j];
         v0 = fmaf(y, w.x, v0);
@@ -329,12 +329,11 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
-            {   // layer-2 epilogue + folded layers 3+4 (80 -> 2) on CUDA cores: partial velocity of this column quarter
-                const int col0 = (cq == 0) ? 0 : 16 + cq * 16;
+            {   // layer-2 epilogue + folded layers 3+4 (80 -> 2) on CUDA cores: partial velocity of this column quarter (20 columns)
+                const int col0 = cq * 20;
                 const float2* w34 = reinterpret_cast<const float2*>(s.f32 + XF_W34) + col0;
                 float v0, v1;
-                if (cq == 0) output_epilogue<2>(tl + XC_RG + col0, s.f32 + XF_B2 + col0, w34, v0, v1);
-                else         output_epilogue<1>(tl + XC_RG + col0, s.f32 + XF_B2 + col0, w34, v0, v1);
+                output_epilogue<20>(tl + XC_RG + col0, s.f32 + XF_B2 + col0, w34, v0, v1);
                 s.vpart[(cq * 2 + 0) * X_ROWS + r] = v0;
                 s.vpart[(cq * 2 + 1) * X_ROWS + r] = v1;
             }
