@@ -156,6 +156,26 @@ int sw_disc_heads_bwd(const float* pack, const float* xrec, int pred_dim, int n_
 int sw_bestofk_metrics(const float* pred, const float* gt, float ss, int n_agents, int n_samples,
                        int n_next, float* out, void* stream);
 
+/* Sample-set statistics of calc_statistics.py.  Samples are [n][n_ped][t_len][2] arrays of fp32
+ * (dtype_bytes 4) or fp64 (8) device data -- numpy's dtype decides the arithmetic there, so it does here; the distance
+ *   d(a, b) = mean_{t >= obsv_len} || a_t - b_t ||_2   (calc_statistics.py:31-32, :56-57)
+ * is evaluated in numpy's operation order (bit-identical matrices).
+ *
+ * sw_traj_nn1_counts: replaces compute_1nn's loops (calc_statistics.py:17-45).  counts[4] (device int32, zeroed by the
+ *   call) = (Real_pos, Real_neg, Fake_pos, Fake_neg) summed over pedestrians; np.argmin's first-minimum rule.
+ * sw_traj_emd_cost: replaces the cost-matrix loop of compute_wasserstein (calc_statistics.py:53-58) including its
+ *   mirrored write (the matrix the solver sees is C[max(a,b)][min(a,b)]); cost [n_ped][n][n] fp64.
+ * sw_lsap_solve: replaces scipy.optimize.linear_sum_assignment (calc_statistics.py:60; scipy is a third-party
+ *   dependency of the reference, version unpinned) for square problems: cost [n_problems][n][n] fp64,
+ *   col4row [n_problems][n] out (column assigned to each row, scipy's tie-breaking), *status = 1 if any problem
+ *   is infeasible.  One warp per problem; sw_lsap_smem_bytes(n) of shared memory bounds n (<= ~4800). */
+int sw_traj_nn1_counts(const void* reals, const void* fakes, int dtype_bytes, int n_reals, int n_fakes, int n_ped,
+                       int t_len, int obsv_len, int* counts, void* stream);
+int sw_traj_emd_cost(const void* reals, const void* fakes, int dtype_bytes, int n, int n_ped, int t_len, int obsv_len,
+                     double* cost, void* stream);
+int sw_lsap_smem_bytes(int n);
+int sw_lsap_solve(const double* cost, int n, int n_problems, int* col4row, int* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -36,6 +36,10 @@ _PROTOTYPES = {
     "sw_disc_heads_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "sw_disc_heads_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "sw_bestofk_metrics": (_I, [_P, _P, _F, _I, _I, _I, _P, _P]),
+    "sw_traj_nn1_counts": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "sw_traj_emd_cost": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
+    "sw_lsap_smem_bytes": (_I, [_I]),
+    "sw_lsap_solve": (_I, [_P, _I, _I, _P, _P, _P]),
 }
 
 _lib = None
