@@ -176,6 +176,22 @@ int sw_traj_emd_cost(const void* reals, const void* fakes, int dtype_bytes, int 
 int sw_lsap_smem_bytes(int n);
 int sw_lsap_solve(const double* cost, int n, int n_problems, int* col4row, int* status, void* stream);
 
+/* Optimiser step on ONE flat fp32 buffer.  Replaces torch.optim.Adam.step() of the optimisers
+ * built at train.py:381,385 (called at :496, :539); same update rule and operation order, step count `step` (one device
+ * float, advanced by the call: safe to replay from a CUDA graph); hyper-parameters are the python doubles torch receives.
+ *   sw_adam_flat: params, grads, exp_avg, exp_avg_sq [n].
+ *   sw_allreduce_adam: additionally replaces the gradient all-reduce of the sharded step (one NCCL call per optimiser step
+ *     otherwise).  peer_bufs_dev = device array of `world` pointers to every rank's SYMMETRIC buffer laid out
+ *     [n_pad floats of gradient | uint32 ready[world] | uint32 done[world]] (flags zero-initialised, n_pad % 32 == 0);
+ *     params / exp_avg / exp_avg_sq are n_pad floats (zero padded); seq = 2 device uint32 (zero-initialised).  Gradients are
+ *     summed with peer loads over NVLink in rank order on every rank (bit-identical replicas); the call returns once
+ *     every peer has finished reading this rank's gradients.  Every rank must make the call (same order). */
+int sw_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step, int n, double lr,
+                 double beta1, double beta2, double eps, int sm_count, void* stream);
+int sw_allreduce_adam(const void* peer_bufs_dev, int rank, int world, int n, int n_pad, float* params, float* exp_avg,
+                      float* exp_avg_sq, float* step, unsigned* seq, double lr, double beta1, double beta2, double eps,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libsocialways_b200.so")
 _P = ctypes.c_void_p
 _I = ctypes.c_int
 _F = ctypes.c_float
+_D = ctypes.c_double
 
 _PROTOTYPES = {
     "sw_abi_version": (_I, []),
@@ -40,6 +41,8 @@ _PROTOTYPES = {
     "sw_traj_emd_cost": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "sw_lsap_smem_bytes": (_I, [_I]),
     "sw_lsap_solve": (_I, [_P, _I, _I, _P, _P, _P]),
+    "sw_adam_flat": (_I, [_P, _P, _P, _P, _P, _I, _D, _D, _D, _D, _I, _P]),
+    "sw_allreduce_adam": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _D, _D, _D, _D, _P]),
 }
 
 _lib = None

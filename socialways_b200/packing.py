@@ -87,7 +87,9 @@ LOG2E = 1.4426950408889634
 def _gate_prescale(device, dtype):
     """[256] scale of the gate-interleaved rows n' = 4*unit + gate: -log2(e) for i, f, o and -2 log2(e) for g, so that the
     gate accumulator is directly the ex2 argument of  sigma(x) = 1/(1 + 2^(-log2e x)),  tanh(x) = 2/(1 + 2^(-2 log2e x)) - 1."""
-    return torch.tensor([-LOG2E, -LOG2E, -2.0 * LOG2E, -LOG2E], device=device, dtype=dtype).repeat(64)
+    s = torch.full((64, 4), -LOG2E, device=device, dtype=dtype)      # device-side fills only: legal inside a CUDA-graph capture
+    s[:, 2] = -2.0 * LOG2E
+    return s.reshape(256)
 
 
 def pack_decoder_tcx(lstm_pack, dec_pack):

@@ -235,9 +235,11 @@ class Discriminator(nn.Module):
         """train.py:311-316: restores the nn.Linear layers ONLY (the LSTM is not rolled back)."""
         for m_from, m_to in zip(backup.modules(), self.modules()):
             if isinstance(m_to, nn.Linear):
-                m_to.weight.data = m_from.weight.data.clone()
+                # same values as the reference's `.data = clone()` rebinding, written in place so that parameters that
+                # live inside a flat optimiser buffer (fused_optim.FlatAdam) keep their storage
+                m_to.weight.data.copy_(m_from.weight.data)
                 if m_to.bias is not None:
-                    m_to.bias.data = m_from.bias.data.clone()
+                    m_to.bias.data.copy_(m_from.bias.data)
 
 
 class Generator(nn.Module):

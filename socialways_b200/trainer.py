@@ -26,7 +26,7 @@ from .scale import Scale
 class SocialWaysTrainer:
     def __init__(self, data, batch_size=256, hidden_size=64, use_social=False, n_unrolling_steps=1,
                  lr_g=1e-4, lr_d=1e-3, device="cuda", weights=None, n_latent_codes=2,
-                 use_info_loss=True, loss_info_w=0.5, world=None, cuda_graph=False):
+                 use_info_loss=True, loss_info_w=0.5, world=None, cuda_graph=False, fused_adam=False):
         self.device = torch.device(device)
         self.batch_size, self.n_unrolling_steps = batch_size, n_unrolling_steps
         self.use_info_loss, self.loss_info_w, self.n_latent_codes = use_info_loss, loss_info_w, n_latent_codes
@@ -64,11 +64,23 @@ class SocialWaysTrainer:
         self.noise_len = hidden_size // 2
         self.cuda_graph = cuda_graph
         self._graphs = {}
-        extra = dict(capturable=True) if cuda_graph else {}
-        self.predictor_optimizer = opt.Adam(self.generator.optimizer_parameters(), lr=lr_g, betas=(0.9, 0.999), **extra)
-        self.D_optimizer = opt.Adam(self.D.parameters(), lr=lr_d, betas=(0.9, 0.999), **extra)
-        self.mse_loss = nn.MSELoss()
         self.world_size, self.rank = swdist.world() if world is None else world
+        self.fused_adam = fused_adam
+        if fused_adam:
+            # one flat buffer per optimiser; step() = ONE kernel that also sums the gradients over the ranks through NVLink
+            # peer memory (fused_optim.FlatAdam / csrc/flat_adam.cu) -- no NCCL call inside the iteration
+            from .fused_optim import FlatAdam
+            group = None
+            if self.world_size > 1:
+                import torch.distributed as dist
+                group = dist.group.WORLD
+            self.predictor_optimizer = FlatAdam(self.generator.optimizer_parameters(), lr=lr_g, betas=(0.9, 0.999), group=group)
+            self.D_optimizer = FlatAdam(self.D.parameters(), lr=lr_d, betas=(0.9, 0.999), group=group)
+        else:
+            extra = dict(capturable=True) if cuda_graph else {}
+            self.predictor_optimizer = opt.Adam(self.generator.optimizer_parameters(), lr=lr_g, betas=(0.9, 0.999), **extra)
+            self.D_optimizer = opt.Adam(self.D.parameters(), lr=lr_d, betas=(0.9, 0.999), **extra)
+        self.mse_loss = nn.MSELoss()
         self.epoch = 1
         self.loss_log = []
 
@@ -90,6 +102,14 @@ class SocialWaysTrainer:
         if not torch.is_grad_enabled():
             return self.generator.predict_k(obsv_p, noise.unsqueeze(0), n_next, sub_batches, precision="fp32")[0]
         return self.generator.predict(obsv_p, noise, n_next, sub_batches)
+
+    def _zero_grad_D(self, set_to_none=False):
+        if self.fused_adam:
+            self.D_optimizer.zero_grad()          # one memset; the gradient views into the flat buffer stay
+        elif set_to_none:
+            self.D.zero_grad(set_to_none=True)
+        else:
+            self.D.zero_grad()
 
     # ------------------------------------------------------------------ train.py:439-560
     def train(self, verbose=True):
@@ -122,7 +142,7 @@ class SocialWaysTrainer:
                 backup = None
                 # ============== Train Discriminator ================ :476-499
                 for u in range(self.n_unrolling_steps + 1):
-                    D.zero_grad()
+                    self._zero_grad_D()
                     if have_rows:
                         with torch.no_grad():
                             pred_hat_4d = self.predict(obsv, noise, self.n_next, sub_batches)
@@ -137,12 +157,13 @@ class SocialWaysTrainer:
                         if self.use_info_loss:
                             d_loss = d_loss + self.loss_info_w * d_loss_info
                         d_loss.backward()
-                    swdist.allreduce_grads(D.parameters(), self.world_size)
+                    if not self.fused_adam:
+                        swdist.allreduce_grads(D.parameters(), self.world_size)
                     self.D_optimizer.step()
                     if u == 0 and self.n_unrolling_steps > 0:
                         backup = copy.deepcopy(D)
                 # =============== Train Generator ================= :501-543
-                D.zero_grad()
+                self._zero_grad_D()
                 self.predictor_optimizer.zero_grad()
                 if have_rows:
                     pred_hat_4d = self.predict(obsv, noise, self.n_next, sub_batches)
@@ -156,7 +177,8 @@ class SocialWaysTrainer:
                     if self.use_info_loss:
                         g_loss = g_loss + self.loss_info_w * g_loss_info
                     g_loss.backward()
-                swdist.allreduce_grads(list(self.generator.optimizer_parameters()), self.world_size)
+                if not self.fused_adam:
+                    swdist.allreduce_grads(list(self.generator.optimizer_parameters()), self.world_size)
                 self.predictor_optimizer.step()
                 if self.n_unrolling_steps > 0:
                     D.load(backup)
@@ -197,7 +219,7 @@ class SocialWaysTrainer:
         obsv_4d, pred_4d = get_traj_4d(obsv, pred)
         lin = [p for m in D.modules() if isinstance(m, nn.Linear) for p in (m.weight, m.bias)]
         for u in range(self.n_unrolling_steps + 1):
-            D.zero_grad(set_to_none=True)
+            self._zero_grad_D(set_to_none=True)
             with torch.no_grad():
                 pred_hat_4d = self.predict(obsv, noise, self.n_next, scenes)
             obsv_h = D.encode_obsv(obsv_4d)
@@ -208,13 +230,14 @@ class SocialWaysTrainer:
             d_real = mse_loss(real_labels, ones)
             d_loss = d_fake + d_real + (self.loss_info_w * d_info if self.use_info_loss else 0.0)
             d_loss.backward()
-            swdist.allreduce_grads(D.parameters(), self.world_size)
+            if not self.fused_adam:
+                swdist.allreduce_grads(D.parameters(), self.world_size)
             self.D_optimizer.step()
             if u == 0 and self.n_unrolling_steps > 0:
                 with torch.no_grad():
                     for b, p in zip(st["backup"], lin):
                         b.copy_(p)
-        D.zero_grad(set_to_none=True)
+        self._zero_grad_D(set_to_none=True)
         self.predictor_optimizer.zero_grad(set_to_none=True)
         pred_hat_4d = self.predict(obsv, noise, self.n_next, scenes)
         with torch.no_grad():
@@ -224,7 +247,8 @@ class SocialWaysTrainer:
         g_info = mse_loss(code_hat, noise[:, :nl])
         g_loss = g_fool + (self.loss_info_w * g_info if self.use_info_loss else 0.0)
         g_loss.backward()
-        swdist.allreduce_grads(list(self.generator.optimizer_parameters()), self.world_size)
+        if not self.fused_adam:
+            swdist.allreduce_grads(list(self.generator.optimizer_parameters()), self.world_size)
         self.predictor_optimizer.step()
         with torch.no_grad():
             if self.n_unrolling_steps > 0:                                   # D.load(backup): Linear layers only
@@ -239,10 +263,11 @@ class SocialWaysTrainer:
         ~10 ms/iteration of Python + launch overhead that bounds small batches).  Needs optimisers built with
         capturable=True (constructor flag cuda_graph=True) and world_size 1.  The first occurrence of a batch
         shape runs eagerly (it also warms up the lazily-initialised optimiser state), the second is captured."""
-        if not self.cuda_graph or self.world_size != 1:
+        if not self.cuda_graph or (self.world_size != 1 and not self.fused_adam):
             # capturing the NCCL all-reduces of the sharded step was tried (torch 2.11 / NCCL 2.28) and hung in capture;
-            # multi-GPU training uses the eager train() until that is resolved
-            raise RuntimeError("train_graphed() needs cuda_graph=True and a single process; use train() for multi-GPU runs")
+            # the sharded step is captured with fused_adam=True instead: its optimiser kernel does the gradient exchange
+            # itself over NVLink peer memory (csrc/flat_adam.cu), so the graph holds plain kernels only
+            raise RuntimeError("train_graphed() needs cuda_graph=True, and fused_adam=True for multi-GPU runs")
         tic = time.perf_counter()
         dev = self.device
         stats_acc = torch.zeros(8, device=dev, dtype=torch.float64)

@@ -28,15 +28,20 @@ def main():
     data = synthetic_scenes(list(rng.randint(1, 9, size=60)), seed=8)
     W = so.init_weights(seed=2)
 
-    def run(w, graph=False):
+    mode = os.environ.get("SW_CHECK_MODE", "nccl")      # nccl | fused (eager, peer-memory all-reduce + Adam) | fused_graph
+    fused, graph_n = mode != "nccl", mode == "fused_graph"
+    epochs = 3 if graph_n else 1                          # graph mode: epoch 1 eager, epoch 2 captures, epoch 3 replays
+
+    def run(w, graph=False, fused=False):
         tr = SocialWaysTrainer(data, batch_size=64, use_social=True, n_unrolling_steps=1, weights=W,
-                               device=f"cuda:{local}", world=w, cuda_graph=graph)
+                               device=f"cuda:{local}", world=w, cuda_graph=graph, fused_adam=fused)
         np.random.seed(5)
         torch.manual_seed(5)
-        ade, fde = (tr.train_graphed if graph else tr.train)(verbose=False)
+        for _ in range(epochs):
+            ade, fde = (tr.train_graphed if graph else tr.train)(verbose=False)
         return tr.reference_weights(), ade, fde
 
-    w_n, ade_n, fde_n = run((world, rank))
+    w_n, ade_n, fde_n = run((world, rank), graph=graph_n, fused=fused)
     ok = True
     # all ranks hold identical weights
     for k, v in w_n.items():
@@ -46,12 +51,12 @@ def main():
             ok = False
             print(f"rank {rank}: {k} differs from rank 0")
     if rank == 0:
-        w_1, ade_1, fde_1 = run((1, 0))
+        w_1, ade_1, fde_1 = run((1, 0))                   # single process, torch.optim.Adam, eager
         worst = max((w_n[k] - w_1[k]).abs().max().item() for k in w_1)
         mean = max((w_n[k] - w_1[k]).abs().mean().item() for k in w_1)
-        print(f"world {world}: max |w_N - w_1| = {worst:.3e}, max mean = {mean:.3e}, "
+        print(f"mode {mode}, world {world}: max |w_N - w_1| = {worst:.3e}, max mean = {mean:.3e}, "
               f"ADE {ade_n:.6f} vs {ade_1:.6f}, FDE {fde_n:.6f} vs {fde_1:.6f}")
-        ok = ok and mean < 2e-5 and abs(ade_n - ade_1) < 1e-4 and abs(fde_n - fde_1) < 1e-4
+        ok = ok and mean < 2e-5 * epochs and abs(ade_n - ade_1) < 1e-4 and abs(fde_n - fde_1) < 1e-4
     flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
