@@ -220,7 +220,10 @@ def run_ours(args):
         ub = torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])
         if timed and headline:
             s2.record()
-        pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
+        if precision == "fp16x2":
+            pooled = ops.pool_tcx(pk["pool"], pk["pool_tcx"], enc["x_last"], enc["h"], ub, scenes)
+        else:
+            pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
         if timed and headline:
             s3.record()
             stage_events.append((s0, s1, s2, s3))
@@ -365,7 +368,8 @@ def run_ours(args):
             # the other kernels of the step, live CUDA-event times (north_star asks for the pairwise kernel's HBM figure;
             # it is compute-bound -- SURVEY.md D9 -- so the fraction is small by construction)
             "secondary_kernels": {
-                "pool_fwd_kernel": {"kernel_ms": pool_ms, "bound": "hbm (as asked; actually compute-bound)",
+                "pool_fwd_tcx_kernel" if args.precision == "fp16x2" else "pool_fwd_kernel": {
+                                    "kernel_ms": pool_ms, "bound": "hbm (as asked; actually compute-bound)",
                                     "algorithmic_bytes": n * 788, "achieved_gbs": n * 788 / (pool_ms * 1e-3) / 1e9,
                                     "peak_gbs": pk_["hbm_gbs"], "frac_of_hbm": n * 788 / (pool_ms * 1e-3) / 1e9 / pk_["hbm_gbs"],
                                     "achieved_tflops_fp32": n * A_PER_SCENE * 4544 / (pool_ms * 1e-3) / 1e12,

@@ -81,6 +81,14 @@ int sw_lstm_seq_bwd(const float* lstm_pack_t, const float* stash_gates, const fl
 int sw_pool_fwd(const float* pool_pack, const float* x_last, const float* h, const float* ub,
                 const int* scene_offsets, const int* agent_scene, float* pooled, float* attn,
                 int n_agents, int max_scene, void* stream);
+/* Same contract, inference only (no attention record), with layer 2 of the pair MLP (32 -> 64, 93 % of the pair's
+ * arithmetic) on the tcgen05 tensor cores: 128 ordered pairs per MMA tile, fp16 hi|lo split operands, fp32 accumulate in
+ * TMEM (~1e-6 of sw_pool_fwd).  pool_w16 = packing.pack_pool_tcx (fp16 [4096]).  Scenes of up to
+ * sw_pool_tcx_max_scene() agents; larger scenes use sw_pool_fwd. */
+int sw_pool_fwd_tcx(const float* pool_pack, const void* pool_w16, const float* x_last, const float* h, const float* ub,
+                    const int* scene_offsets, const int* agent_scene, float* pooled, int n_agents, int max_scene,
+                    void* stream);
+int sw_pool_tcx_max_scene(void);
 
 /* Backward of sw_pool_fwd.  Replaces autograd through AttentionPooling.forward / EmbedSocialFeatures.fc
  * (train.py:160-175,183-188) inside g_loss.backward() (train.py:538).

@@ -132,6 +132,24 @@ def pool(pool_pack, x_last, h, ub, scenes, want_attn=False):
     return (pooled, attn) if want_attn else pooled
 
 
+def pool_tcx_max_scene():
+    return _lib.lib().sw_pool_tcx_max_scene()
+
+
+def pool_tcx(pool_pack, pool_w16, x_last, h, ub, scenes):
+    """sw_pool_fwd_tcx: the pooling kernel with layer 2 of the pair MLP on tcgen05 (fp16 hi/lo split operands,
+    fp32-faithful); inference only, scenes of up to pool_tcx_max_scene() agents."""
+    n = h.shape[0]
+    if pool_w16.dtype != torch.float16 or not pool_w16.is_contiguous() or pool_w16.numel() != 4096:
+        raise ValueError("pool_tcx: pool_w16 must be the contiguous fp16 [4096] pack of packing.pack_pool_tcx")
+    pooled = torch.empty(n, H, device=h.device)
+    code = _lib.lib().sw_pool_fwd_tcx(_lib.ptr(_f32(pool_pack)), pool_w16.data_ptr(), _lib.ptr(_f32(x_last)), _lib.ptr(_f32(h)),
+                                      _lib.ptr(_f32(ub)), _lib.ptr(scenes.offsets), _lib.ptr(scenes.agent_scene),
+                                      _lib.ptr(pooled), n, scenes.max_scene, _stream())
+    _lib.check(code, "sw_pool_fwd_tcx")
+    return pooled
+
+
 def pool_bwd(pool_pack, x_last, h, ub, d_pooled, tdot, attn, scenes):
     """sw_pool_bwd -> (dub [N,65], dh_direct [N,64], per-pair stashes A1 [P,32], G2 [P,64], G1 [P,32], F [P,4])."""
     n, dev, p = h.shape[0], h.device, scenes.n_pairs

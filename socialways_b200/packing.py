@@ -131,6 +131,13 @@ def pack_decoder_tcx(lstm_pack, dec_pack):
     return w16, wsz16, f32
 
 
+def pack_pool_tcx(fc2_w):
+    """Layer-2 operand of the tensor-core pooling kernel (csrc/pool_fwd_tcx.cu): EmbedSocialFeatures.fc.2.weight [64 n][32 k]
+    as canonical hi block then canonical lo block ([4][64][8] each), fp16 [4096]."""
+    hi, lo = _split_f16(fc2_w.contiguous())
+    return torch.cat([_canonical_kmajor(hi), _canonical_kmajor(lo)]).contiguous()
+
+
 def pack_encoder_tcx(lstm_pack):
     """Operands of the tensor-core observation encoder (csrc/lstm_seq_fwd_tcx.cu): Whh [256 n'][64 k] as canonical
     hi | lo fp16 blocks (x = hi + lo), and fp32 [1280] = wx4 [256 n'][4] | bL [256]."""

@@ -279,6 +279,7 @@ class Generator(nn.Module):
                 packs["tc_w16"], packs["tc_f32"] = packing.pack_decoder_tc(packs["enc"], packs["dec"])
                 packs["tcx"] = packing.pack_decoder_tcx(packs["enc"], packs["dec"])
                 packs["enc_tcx"] = packing.pack_encoder_tcx(packs["enc"])
+                packs["pool_tcx"] = packing.pack_pool_tcx(fe[2].weight)
             self._pack_cache = (key, packs)
         return self._pack_cache[1]
 
@@ -313,7 +314,10 @@ class Generator(nn.Module):
         if self.use_social:                                                    # train.py:408-413
             scenes = self.scene_index(sub_batches, n, obsv_p.device)
             ub = torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])
-            pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
+            if precision == "fp16x2" and scenes.max_scene <= ops.pool_tcx_max_scene():
+                pooled = ops.pool_tcx(pk["pool"], pk["pool_tcx"], enc["x_last"], enc["h"], ub, scenes)   # layer 2 on tcgen05
+            else:
+                pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
         if precision == "bf16":
             return ops.decode_tc(pk["tc_w16"], pk["tc_f32"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
         if precision == "fp16x2":

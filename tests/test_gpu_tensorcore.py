@@ -131,3 +131,43 @@ def test_config3_zara_shape_bf16_fast_mode():
     e = (((want[..., :2] - pred) / sc.sx) ** 2).sum(-1).sqrt()
     ref = torch.stack([e.mean(2).mean(0), e[:, :, -1].mean(0), e.mean(2).min(0)[0], e[:, :, -1].min(0)[0]], 1).sum(0)
     assert ((m - ref).abs() / ref).max().item() < 0.02
+
+
+@pytest.mark.parametrize("sizes", [[8] * 40, [1, 2, 6, 8, 5, 3, 1, 1, 9], [32, 31, 33, 32, 7], [64, 1, 63, 20], [3] * 100 + [64]])
+def test_pool_tcx_matches_ffma_pool_and_oracle(sizes):
+    """Pooling kernel with layer 2 on tcgen05 (fp16 hi/lo split) vs the FFMA kernel and the fp32 oracle (closed form)."""
+    import socialways_b200 as sw
+    from socialways_b200 import ops
+    from oracle import socialways_oracle as so
+    P = so.init_weights(seed=8)
+    data = synthetic_scenes(sizes, seed=17)
+    sc = so.IsoScale(data["obsvs"], data["preds"])
+    obsv = torch.from_numpy(sc.normalize(data["obsvs"]))
+    n = obsv.shape[0]
+    gen = sw.Generator(use_social=True)
+    gen.load_state_dict({key: v for key, v in P.items() if not key.startswith("D.")})
+    gen = gen.cuda().requires_grad_(False)
+    pk = gen.packs()
+    enc = ops.lstm_seq(pk["enc"], obsv.cuda(), want_x_last=True)
+    scenes = gen.scene_index(data["batches"], n, torch.device("cuda"))
+    ub = torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])
+    ref = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
+    got = ops.pool_tcx(pk["pool"], pk["pool_tcx"], enc["x_last"], enc["h"], ub, scenes)
+    err = (got - ref).abs().max().item()
+    print(f"pool_tcx vs pool (scenes up to {max(sizes)}): max abs diff {err:.2e}")
+    assert torch.isfinite(got).all() and err < 5e-6
+    want = so.attention_pool_closed(P, enc["x_last"].cpu(), enc["h"].cpu(), data["batches"])
+    assert (got.cpu() - want).abs().max().item() < 2e-5
+
+
+def test_pool_tcx_rejects_scenes_beyond_its_limit():
+    from socialways_b200 import ops
+    from socialways_b200._lib import SocialWaysCudaError
+    import socialways_b200 as sw
+    n = ops.pool_tcx_max_scene() + 1
+    gen = sw.Generator(use_social=True).cuda().requires_grad_(False)
+    pk = gen.packs()
+    scenes = gen.scene_index([(0, n)], n, torch.device("cuda"))
+    z = torch.zeros(n, 64, device="cuda")
+    with pytest.raises(SocialWaysCudaError):
+        ops.pool_tcx(pk["pool"], pk["pool_tcx"], torch.zeros(n, 4, device="cuda"), z, torch.zeros(n, 65, device="cuda"), scenes)
