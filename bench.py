@@ -159,7 +159,8 @@ def run_reference(args):
 
 
 def workload_config(args, scenes):
-    return {"workload": f"ETH-shaped synthetic K-sample inference: {scenes} scenes/GPU/step x {A_PER_SCENE} agents, "
+    shape = {8: "ETH-shaped", 32: "Zara-shaped", 256: "dense-crowd"}.get(A_PER_SCENE, "synthetic")
+    return {"workload": f"{shape} synthetic K-sample inference: {scenes} scenes/GPU/step x {A_PER_SCENE} agents, "
                         f"obs {N_PAST} pred {N_NEXT}, K={K_SAMPLES}, hidden 64, use_social=True",
             "scenes_per_gpu_per_step": scenes, "agents_per_scene": A_PER_SCENE, "K": K_SAMPLES,
             "obs_len": N_PAST, "pred_len": N_NEXT, "parallelism": f"scenes sharded x{args.gpus}, no collective",
@@ -220,7 +221,7 @@ def run_ours(args):
         ub = torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])
         if timed and headline:
             s2.record()
-        if precision == "fp16x2":
+        if precision == "fp16x2" and A_PER_SCENE <= ops.pool_tcx_max_scene():
             pooled = ops.pool_tcx(pk["pool"], pk["pool_tcx"], enc["x_last"], enc["h"], ub, scenes)
         else:
             pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
@@ -368,7 +369,7 @@ def run_ours(args):
             # the other kernels of the step, live CUDA-event times (north_star asks for the pairwise kernel's HBM figure;
             # it is compute-bound -- SURVEY.md D9 -- so the fraction is small by construction)
             "secondary_kernels": {
-                "pool_fwd_tcx_kernel" if args.precision == "fp16x2" else "pool_fwd_kernel": {
+                "pool_fwd_tcx_kernel" if args.precision == "fp16x2" and A_PER_SCENE <= ops.pool_tcx_max_scene() else "pool_fwd_kernel": {
                                     "kernel_ms": pool_ms, "bound": "hbm (as asked; actually compute-bound)",
                                     "algorithmic_bytes": n * 788, "achieved_gbs": n * 788 / (pool_ms * 1e-3) / 1e9,
                                     "peak_gbs": pk_["hbm_gbs"], "frac_of_hbm": n * 788 / (pool_ms * 1e-3) / 1e9 / pk_["hbm_gbs"],
@@ -413,7 +414,13 @@ def main():
     ap.add_argument("--precision", default="fp16x2", choices=["fp32", "fp16x2", "bf16"],
                     help="decode kernel of the headline line: fp16x2 = tcgen05 on fp16 hi/lo split operands "
                          "(fp32-faithful, default), fp32 = CUDA-core FFMA, bf16 = tcgen05 on bf16 operands (fast mode)")
+    ap.add_argument("--agents-per-scene", type=int, default=8,
+                    help="8 = BASELINE configs[1] (ETH-shaped, the headline); 32 = Zara-shaped; 256 with --k 128 = the dense-crowd "
+                         "stress of configs[4] (give --scenes so that scenes x agents x K fits the GPU)")
+    ap.add_argument("--k", type=int, default=20, help="samples per agent (K)")
     args = ap.parse_args()
+    global A_PER_SCENE, K_SAMPLES
+    A_PER_SCENE, K_SAMPLES = args.agents_per_scene, args.k
     if args.impl == "reference":
         run_reference(args)
     else:

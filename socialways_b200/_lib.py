@@ -7,7 +7,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsocialways_b200.so")
+# SOCIALWAYS_B200_LIB: an alternative build of the SAME library (A/B experiments with compile-time constants)
+LIB_PATH = os.environ.get("SOCIALWAYS_B200_LIB") or os.path.join(HERE, "libsocialways_b200.so")
 
 _P = ctypes.c_void_p
 _I = ctypes.c_int

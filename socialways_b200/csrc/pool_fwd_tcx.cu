@@ -22,10 +22,12 @@
 namespace sw {
 
 constexpr int PT_THREADS = 128;      // thread p = pair p of the current tile = TMEM lane p
-constexpr int PT_ROWS = 64;
+#ifndef SW_PT_ROWS
+#define SW_PT_ROWS 64     // agent rows per work unit (A/B-tested with -DSW_PT_ROWS=32 / 128)
+#endif
+constexpr int PT_ROWS = SW_PT_ROWS;
 constexpr int PT_LD = 65;
 constexpr int PT_A_MAX = 64;         // largest scene this kernel takes (larger ones go to pool_fwd_kernel)
-constexpr int PT_SPAN_MAX = PT_ROWS + 2 * (PT_A_MAX - 1);
 constexpr int PT_PP_P1 = 0, PT_PP_B2 = 128 + 64 * 32;      // offsets inside pool_pack (pool_fwd.cu)
 
 __device__ __forceinline__ void split2_pt(float a, float b, uint32_t& hi, uint32_t& lo) {
