@@ -32,6 +32,21 @@ def test_oracle_rejects_non_square_like_the_reference():
         so.compute_wasserstein(reals, fakes[:-1], obsv_len)
 
 
+@pytest.mark.parametrize("kind", ["generic", "ties", "half_steps"])
+def test_lsap_restatement_matches_scipy_assignments(kind):
+    """oracle/lsap_ref.c (the sequential form of the kernel's algorithm, tie rule included) returns scipy's ASSIGNMENT --
+    scipy.optimize.linear_sum_assignment is what the reference calls (calc_statistics.py:60) -- also when the optimum is
+    not unique."""
+    import scipy.optimize as op
+    from oracle import build_lsap
+    for seed in range(120):
+        rng = np.random.RandomState(seed)
+        n = int(rng.randint(1, 48))
+        cost = {"generic": rng.rand(n, n) * 10 - 3, "ties": rng.randint(0, 4, size=(n, n)).astype(np.float64),
+                "half_steps": np.round(rng.rand(n, n) * 5) / 2}[kind]
+        assert np.array_equal(build_lsap.solve(cost), op.linear_sum_assignment(cost)[1]), (kind, seed)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", CASES)
 def test_cuda_statistics_match_reference_golden(name):
@@ -66,6 +81,23 @@ def test_lsap_kernel_matches_scipy(n, p, seed, ties):
             assert cost[k][np.arange(n), col[k]].sum() == cost[k][row_ref, col_ref].sum()
         else:
             assert np.array_equal(col[k], col_ref)
+
+
+@pytest.mark.gpu
+def test_lsap_kernel_reproduces_scipy_tie_breaking():
+    """Tie-heavy integer costs: the warp-parallel scan must pick the column the sequential scan picks (lowest value; among
+    equals the last unassigned column in scan order, else the first) -- same assignment as scipy and as oracle/lsap_ref.c."""
+    import scipy.optimize as op
+    from oracle import build_lsap
+    from socialways_b200 import statistics as st
+    for n, p, seed in [(7, 40, 0), (24, 40, 1), (33, 30, 2), (64, 12, 3), (100, 6, 4)]:
+        rng = np.random.RandomState(seed)
+        cost = rng.randint(0, 4, size=(p, n, n)).astype(np.float64)
+        col = st.linear_sum_assignment(torch.from_numpy(cost).cuda()).cpu().numpy()
+        for k in range(p):
+            want = op.linear_sum_assignment(cost[k])[1]
+            assert np.array_equal(build_lsap.solve(cost[k]), want)
+            assert np.array_equal(col[k], want), (n, k)
 
 
 @pytest.mark.gpu
