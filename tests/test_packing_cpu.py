@@ -1,0 +1,122 @@
+"""Host-side operand packing of the tensor-core kernels (socialways_b200/packing.py), checked on the CPU: layouts are
+inverted and the kernels' arithmetic is emulated from the PACKED operands (fp16 hi/lo three-product split, x-feedback K
+block, ex2 prescale, shared-reciprocal cell) against the oracle's fp32 LSTM cell.  No GPU involved."""
+import ctypes
+
+import numpy as np
+import torch
+
+from socialways_b200 import packing
+
+LOG2E = 1.4426950408889634
+
+
+def uncanon(flat, n, k):
+    """inverse of packing._canonical_kmajor: [K/8][N][8] -> [N, K]"""
+    return flat.reshape(k // 8, n, 8).permute(1, 0, 2).reshape(n, k)
+
+
+def make_packs(seed=0):
+    from oracle import socialways_oracle as so
+    P = so.init_weights(seed=seed)
+    enc = packing.pack_encoder(P["encoder.embed.weight"], P["encoder.embed.bias"], P["encoder.lstm.weight_ih_l0"],
+                               P["encoder.lstm.weight_hh_l0"], P["encoder.lstm.bias_ih_l0"], P["encoder.lstm.bias_hh_l0"])
+    f = lambda i, t: P[f"decoder.fc1.{i}.{t}"]
+    dec = packing.pack_decoder(f(0, "weight"), f(0, "bias"), f(2, "weight"), f(2, "bias"), f(4, "weight"), f(4, "bias"),
+                               f(5, "weight"), f(5, "bias"))
+    return P, enc, dec
+
+
+def test_tcx_pack_sizes_match_the_kernel():
+    from socialways_b200 import _lib
+    _, enc, dec = make_packs()
+    w16, wsz16, f32 = packing.pack_decoder_tcx(enc, dec)
+    a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert _lib.lib().sw_decode_tcx_pack_sizes(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)) == 0
+    assert (w16.numel(), wsz16.numel(), f32.numel()) == (a.value, b.value, c.value)
+    assert w16.dtype == torch.float16 and wsz16.dtype == torch.float16 and f32.dtype == torch.float32
+    assert packing.pack_pool_tcx(torch.randn(64, 32)).shape == (4096,)
+
+
+def test_tcx_pack_layout_and_split_precision():
+    _, enc, dec = make_packs(1)
+    w16, wsz16, f32 = packing.pack_decoder_tcx(enc, dec)
+    w16 = w16.float()
+    w1 = dec[:25600].view(160, 160).t()
+    w2 = dec[25760:38560].view(160, 80).t()
+    scale = torch.tensor([-LOG2E, -LOG2E, -2 * LOG2E, -LOG2E]).repeat(64)
+    # W1[h rows]: canonical hi block then lo block
+    w1h = uncanon(w16[0:10240], 160, 64) + uncanon(w16[10240:20480], 160, 64)
+    assert (w1h - w1[:, :64]).abs().max() <= 2.0 ** -21 * w1[:, :64].abs().max()
+    # W2: one block of 160 rows = hi rows then lo rows
+    cat = uncanon(w16[20480:46080], 160, 160)
+    assert (cat[:80] + cat[80:] - w2).abs().max() <= 2.0 ** -21 * w2.abs().max()
+    assert torch.equal(cat[:80], w2.half().float())
+    # Whh with the ex2 prescale on the gate-interleaved rows n' = 4 unit + gate
+    whh = uncanon(w16[46080:62464], 256, 64) + uncanon(w16[62464:78848], 256, 64)
+    want = enc[4:68].t() * scale[:, None]
+    assert (whh - want).abs().max() <= 2.0 ** -20 * want.abs().max()
+    # x-feedback K block [2][256][8]: Wx_hi | Wx_hi | Wx_lo | b_hi | b_lo | 0 0
+    xk = uncanon(w16[78848:82944], 256, 16)
+    wx, bl = enc[0:4].t() * scale[:, None], enc[68] * scale
+    assert torch.equal(xk[:, 0:4], xk[:, 4:8]) and torch.equal(xk[:, 0:4], wx.half().float())
+    assert (xk[:, 0:4] + xk[:, 8:12] - wx).abs().max() <= 2.0 ** -20 * wx.abs().max()
+    assert (xk[:, 12] + xk[:, 13] - bl).abs().max() <= 2.0 ** -20 * bl.abs().max()
+    assert xk[:, 14:].abs().max() == 0
+    # hoisted rows of W1 ([S ; z], K = 96) in three K = 32 chunks, hi | lo each
+    wsz = wsz16.float().view(3, 2, -1)
+    for ch in range(3):
+        rec = uncanon(wsz[ch, 0], 160, 32) + uncanon(wsz[ch, 1], 160, 32)
+        want = w1[:, 64 + 32 * ch:96 + 32 * ch]
+        assert (rec - want).abs().max() <= 2.0 ** -21 * want.abs().max()
+    # fp32 section: b1 | b2 | b34 | pad | W34 [80][2]
+    assert torch.equal(f32[0:160], dec[25600:25760]) and torch.equal(f32[160:240], dec[38560:38640])
+    assert torch.equal(f32[240:242], dec[38800:38802]) and torch.equal(f32[256:416], dec[38640:38800])
+
+
+def split(x):
+    hi = x.half().float()
+    return hi, (x - hi).half().float()
+
+
+def test_emulated_gate_mma_and_cell_match_the_fp32_lstm_cell():
+    """One encoder step on the decode path (train.py:430), computed the way decode_fwd_tcx_kernel does it from the packed
+    operands, vs the oracle's explicit fp32 LSTM cell on the reference parameters."""
+    from oracle import socialways_oracle as so
+    P, enc, dec = make_packs(2)
+    w16 = packing.pack_decoder_tcx(enc, dec)[0].float()
+    whh_hi, whh_lo = uncanon(w16[46080:62464], 256, 64), uncanon(w16[62464:78848], 256, 64)
+    xk = uncanon(w16[78848:82944], 256, 16)
+    g = torch.Generator().manual_seed(0)
+    n = 64
+    h, c = torch.randn(n, 64, generator=g) * 0.5, torch.randn(n, 64, generator=g) * 0.7
+    x4 = torch.cat([torch.rand(n, 2, generator=g), torch.randn(n, 2, generator=g) * 0.05], 1)
+    # the MMA: three products for h, one K block [x_hi | x_lo | x_hi | 1 | 1 | 0 0] for the feedback and the bias
+    h_hi, h_lo = split(h)
+    x_hi, x_lo = split(x4)
+    a_blk = torch.cat([x_hi, x_lo, x_hi, torch.ones(n, 2), torch.zeros(n, 2)], 1)
+    e = h_hi @ whh_hi.t() + h_hi @ whh_lo.t() + h_lo @ whh_hi.t() + a_blk @ xk.t()          # [n, 256], ex2 arguments
+    e = e.view(n, 64, 4)
+    # lstm_cell_pair_prescaled (csrc/sw_umma.cuh)
+    ai, af, ag, ao = (1 + torch.exp2(torch.clamp(e[..., q], max=30.0)) for q in range(4))
+    r = 1.0 / (ai * ag * af * ao)
+    r_ig, r_fo = r * (af * ao), r * (ai * ag)
+    c_new = (ao * r_fo) * c + (ag * r_ig) * (2 * ai * r_ig - 1)
+    a_c = 1 + torch.exp2(torch.clamp(-2 * LOG2E * c_new, max=60.0))
+    h_new = (af * r_fo) * (2 / a_c - 1)
+    # reference arithmetic: embed (Linear 4 -> 64) + LSTM cell with the un-folded parameters
+    emb = x4 @ P["encoder.embed.weight"].t() + P["encoder.embed.bias"]
+    h_ref, c_ref = so.lstm_cell(emb, h, c, P["encoder.lstm.weight_ih_l0"], P["encoder.lstm.weight_hh_l0"],
+                                P["encoder.lstm.bias_ih_l0"], P["encoder.lstm.bias_hh_l0"])
+    assert (h_new - h_ref).abs().max() < 2e-6 and (c_new - c_ref).abs().max() < 2e-6
+
+
+def test_pool_tcx_pack_reconstructs_layer_two():
+    w = torch.randn(64, 32, generator=torch.Generator().manual_seed(3)) * 0.3
+    p = packing.pack_pool_tcx(w).float()
+    hi, lo = uncanon(p[:2048], 64, 32), uncanon(p[2048:], 64, 32)
+    assert torch.equal(hi, w.half().float()) and (hi + lo - w).abs().max() <= 2.0 ** -21 * w.abs().max()
+    a1 = torch.relu(torch.randn(128, 32, generator=torch.Generator().manual_seed(4)))
+    a_hi, a_lo = split(a1)
+    got = a_hi @ hi.t() + a_hi @ lo.t() + a_lo @ hi.t()
+    assert (got - a1 @ w.t()).abs().max() < 5e-6
