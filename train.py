@@ -12,6 +12,10 @@ Flags ADDED here (the reference hard-codes these as module constants / paths, tr
   --seed            seeds numpy and torch (the reference seeds nothing)
   --test-samples    K of the periodic test() call (reference: 128, train.py:668)
   --cuda-graph      replay the whole GAN iteration from a CUDA graph per batch shape (5x at batch 256)
+  --fused-adam      one kernel per optimiser step on flat buffers (fused_optim.FlatAdam); under torchrun it also carries
+                    the gradient all-reduce of the sharded step over NVLink peer memory, which is what lets --cuda-graph
+                    capture the multi-GPU iteration
+Under `torchrun --nproc-per-node N train.py ...` the scenes of every mini-batch are sharded over the N GPUs.
 All arithmetic runs in the sm_100a kernels of socialways_b200 (no CPU fallback).
 """
 import argparse
@@ -48,6 +52,8 @@ parser.add_argument('--seed', type=int, default=None)
 parser.add_argument('--test-samples', type=int, default=128)
 parser.add_argument('--cuda-graph', action='store_true',
                     help='capture each mini-batch shape of train() into a CUDA graph and replay it')
+parser.add_argument('--fused-adam', action='store_true',
+                    help='flat-buffer Adam in one kernel (with the gradient all-reduce fused in under torchrun)')
 
 
 def main():
@@ -58,10 +64,20 @@ def main():
         np.random.seed(args.seed)
         torch.manual_seed(args.seed)
     print(os.path.dirname(os.path.realpath(__file__)))
+    device = "cuda"
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:                   # torchrun: one rank per GPU, scenes sharded
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        device = f"cuda:{local}"
+        dist.init_process_group("nccl", device_id=torch.device(device))
+        if args.cuda_graph and not args.fused_adam:
+            raise SystemExit("--cuda-graph under torchrun needs --fused-adam (NCCL calls are not captured)")
     data = np.load(args.input_file)
     tr = SocialWaysTrainer(data, batch_size=args.batch_size, hidden_size=args.hidden_size,
                            use_social=args.use_social, n_unrolling_steps=args.unrolling_steps,
-                           lr_g=args.g_learning_rate, lr_d=args.d_learning_rate, cuda_graph=args.cuda_graph)
+                           lr_g=args.g_learning_rate, lr_d=args.d_learning_rate, cuda_graph=args.cuda_graph,
+                           fused_adam=args.fused_adam, device=device)
     print(args.input_file, ' # Training samples: ', tr.n_train_samples)
     print('hidden dim = %d | lr(G) =  %.5f | lr(D) =  %.5f' % (args.hidden_size, args.g_learning_rate, args.d_learning_rate))
     if os.path.isfile(model_file):                                   # train.py:622-637
@@ -72,6 +88,8 @@ def main():
     for epoch in trange(start_epoch, args.epochs + 1):               # train.py:646-668
         tr.epoch = epoch
         (tr.train_graphed if args.cuda_graph else tr.train)()
+        if tr.rank != 0:                                            # replicas are bit-identical: rank 0 writes files
+            continue
         if epoch % 50 == 0:
             print('Saving model to file ...', model_file)
             os.makedirs(os.path.dirname(os.path.abspath(model_file)), exist_ok=True)
