@@ -56,3 +56,29 @@ def test_no_cpu_fallback():
     g = sw.Generator(use_social=True)
     with pytest.raises(sw.SocialWaysCudaError):
         g.predict_k(torch.zeros(4, 8, 2), torch.zeros(1, 4, 32), 12, [[0, 4]])
+
+
+def test_new_rows_have_no_cpu_path_either():
+    """statistics / fused optimiser: CPU inputs are rejected, nothing falls back to numpy or torch.optim."""
+    import numpy as np
+    import pytest
+    import torch
+    import socialways_b200 as sw
+    if torch.cuda.is_available():
+        pytest.skip("CPU-tier check")
+    with pytest.raises(sw.SocialWaysCudaError):
+        sw.fused_optim.FlatAdam([torch.nn.Parameter(torch.zeros(4))], lr=1e-3)
+    with pytest.raises((sw.SocialWaysCudaError, RuntimeError, AssertionError)):
+        sw.statistics.compute_wasserstein(np.zeros((3, 2, 4, 2), np.float32), np.zeros((3, 2, 4, 2), np.float32))
+
+
+def test_null_pointers_are_rejected_by_the_new_entry_points():
+    from socialways_b200 import _lib
+    lib = _lib.lib()
+    assert lib.sw_traj_nn1_counts(None, None, 4, 1, 1, 1, 4, 2, None, None) == -1
+    assert lib.sw_traj_emd_cost(None, None, 4, 1, 1, 4, 2, None, None) == -1
+    assert lib.sw_lsap_solve(None, 4, 1, None, None, None) == -1
+    assert lib.sw_adam_flat(None, None, None, None, None, 4, 1e-3, 0.9, 0.999, 1e-8, 148, None) == -1
+    assert lib.sw_allreduce_adam(None, 0, 2, 4, 32, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, None) == -1
+    assert lib.sw_pool_fwd_tcx(None, None, None, None, None, None, None, None, 1, 1, None) == -1
+    assert lib.sw_pool_tcx_max_scene() == 64 and lib.sw_lsap_smem_bytes(20) == 20 * 42
