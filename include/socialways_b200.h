@@ -25,6 +25,8 @@
 #ifndef SOCIALWAYS_B200_H
 #define SOCIALWAYS_B200_H
 
+#include "sw_contract.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -92,13 +94,14 @@ int sw_pool_tcx_max_scene(void);
 
 /* Backward of sw_pool_fwd.  Replaces autograd through AttentionPooling.forward / EmbedSocialFeatures.fc
  * (train.py:160-175,183-188) inside g_loss.backward() (train.py:538).
- *   dS [N][64] gradient of the pooled vector, tdot [N] = dS_i . S_i, attn from the forward call,
+ *   dS [N][64] gradient of the pooled vector, tdot [N] = dS_i . S_i (or NULL: evaluated in the kernel from `pooled`
+ *   [N][64], the forward output), attn from the forward call,
  *   pair_offsets [n_scenes+1] (int64) start of every scene's A*A block of ordered pairs
  *   dub out [N][65] gradient of (u | beta); dh_direct out [N][64] = sum_i a_ij dS_i
  *   st_a1 [P][32], st_g2 [P][64], st_g1 [P][32], st_f [P][4] out: per-pair layer-1 activations, layer-2 /
  *   layer-1 pre-activation gradients and (features, 1); the MLP weight gradients are plain GEMMs of these */
 int sw_pool_bwd(const float* pool_pack, const float* x_last, const float* h, const float* ub,
-                const float* dS, const float* tdot, const float* attn, const int* scene_offsets,
+                const float* dS, const float* tdot, const float* pooled, const float* attn, const int* scene_offsets,
                 const int* agent_scene, const long long* pair_offsets, float* dub, float* dh_direct,
                 float* st_a1, float* st_g2, float* st_g1, float* st_f, int n_agents, int max_scene,
                 void* stream);
@@ -109,21 +112,26 @@ int sw_pool_bwd(const float* pool_pack, const float* x_last, const float* h, con
  *   h0,c0 [N][64], pooled [N][64] or NULL (use_social False, train.py:413), noise [K][N][32],
  *   x_last [N][4]; out [K][N][n_next][4] = (p, v) per step (train.py:425,432)
  *   stash_xh [T][tiles][68][32], stash_gates [T-1][tiles][5][64][32], stash_a1 [T][tiles][160][32],
- *   stash_a2 [T][tiles][80][32]: backward-pass stash (tile images), all NULL for inference */
+ *   stash_a2 [T][tiles][80][32]: backward-pass stash (tile images), all NULL for inference;
+ *   stash_sz [tiles][96][32] (optional, with the stash only): the step-invariant layer-1 operand [S ; z] as a tile image
+ *   (zeros in the S rows when pooled is NULL) -- the A operand of the W1[S,z] weight gradient */
 int sw_decode_fwd(const float* lstm_pack, const float* dec_pack, const float* h0, const float* c0,
                   const float* pooled, const float* noise, const float* x_last, float* out,
-                  float* stash_xh, float* stash_gates, float* stash_a1, float* stash_a2,
+                  float* stash_xh, float* stash_gates, float* stash_a1, float* stash_a2, float* stash_sz,
                   int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 
 /* Backward of sw_decode_fwd.  Replaces autograd through the decode loop (train.py:418-430) inside
  * g_loss.backward() (train.py:538).  dec_pack_t (sw_decode_pack_t_floats() floats) =
  * W1h^T [160][64] | W2^T [80][160] | W34 [80][2].  d_out [K*N][T][4] gradient of the emitted (p, v).
  * Outputs (tile images): g_gates [T-1][tiles][256][32], g_a1 [T][tiles][160][32], g_a2 [T][tiles][80][32],
- * g_v [T][tiles][2][32]; dh0, dc0 [K*N][64] gradients of the initial state.  Weight gradients = plain GEMMs
- * of the forward stash images against these (packing.py / autograd_path.py). */
+ * g_v [T][tiles][2][32]; dh0, dc0 [K*N][64] gradients of the initial state.  Weight gradients = contractions of the
+ * forward stash images against these (sw_contract).  Optional (NULL to skip): g_a1sum [tiles][160][32] = sum over the
+ * steps of g_a1 (gradient operand of the step-invariant [S ; z] columns of layer 1 and of b1); d_pooled [K*N][64] =
+ * dL/dS per row, which needs w1_torch = DecoderFC.fc1[0].weight [160][160] in torch layout. */
 int sw_decode_bwd(const float* lstm_pack_t, const float* dec_pack_t, const float* c0,
                   const float* stash_gates, const float* stash_a1, const float* stash_a2, const float* d_out,
                   float* g_gates, float* g_a1, float* g_a2, float* g_v, float* dh0, float* dc0,
+                  float* g_a1sum, const float* w1_torch, float* d_pooled,
                   int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 
 /* Tensor-core variant of sw_decode_fwd: tcgen05.mma with BF16 operands in shared memory and FP32 accumulators
@@ -158,6 +166,75 @@ int sw_disc_heads_bwd(const float* pack, const float* xrec, int pred_dim, int n_
                       const float* d_label, const float* d_code, float* d_h, float* d_pred, float* grec,
                       void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * The training iteration as ~30 launches (socialways_b200/native_step.py): what torch.autograd, ATen and cuBLAS do
+ * around the forward / backward kernels in train() (reference train.py:470-551) -- parameter folding, the heads of the
+ * discriminator with their losses, every weight gradient, the loss / ADE / FDE scalars -- as entry points of this library.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* Generator parameter folds (packing.py as ONE kernel).  params22 = HOST array of 22 device pointers in
+ * Generator.optimizer_parameters() order (train.py:379-380):
+ *   attention.W.{weight,bias}, feature_embedder.fc.{0,2,4}.{weight,bias}, encoder.embed.{weight,bias},
+ *   encoder.lstm.{weight_ih_l0,weight_hh_l0,bias_ih_l0,bias_hh_l0}, decoder.fc1.{0,2,4,5}.{weight,bias}.
+ * Outputs (sizes from sw_gen_pack_sizes): enc_pack [69][256] and its transpose rows 0..67 [256][68], dec_pack, dec_pack_t,
+ * pool_pack, pool_m = M [64][65] | m0 [65] with (u | beta) = h.M + m0, pool_mt = M^T [65][64].
+ * sw_gen_pack_bwd: the adjoint of the folds -- from d_enc [69][256] (pack layout), d_w34 [80][2] | d_b34 [2] and
+ * d_m [64][65] | d_m0 [65] (written by sw_contract) to the gradients of attention.W, fc.4, embed, the LSTM and fc1.4/fc1.5
+ * (grads22 = host array of 22 device pointers, same order; the other tensors' gradients are written by sw_contract directly).
+ * have_pool = 0 (use_social False, train.py:83): the four pooling tensors get zero gradients. */
+int sw_gen_pack_sizes(int* enc_pack, int* enc_pack_t, int* dec_pack, int* dec_pack_t, int* pool_pack, int* pool_m, int* pool_mt);
+int sw_gen_pack(const float* const* params22, float* enc_pack, float* enc_pack_t, float* dec_pack, float* dec_pack_t,
+                float* pool_pack, float* pool_m, float* pool_mt, void* stream);
+int sw_gen_pack_bwd(const float* const* params22, float* const* grads22, const float* d_enc, const float* d_w34,
+                    const float* d_m, int have_pool, void* stream);
+
+/* Discriminator packs.  params20 = host array of 20 device pointers in Discriminator.parameters() order (train.py:278-292):
+ * obsv_encoder_lstm.{weight_ih_l0,weight_hh_l0,bias_ih_l0,bias_hh_l0}, obsv_encoder_fc.{0,2}, pred_encoder.{0,2},
+ * classifier.{0,2}, latent_decoder.{0,2} (.weight, .bias each).  pred_dim = n_next * 4.
+ * Outputs: lstm_pack [69][256], lstm_pack_t [256][68], heads_work (layout csrc/disc_layout.cuh; sw_disc_pack_sizes). */
+int sw_disc_pack_sizes(int pred_dim, int* lstm_pack, int* lstm_pack_t, int* heads_work);
+int sw_disc_pack(const float* const* params20, int pred_dim, float* lstm_pack, float* lstm_pack_t, float* heads_work,
+                 void* stream);
+
+/* Discriminator heads + losses + their backward pass in one launch.  Replaces Discriminator.forward after the LSTM
+ * (train.py:300-309), the nn.MSELoss terms (train.py:484-493 D step, :514-521 G step) and the part of d_loss.backward() /
+ * g_loss.backward() (train.py:495,538) that runs through the heads.
+ *   mode 0 (D step): rows = every agent's fake trajectory pred_fake [N][pred_dim] AND its real one, formed on the fly from
+ *     pred_pos [N][n_next][2] and the last observed position of obsv_pos [N][n_past][2] (get_traj_4d, train.py:135-137).
+ *     Targets: fake -> targets[0] (`zeros`, train.py:471), real -> targets[1] (`ones`, :472); info loss on the fake rows.
+ *     Outputs: d_h [N][64] (gradient of the observation code, both branches summed), x_img [ceil(N/16)][x_rows][32] and
+ *     g_img [ceil(N/16)][g_rows][32] tile-image records for sw_contract (rows: csrc/disc_layout.cuh, sw_disc_step_image_rows).
+ *   mode 1 (G step): fake rows only, target targets[1]; output d_pred [N][pred_dim] = dL/d(pred_hat_4d).
+ *   noise [N][noise_ld]: columns 0,1 are the latent codes (train.py:486,518); inv_n = 1 / (GLOBAL number of agents of the
+ *   mini-batch) so that per-rank gradients sum to nn.MSELoss's over the global batch; info_w = loss_info_w.
+ *   loss_part [tiles][4] = per-tile sums of squared errors (fake-or-fooling label, real label, info, 0).
+ *   label_out [2N or N], code_out [N][2]: optional raw outputs. */
+int sw_disc_step_image_rows(int pred_dim, int* x_rows, int* g_rows);
+int sw_disc_step(const float* heads_work, int pred_dim, int mode, const float* obsv_h, const float* pred_fake,
+                 const float* pred_pos, const float* obsv_pos, int n_past, const float* noise, int noise_ld,
+                 const float* targets, float inv_n, float info_w, float* d_h, float* d_pred, float* x_img, float* g_img,
+                 float* loss_part, float* label_out, float* code_out, int n_agents, int sm_count, void* stream);
+
+/* All weight-gradient contractions of one backward pass in one launch (job descriptor: sw_contract.h).  Replaces the
+ * grad_weight halves of autograd's Linear / LSTM nodes (train.py:495,538).  `workspace` (sw_contract_plan floats) holds
+ * the partial tiles of jobs that are split over CTAs, `counters` (zero-initialised, restored by the kernel) one word per
+ * output tile.  Deterministic: the summation order does not depend on scheduling. */
+int sw_contract_plan(const sw_contract_job* jobs, int n_jobs, int sm_count, long long* workspace_floats, int* n_counters);
+int sw_contract(const sw_contract_job* jobs, int n_jobs, float* workspace, long long workspace_floats, unsigned* counters,
+                int n_counters, int sm_count, void* stream);
+
+/* out[row][n] = bias[n] + add1[row][n] + add2[row][n] + sum_k x[row][k] w[k][n]  (k_in, n_out <= 80; bias/add1/add2 may
+ * be NULL; add1/add2 have row stride ldo).  (u | beta) = h.M + m0 (train.py:158,167-169,185 folded) and its adjoint. */
+int sw_rows_linear(const float* x, int ldx, const float* w, const float* bias, const float* add1, const float* add2,
+                   float* out, int ldo, int n_rows, int k_in, int n_out, void* stream);
+
+/* Scalars of one iteration (train.py:546-551 and the mse_loss values): stats[8] = (sum ADE terms / n_next, sum FDE terms,
+ * d_loss, d_fake, d_real, d_info, g_fooling, g_info) from pred_hat [N][n_next][4], pred [N][n_next][2], ss = Scale.sx and
+ * the loss_part arrays of the last D pass / the G pass.  partial [sm_count][2] and counter (zero-initialised) are scratch. */
+int sw_train_stats(const float* pred_hat, const float* pred, int n_rows, int n_next, float ss, const float* d_parts,
+                   int d_tiles, const float* g_parts, int g_tiles, float inv_n, float info_w, float* partial,
+                   unsigned* counter, float* stats, int sm_count, void* stream);
+
 /* Best-of-K error metrics.  Replaces train.py:587 and :602-607 of test().
  *   pred [K][N][T][4], gt [N][T][2] (normalised), ss = Scale.sx (train.py:121)
  *   out [N][4] = (avg-K ADE, avg-K FDE, min-K ADE, min-K FDE) per agent */
@@ -185,17 +262,21 @@ int sw_lsap_smem_bytes(int n);
 int sw_lsap_solve(const double* cost, int n, int n_problems, int* col4row, int* status, void* stream);
 
 /* Optimiser step on ONE flat fp32 buffer.  Replaces torch.optim.Adam.step() of the optimisers
- * built at train.py:381,385 (called at :496, :539); same update rule and operation order, step count `step` (one device
- * float, advanced by the call: safe to replay from a CUDA graph); hyper-parameters are the python doubles torch receives.
+ * built at train.py:381,385 (called at :496, :539); same update rule and operation order; `step` = TWO device words:
+ * [0] the step count as a float (advanced by the call: safe to replay from a CUDA graph), [1] a zero-initialised
+ * scratch word (sw_adam_flat's finished-CTA counter); hyper-parameters are the python doubles torch receives.
  *   sw_adam_flat: params, grads, exp_avg, exp_avg_sq [n].
  *   sw_allreduce_adam: additionally replaces the gradient all-reduce of the sharded step (one NCCL call per optimiser step
  *     otherwise).  peer_bufs_dev = device array of `world` pointers to every rank's SYMMETRIC buffer laid out
  *     [n_pad floats of gradient | uint32 ready[world] | uint32 done[world]] (flags zero-initialised, n_pad % 32 == 0);
- *     params / exp_avg / exp_avg_sq are n_pad floats (zero padded); seq = 2 device uint32 (zero-initialised).  Gradients are
- *     summed with peer loads over NVLink in rank order on every rank (bit-identical replicas); the call returns once
- *     every peer has finished reading this rank's gradients.  Every rank must make the call (same order). */
+ *     params / exp_avg / exp_avg_sq are n_pad floats (zero padded); seq = 4 device uint32 (zero-initialised; seq[2] is a
+ *     status word: 0 = ok, 1 = a peer never published its gradients within the wait bound and the step was NOT applied,
+ *     2 = a peer never acknowledged reading).  Gradients are summed with peer loads over NVLink in rank order on every rank
+ *     (bit-identical replicas); the kernel returns once every peer has finished reading this rank's gradients.  Every rank
+ *     must make the call (same order).  sw_set_peer_wait_timeout_ms bounds every wait in time (default 60 000 ms). */
 int sw_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step, int n, double lr,
                  double beta1, double beta2, double eps, int sm_count, void* stream);
+int sw_set_peer_wait_timeout_ms(int ms);
 int sw_allreduce_adam(const void* peer_bufs_dev, int rank, int world, int n, int n_pad, float* params, float* exp_avg,
                       float* exp_avg_sq, float* step, unsigned* seq, double lr, double beta1, double beta2, double eps,
                       void* stream);

@@ -26,11 +26,11 @@ _PROTOTYPES = {
     "sw_lstm_seq_fwd_tcx": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
     "sw_lstm_seq_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "sw_pool_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
-    "sw_pool_bwd": (_I, [_P] * 16 + [_I, _I, _P]),
+    "sw_pool_bwd": (_I, [_P] * 17 + [_I, _I, _P]),
     "sw_pool_fwd_tcx": (_I, [_P] * 8 + [_I, _I, _P]),
     "sw_pool_tcx_max_scene": (_I, []),
-    "sw_decode_fwd": (_I, [_P] * 12 + [_I, _I, _I, _I, _P]),
-    "sw_decode_bwd": (_I, [_P] * 13 + [_I, _I, _I, _I, _P]),
+    "sw_decode_fwd": (_I, [_P] * 13 + [_I, _I, _I, _I, _P]),
+    "sw_decode_bwd": (_I, [_P] * 16 + [_I, _I, _I, _I, _P]),
     "sw_decode_fwd_tc": (_I, [_P] * 8 + [_I, _I, _I, _I, _P]),
     "sw_decode_tc_pack_sizes": (_I, [_P, _P]),
     "sw_decode_fwd_tcx": (_I, [_P] * 9 + [_I, _I, _I, _I, _P]),
@@ -39,12 +39,24 @@ _PROTOTYPES = {
     "sw_disc_heads_record_dims": (_I, [_I, _I, _P, _P]),
     "sw_disc_heads_fwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P]),
     "sw_disc_heads_bwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
+    "sw_gen_pack_sizes": (_I, [_P] * 7),
+    "sw_gen_pack": (_I, [_P] * 9),
+    "sw_gen_pack_bwd": (_I, [_P] * 5 + [_I, _P]),
+    "sw_disc_pack_sizes": (_I, [_I, _P, _P, _P]),
+    "sw_disc_pack": (_I, [_P, _I, _P, _P, _P, _P]),
+    "sw_disc_step_image_rows": (_I, [_I, _P, _P]),
+    "sw_disc_step": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _F, _F] + [_P] * 7 + [_I, _I, _P]),
+    "sw_contract_plan": (_I, [_P, _I, _I, _P, _P]),
+    "sw_contract": (_I, [_P, _I, _P, ctypes.c_longlong, _P, _I, _I, _P]),
+    "sw_rows_linear": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "sw_train_stats": (_I, [_P, _P, _I, _I, _F, _P, _I, _P, _I, _F, _F, _P, _P, _P, _I, _P]),
     "sw_bestofk_metrics": (_I, [_P, _P, _F, _I, _I, _I, _P, _P]),
     "sw_traj_nn1_counts": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "sw_traj_emd_cost": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "sw_lsap_smem_bytes": (_I, [_I]),
     "sw_lsap_solve": (_I, [_P, _I, _I, _P, _P, _P]),
     "sw_adam_flat": (_I, [_P, _P, _P, _P, _P, _I, _D, _D, _D, _D, _I, _P]),
+    "sw_set_peer_wait_timeout_ms": (_I, [_I]),
     "sw_allreduce_adam": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _P, _P, _D, _D, _D, _D, _P]),
 }
 

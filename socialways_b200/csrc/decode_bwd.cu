@@ -43,6 +43,9 @@ decode_bwd_kernel(const float* __restrict__ pack_t, const float* __restrict__ de
                   float* __restrict__ g_gates /*[T-1][tiles][256][32]*/, float* __restrict__ g_a1 /*[T][tiles][160][32]*/,
                   float* __restrict__ g_a2 /*[T][tiles][80][32]*/, float* __restrict__ g_v /*[T][tiles][2][32]*/,
                   float* __restrict__ dh0 /*[rows][64]*/, float* __restrict__ dc0 /*[rows][64]*/,
+                  float* __restrict__ g_a1sum /*[tiles][160][32] = sum_t da1pre, or null*/,
+                  const float* __restrict__ w1_sz /*DecoderFC.fc1.0.weight [160][160] (torch layout), or null*/,
+                  float* __restrict__ d_pooled /*[rows][64] = (sum_t da1pre) . W1[:, 64:128], or null*/,
                   int n_agents, long long n_rows, int T, int n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecodeBwdSmem& s = *reinterpret_cast<DecodeBwdSmem*>(smem_raw);
@@ -69,6 +72,11 @@ decode_bwd_kernel(const float* __restrict__ pack_t, const float* __restrict__ de
         }
         float dc[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
         float carry0 = 0.0f, carry1 = 0.0f;          // dL/dp_t flowing to p_{t-1}  (x_ks == 0 lanes)
+        float sum_a1[5][4];                          // sum_t da1pre of this thread's columns (the hoisted [S ; z] operand's gradient)
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sum_a1[q][i] = 0.0f;
         __syncthreads();
 
         for (int t = T - 1; t >= 0; --t) {
@@ -141,6 +149,7 @@ decode_bwd_kernel(const float* __restrict__ pack_t, const float* __restrict__ de
                                                      av.z > 0.f ? acc[2][j] : 0.2f * acc[2][j], av.w > 0.f ? acc[3][j] : 0.2f * acc[3][j]);
                         *reinterpret_cast<float4*>(da1 + off) = g;
                         *reinterpret_cast<float4*>(ga1 + off) = g;
+                        sum_a1[j >> 1][0] += g.x; sum_a1[j >> 1][1] += g.y; sum_a1[j >> 1][2] += g.z; sum_a1[j >> 1][3] += g.w;
                     }
             }
             __syncthreads();
@@ -165,6 +174,36 @@ decode_bwd_kernel(const float* __restrict__ pack_t, const float* __restrict__ de
             if (r < rows_valid)
                 *reinterpret_cast<float2*>(dc0 + (size_t)(row0 + r) * SW_H + lmG.cg * 2) = make_float2(dc[i][0], dc[i][1]);
         }
+        if (g_a1sum) {
+            // ---- the step-invariant part of layer 1: its gradient operand is sum_t da1pre (image, for the W1[S,z] / b1
+            //      weight gradients) and dL/dS = (sum_t da1pre) . W1[:, S columns] ----
+#pragma unroll
+            for (int j = 0; j < 10; ++j)
+                if ((j & 1) == lm2.ks)
+                    *reinterpret_cast<float4*>(da1 + (lm2.cg * 10 + j) * SW_ROWS + lm2.rg * 4) =
+                        make_float4(sum_a1[j >> 1][0], sum_a1[j >> 1][1], sum_a1[j >> 1][2], sum_a1[j >> 1][3]);
+            __syncthreads();     // also: the dh0 writer above is done with s.dh
+            store_image(g_a1sum + (size_t)tile * (160 * SW_ROWS), da1, 160 * SW_ROWS);
+            if (d_pooled) {
+                float acc[4][8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+                fma_tile<8, 4>(acc, da1, w1_sz + 64, 160, 160, lmH);       // W[n][64 + k], n = contraction index
+                ksplit_reduce<8, 4>(acc);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if ((j & 3) == lmH.ks)
+                        *reinterpret_cast<float4*>(s.dh + (lmH.cg * 8 + j) * SW_ROWS + lmH.rg * 4) =
+                            make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+                __syncthreads();
+                for (int i = tid; i < SW_ROWS * SW_H; i += SW_THREADS) {
+                    const int r = i >> 6, k = i & 63;
+                    if (r < rows_valid) d_pooled[(size_t)(row0 + r) * SW_H + k] = s.dh[k * SW_ROWS + r];
+                }
+            }
+        }
     }
 }
 
@@ -173,11 +212,13 @@ decode_bwd_kernel(const float* __restrict__ pack_t, const float* __restrict__ de
 extern "C" int sw_decode_bwd(const float* lstm_pack_t, const float* dec_pack_t, const float* c0,
                              const float* stash_gates, const float* stash_a1, const float* stash_a2, const float* d_out,
                              float* g_gates, float* g_a1, float* g_a2, float* g_v, float* dh0, float* dc0,
+                             float* g_a1sum, const float* w1_torch, float* d_pooled,
                              int n_agents, int n_samples, int n_next, int sm_count, void* stream) {
     if (!lstm_pack_t || !dec_pack_t || !c0 || !stash_a1 || !stash_a2 || !d_out || !g_a1 || !g_a2 || !g_v || !dh0 || !dc0)
         return SW_ERR_ARG;
     if (n_next > 1 && (!stash_gates || !g_gates)) return SW_ERR_ARG;
     if (n_agents <= 0 || n_samples <= 0 || n_next <= 0 || sm_count <= 0) return SW_ERR_ARG;
+    if (d_pooled && (!g_a1sum || !w1_torch)) return SW_ERR_ARG;
     const long long n_rows = (long long)n_agents * n_samples;
     const long long tiles = (n_rows + SW_ROWS - 1) / SW_ROWS;
     if (tiles > 0x7fffffffLL) return SW_ERR_UNSUPPORTED;
@@ -185,8 +226,8 @@ extern "C" int sw_decode_bwd(const float* lstm_pack_t, const float* dec_pack_t, 
     SW_SET_MAX_SMEM(sw::decode_bwd_kernel, smem);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     sw::decode_bwd_kernel<<<grid, SW_THREADS, smem, (cudaStream_t)stream>>>(
-        lstm_pack_t, dec_pack_t, c0, stash_gates, stash_a1, stash_a2, d_out, g_gates, g_a1, g_a2, g_v, dh0, dc0, n_agents,
-        n_rows, n_next, (int)tiles);
+        lstm_pack_t, dec_pack_t, c0, stash_gates, stash_a1, stash_a2, d_out, g_gates, g_a1, g_a2, g_v, dh0, dc0, g_a1sum,
+        w1_torch, d_pooled, n_agents, n_rows, n_next, (int)tiles);
     SW_CUDA_TRY(cudaGetLastError());
     return SW_OK;
 }

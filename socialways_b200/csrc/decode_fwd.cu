@@ -45,6 +45,7 @@ decode_fwd_kernel(const float* __restrict__ lstm_pack, const float* __restrict__
                   const float* __restrict__ x_last, float* __restrict__ out,
                   float* __restrict__ stash_xh /*[T][tiles][68][32]*/, float* __restrict__ stash_gates /*[T-1][tiles][5][64][32]*/,
                   float* __restrict__ stash_a1 /*[T][tiles][160][32]*/, float* __restrict__ stash_a2 /*[T][tiles][80][32]*/,
+                  float* __restrict__ stash_sz /*[tiles][96][32]: the hoisted operand [S ; z], or null*/,
                   int n_agents, long long n_rows, int n_next, int n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecodeSmem& s = *reinterpret_cast<DecodeSmem*>(smem_raw);
@@ -79,10 +80,15 @@ decode_fwd_kernel(const float* __restrict__ lstm_pack, const float* __restrict__
             for (int j = 0; j < 10; ++j) c1[i][j] = 0.0f;
         if (pooled != nullptr) {
             load_rows_kmajor(s.a1, s.a2, pooled, 64, rows_valid, agent_of);
+            if (STASH && stash_sz) store_image(stash_sz + (size_t)tile * (96 * SW_ROWS), s.a1, 64 * SW_ROWS);
             fma_tile<10, 2>(c1, s.a1, dec_pack + DP_W1 + 64 * 160, 160, 64, lm1);
             __syncthreads();
+        } else if (STASH && stash_sz) {
+            for (int i = tid * 4; i < 64 * SW_ROWS; i += SW_THREADS * 4)
+                *reinterpret_cast<float4*>(stash_sz + (size_t)tile * (96 * SW_ROWS) + i) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         load_rows_kmajor(s.a1, s.a2, noise, SW_Z, rows_valid, [&](int r) { return row0 + r; });
+        if (STASH && stash_sz) store_image(stash_sz + (size_t)tile * (96 * SW_ROWS) + 64 * SW_ROWS, s.a1, SW_Z * SW_ROWS);
         fma_tile<10, 2>(c1, s.a1, dec_pack + DP_W1 + 128 * 160, 160, SW_Z, lm1);
         ksplit_reduce<10, 2>(c1);
 #pragma unroll
@@ -180,7 +186,7 @@ decode_fwd_kernel(const float* __restrict__ lstm_pack, const float* __restrict__
 
 extern "C" int sw_decode_fwd(const float* lstm_pack, const float* dec_pack, const float* h0, const float* c0,
                              const float* pooled, const float* noise, const float* x_last, float* out,
-                             float* stash_xh, float* stash_gates, float* stash_a1, float* stash_a2,
+                             float* stash_xh, float* stash_gates, float* stash_a1, float* stash_a2, float* stash_sz,
                              int n_agents, int n_samples, int n_next, int sm_count, void* stream) {
     if (!lstm_pack || !dec_pack || !h0 || !c0 || !noise || !x_last || !out) return SW_ERR_ARG;
     if (n_agents <= 0 || n_samples <= 0 || n_next <= 0 || sm_count <= 0) return SW_ERR_ARG;
@@ -195,7 +201,7 @@ extern "C" int sw_decode_fwd(const float* lstm_pack, const float* dec_pack, cons
     SW_SET_MAX_SMEM(sw::decode_fwd_kernel<false>, smem);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     kern<<<grid, SW_THREADS, smem, (cudaStream_t)stream>>>(lstm_pack, dec_pack, h0, c0, pooled, noise, x_last, out, stash_xh,
-                                                           stash_gates, stash_a1, stash_a2, n_agents, n_rows, n_next,
+                                                           stash_gates, stash_a1, stash_a2, stash_sz, n_agents, n_rows, n_next,
                                                            (int)tiles);
     SW_CUDA_TRY(cudaGetLastError());
     return SW_OK;

@@ -13,7 +13,9 @@
 // "I have finished reading" and waits for the peers' same message before returning, so nobody overwrites a gradient
 // buffer that is still being read.  The payload is 27 939 (D) / 86 122 (G) floats: latency-bound, so a handful of CTAs
 // with every peer load of a round in flight; plain kernels, so the whole sharded iteration can sit in a CUDA graph (NCCL
-// capture hung in this stack).  Spins are bounded: a missing peer becomes a trap (CUDA error), never a hung GPU.
+// capture hung in this stack).  Waits are bounded in TIME (%globaltimer; sw_set_peer_wait_timeout_ms, default 60 s): a peer
+// that never shows up makes the kernel give up WITHOUT touching the parameters and raise the status word seq[2] -- the
+// context stays alive (no trap) and the host reads the word when it next synchronises (FlatAdam.check_status()).
 #include "sw_common.cuh"
 
 namespace sw {
@@ -43,16 +45,27 @@ __device__ __forceinline__ void adam_scalars(float t, const AdamHyper h, float& 
     inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
 }
 
-__global__ void adam_step_advance_kernel(float* step) { *step += 1.0f; }
-
+// step[0] = step count t (float, as torch keeps it), step[1] = finished-CTA counter (uint32 bits, zero between launches).
+// Every CTA reads t when it starts; the CTA that finishes LAST advances it -- one launch per optimiser step, and no CTA
+// can observe the advanced value.
 __global__ void adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                                 const float* __restrict__ step, int n, AdamHyper h) {
+                                 float* __restrict__ step, int n, AdamHyper h) {
+    __shared__ float t_s;
+    if (threadIdx.x == 0) t_s = *reinterpret_cast<volatile float*>(step) + 1.0f;
+    __syncthreads();
+    const float t = t_s;
     float step_size, inv_bc2_sqrt;
-    adam_scalars(*step, h, step_size, inv_bc2_sqrt);
+    adam_scalars(t, h, step_size, inv_bc2_sqrt);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float pi = p[i], mi = m[i], vi = v[i];
         adam_update(g[i], pi, mi, vi, h, step_size, inv_bc2_sqrt);
         p[i] = pi; m[i] = mi; v[i] = vi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* counter = reinterpret_cast<unsigned*>(step + 1);
+        __threadfence();
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) { *counter = 0u; *step = t; }
     }
 }
 
@@ -63,6 +76,18 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* addr) {
     unsigned v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// wait until *flag has reached `seq` (wrap-safe); false after timeout_ns
+__device__ __forceinline__ bool wait_flag(const unsigned* flag, unsigned seq, unsigned long long timeout_ns) {
+    const unsigned long long t0 = global_ns();
+    for (unsigned spins = 0; (int)(ld_acquire_sys(flag) - seq) < 0; ++spins)
+        if ((spins & 1023u) == 1023u && global_ns() - t0 > timeout_ns) return false;
+    return true;
 }
 __device__ __forceinline__ float4 ld_volatile_f32x4(const float* addr) {
     float4 v;
@@ -80,13 +105,15 @@ constexpr int AR_MAX_WORLD = 16;
 __global__ void __launch_bounds__(AR_THREADS, 1)
 allreduce_adam_kernel(const unsigned long long* __restrict__ peer_bufs, int rank, int world, int n_pad,
                       float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, float* __restrict__ step,
-                      unsigned* __restrict__ seq_ptr /* [0] sequence number, [1] finished-CTA counter */, AdamHyper h) {
+                      unsigned* __restrict__ seq_ptr /* [0] sequence number, [1] finished-CTA counter, [2] status */,
+                      AdamHyper h, unsigned long long timeout_ns) {
     __shared__ unsigned seq_s;
     __shared__ float t_s;
     __shared__ bool last_s;
+    __shared__ int timed_out_s;
     __shared__ unsigned long long bufs[AR_MAX_WORLD];
     const int tid = threadIdx.x;
-    if (tid == 0) { seq_s = *seq_ptr + 1u; t_s = *step + 1.0f; }
+    if (tid == 0) { seq_s = *seq_ptr + 1u; t_s = *step + 1.0f; timed_out_s = 0; }
     if (tid < world) bufs[tid] = peer_bufs[tid];
     __syncthreads();
     const unsigned seq = seq_s;
@@ -98,10 +125,13 @@ allreduce_adam_kernel(const unsigned long long* __restrict__ peer_bufs, int rank
             __threadfence_system();
             st_release_sys(peer_flags + rank, seq);
         }
-        for (unsigned spins = 0; (int)(ld_acquire_sys(my_flags + tid) - seq) < 0; ++spins)
-            if (spins > (1u << 27)) __trap();
+        if (!wait_flag(my_flags + tid, seq, timeout_ns)) atomicExch(&timed_out_s, 1);
     }
     __syncthreads();
+    if (timed_out_s) {            // a peer never published its gradients: leave the parameters alone, tell the host
+        if (tid == 0) atomicExch(seq_ptr + 2, 1u);
+        return;
+    }
     // (3) sum in rank order + Adam, one float4 per thread and round, all peers' loads of a round in flight together
     float step_size, inv_bc2_sqrt;
     adam_scalars(t_s, h, step_size, inv_bc2_sqrt);
@@ -137,8 +167,7 @@ allreduce_adam_kernel(const unsigned long long* __restrict__ peer_bufs, int rank
     if (tid < world) {
         unsigned* peer_flags = reinterpret_cast<unsigned*>(reinterpret_cast<float*>(bufs[tid]) + n_pad);
         st_release_sys(peer_flags + world + rank, seq);
-        for (unsigned spins = 0; (int)(ld_acquire_sys(my_flags + world + tid) - seq) < 0; ++spins)
-            if (spins > (1u << 27)) __trap();
+        if (!wait_flag(my_flags + world + tid, seq, timeout_ns)) atomicExch(seq_ptr + 2, 2u);
     }
     __syncthreads();
     if (tid == 0) { seq_ptr[1] = 0u; *seq_ptr = seq; *step = t_s; }
@@ -155,12 +184,18 @@ extern "C" int sw_adam_flat(float* params, const float* grads, float* exp_avg, f
     if (!adam_args_ok(params, exp_avg, exp_avg_sq, step, n, lr, beta1, beta2, eps) || !grads || sm_count <= 0) return SW_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     const sw::AdamHyper h = sw::make_hyper(lr, beta1, beta2, eps);
-    sw::adam_step_advance_kernel<<<1, 1, 0, st>>>(step);
     const int block = 256;
     int grid = (n + block - 1) / block;
     if (grid > sm_count * 4) grid = sm_count * 4;
     sw::adam_flat_kernel<<<grid, block, 0, st>>>(params, grads, exp_avg, exp_avg_sq, step, n, h);
     SW_CUDA_TRY(cudaGetLastError());
+    return SW_OK;
+}
+
+static unsigned long long g_peer_wait_timeout_ns = 60ull * 1000000000ull;
+extern "C" int sw_set_peer_wait_timeout_ms(int ms) {
+    if (ms <= 0) return SW_ERR_ARG;
+    g_peer_wait_timeout_ns = (unsigned long long)ms * 1000000ull;
     return SW_OK;
 }
 
@@ -173,7 +208,8 @@ extern "C" int sw_allreduce_adam(const void* peer_bufs_dev, int rank, int world,
     int grid = (n_pad / 4 + sw::AR_THREADS - 1) / sw::AR_THREADS;
     if (grid > 32) grid = 32;
     sw::allreduce_adam_kernel<<<grid, sw::AR_THREADS, 0, (cudaStream_t)stream>>>(
-        (const unsigned long long*)peer_bufs_dev, rank, world, n_pad, params, exp_avg, exp_avg_sq, step, seq, h);
+        (const unsigned long long*)peer_bufs_dev, rank, world, n_pad, params, exp_avg, exp_avg_sq, step, seq, h,
+        g_peer_wait_timeout_ns);
     SW_CUDA_TRY(cudaGetLastError());
     return SW_OK;
 }

@@ -25,7 +25,8 @@ constexpr int PBP_P1 = 0, PBP_P2 = 128, PBP_B2 = PBP_P2 + 64 * 32;
 template <int G>
 __global__ void __launch_bounds__(SW_THREADS, 1)
 pool_bwd_kernel(const float* __restrict__ pool_pack, const float* __restrict__ x_last, const float* __restrict__ h,
-                const float* __restrict__ ub, const float* __restrict__ dS, const float* __restrict__ tdot /*[N] dS_i.S_i*/,
+                const float* __restrict__ ub, const float* __restrict__ dS, const float* __restrict__ tdot /*[N] dS_i.S_i, or null*/,
+                const float* __restrict__ pooled /*[N][64] S (used when tdot is null)*/,
                 const float* __restrict__ attn, const int* __restrict__ scene_offsets, const int* __restrict__ agent_scene,
                 const long long* __restrict__ pair_offsets, float* __restrict__ dub /*[N][65]*/,
                 float* __restrict__ dh_direct /*[N][64]*/, float* __restrict__ stA1 /*[P][32]*/, float* __restrict__ stG2 /*[P][64]*/,
@@ -98,8 +99,15 @@ pool_bwd_kernel(const float* __restrict__ pool_pack, const float* __restrict__ x
                 a1[n] = fmaxf(fmaf(w.x, dist, fmaf(w.y, bearing, fmaf(w.z, dca, w.w))), 0.0f);
             }
             // ---- dsigma_ij = a_ij * (dS_i . h_j - dS_i . S_i) ----
-            float da = -__ldg(tdot + i);
             const float* dsi = dp + (size_t)ii * ldd;
+            float da = 0.0f;
+            if (tdot) {
+                da = -__ldg(tdot + i);
+            } else {                       // dS_i . S_i evaluated here (64 FMAs against ~4 500 of the pair): no extra launch
+                const float* si = pooled + (size_t)i * SW_H;
+#pragma unroll 8
+                for (int n = 0; n < SW_H; ++n) da = fmaf(-dsi[n], __ldg(si + n), da);
+            }
 #pragma unroll 8
             for (int n = 0; n < SW_H; ++n) da = fmaf(dsi[n], __ldg(hj + n), da);
             const float g = __ldg(attn + (size_t)i * a_cap + (j - a)) * da;
@@ -170,11 +178,11 @@ pool_bwd_kernel(const float* __restrict__ pool_pack, const float* __restrict__ x
 }  // namespace sw
 
 extern "C" int sw_pool_bwd(const float* pool_pack, const float* x_last, const float* h, const float* ub,
-                           const float* dS, const float* tdot, const float* attn, const int* scene_offsets,
+                           const float* dS, const float* tdot, const float* pooled, const float* attn, const int* scene_offsets,
                            const int* agent_scene, const long long* pair_offsets, float* dub, float* dh_direct,
                            float* st_a1, float* st_g2, float* st_g1, float* st_f, int n_agents, int max_scene,
                            void* stream) {
-    if (!pool_pack || !x_last || !h || !ub || !dS || !tdot || !attn || !scene_offsets || !agent_scene || !pair_offsets ||
+    if (!pool_pack || !x_last || !h || !ub || !dS || (!tdot && !pooled) || !attn || !scene_offsets || !agent_scene || !pair_offsets ||
         !dub || !dh_direct || !st_a1 || !st_g2 || !st_g1 || !st_f)
         return SW_ERR_ARG;
     if (n_agents <= 0 || max_scene <= 0) return SW_ERR_ARG;
@@ -189,7 +197,7 @@ extern "C" int sw_pool_bwd(const float* pool_pack, const float* x_last, const fl
     do {                                                                                                             \
         SW_SET_MAX_SMEM(sw::pool_bwd_kernel<GG>, \
                                          (int)smem);                                                                \
-        sw::pool_bwd_kernel<GG><<<grid, SW_THREADS, smem, st>>>(pool_pack, x_last, h, ub, dS, tdot, attn,             \
+        sw::pool_bwd_kernel<GG><<<grid, SW_THREADS, smem, st>>>(pool_pack, x_last, h, ub, dS, tdot, pooled, attn,     \
                                                                  scene_offsets, agent_scene, pair_offsets, dub,      \
                                                                  dh_direct, st_a1, st_g2, st_g1, st_f, n_agents,     \
                                                                  a_cap, span_cap);                                   \

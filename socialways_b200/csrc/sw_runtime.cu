@@ -4,7 +4,7 @@
 static thread_local int g_last_cuda_error = 0;
 void sw_set_last_cuda_error(int e) { g_last_cuda_error = e; }
 
-extern "C" int sw_abi_version(void) { return 1; }
+extern "C" int sw_abi_version(void) { return 2; }
 extern "C" int sw_last_cuda_error(void) { return g_last_cuda_error; }
 extern "C" const char* sw_error_string(int code) {
     switch (code) {

@@ -36,7 +36,7 @@ class FlatAdam:
         self.flat_p = torch.zeros(self.n_pad, device=dev)
         self.exp_avg = torch.zeros(self.n_pad, device=dev)
         self.exp_avg_sq = torch.zeros(self.n_pad, device=dev)
-        self.step_t = torch.zeros(1, device=dev)
+        self.step_t = torch.zeros(2, device=dev)            # [step count, scratch word of the kernel]
         self._symm = None
         if self.world > 1:
             import torch.distributed as dist
@@ -47,7 +47,7 @@ class FlatAdam:
             self._symm = symm_mem.rendezvous(self._buf, group.group_name if hasattr(group, "group_name") else group)
             self.flat_g = self._buf[:self.n_pad]
             self._peer_ptrs = torch.tensor([int(x) for x in self._symm.buffer_ptrs], dtype=torch.int64, device=dev)
-            self._seq = torch.zeros(2, dtype=torch.int32, device=dev)
+            self._seq = torch.zeros(4, dtype=torch.int32, device=dev)     # sequence, CTA counter, status, pad
             torch.cuda.synchronize(dev)
             dist.barrier(group)                       # every rank's flags are zero before anyone signals
         else:
@@ -99,11 +99,20 @@ class FlatAdam:
         # the kernels write the parameters through raw pointers: advance the version counters the packed-weight caches key on
         torch.autograd.graph.increment_version(self.params)
 
+    def check_status(self):
+        """Host-side read of the all-reduce kernel's status word (synchronises): raises if a peer missed a step."""
+        if self.world > 1:
+            code = int(self._seq[2].item())
+            if code:
+                raise _lib.SocialWaysCudaError(
+                    f"sw_allreduce_adam: rank {self.rank} gave up waiting for a peer (status {code}); the step was "
+                    + ("not applied" if code == 1 else "applied, a peer never acknowledged"))
+
     def state_dict(self):
         state, off = {}, 0
         for i, p in enumerate(self.params):
             k = p.numel()
-            state[i] = {"step": self.step_t.detach().clone().reshape(()).cpu(),
+            state[i] = {"step": self.step_t[0].detach().clone().reshape(()).cpu(),
                         "exp_avg": self.exp_avg[off:off + k].view(p.shape).clone(),
                         "exp_avg_sq": self.exp_avg_sq[off:off + k].view(p.shape).clone()}
             off += k
@@ -125,4 +134,4 @@ class FlatAdam:
                     self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
                     step = max(step, float(st["step"]))
                 off += k
-            self.step_t.fill_(step)
+            self.step_t[0] = step

@@ -158,7 +158,7 @@ def pool_bwd(pool_pack, x_last, h, ub, d_pooled, tdot, attn, scenes):
     st_a1, st_g2 = torch.zeros(p, 32, device=dev), torch.zeros(p, 64, device=dev)
     st_g1, st_f = torch.zeros(p, 32, device=dev), torch.zeros(p, 4, device=dev)
     code = _lib.lib().sw_pool_bwd(_lib.ptr(_f32(pool_pack)), _lib.ptr(_f32(x_last)), _lib.ptr(_f32(h)), _lib.ptr(_f32(ub)),
-                                  _lib.ptr(_f32(d_pooled)), _lib.ptr(_f32(tdot)), _lib.ptr(_f32(attn)),
+                                  _lib.ptr(_f32(d_pooled)), _lib.ptr(_f32(tdot)), None, _lib.ptr(_f32(attn)),
                                   _lib.ptr(scenes.offsets), _lib.ptr(scenes.agent_scene), _lib.ptr(scenes.pair_offsets),
                                   _lib.ptr(dub), _lib.ptr(dh), _lib.ptr(st_a1), _lib.ptr(st_g2), _lib.ptr(st_g1),
                                   _lib.ptr(st_f), n, scenes.max_scene, _stream())
@@ -166,7 +166,7 @@ def pool_bwd(pool_pack, x_last, h, ub, d_pooled, tdot, attn, scenes):
     return dub, dh, st_a1, st_g2, st_g1, st_f
 
 
-def decode(lstm_pack, dec_pack, h0, c0, pooled, noise, x_last, n_next, out=None, stash=False):
+def decode(lstm_pack, dec_pack, h0, c0, pooled, noise, x_last, n_next, out=None, stash=False, stash_bufs=None):
     """sw_decode_fwd.  noise [K,N,32] -> out [K,N,n_next,4] (plus the backward stash if asked)."""
     noise = _f32(noise)
     k, n, z = noise.shape
@@ -175,15 +175,17 @@ def decode(lstm_pack, dec_pack, h0, c0, pooled, noise, x_last, n_next, out=None,
     dev = noise.device
     if out is None:
         out = torch.empty(k, n, n_next, 4, device=dev)
-    st = [None] * 4
-    if stash:
+    st = [None] * 5
+    if stash_bufs is not None:          # caller-owned stash (xh, gates, a1, a2, sz): the native training step
+        st = list(stash_bufs)
+    elif stash:
         tl = n_tiles(k * n)
         st = [torch.empty(n_next, tl, 68, 32, device=dev), torch.empty(max(n_next - 1, 1), tl, 5, H, 32, device=dev),
-              torch.empty(n_next, tl, 160, 32, device=dev), torch.empty(n_next, tl, 80, 32, device=dev)]
+              torch.empty(n_next, tl, 160, 32, device=dev), torch.empty(n_next, tl, 80, 32, device=dev), None]
     code = _lib.lib().sw_decode_fwd(_lib.ptr(_f32(lstm_pack)), _lib.ptr(_f32(dec_pack)), _lib.ptr(_f32(h0)),
                                     _lib.ptr(_f32(c0)), _lib.ptr(None if pooled is None else _f32(pooled)),
                                     _lib.ptr(noise), _lib.ptr(_f32(x_last)), _lib.ptr(out),
-                                    _lib.ptr(st[0]), _lib.ptr(st[1]), _lib.ptr(st[2]), _lib.ptr(st[3]),
+                                    _lib.ptr(st[0]), _lib.ptr(st[1]), _lib.ptr(st[2]), _lib.ptr(st[3]), _lib.ptr(st[4]),
                                     n, k, n_next, sm_count(dev), _stream())
     _lib.check(code, "sw_decode_fwd")
     if stash:
@@ -262,7 +264,7 @@ def decode_bwd(lstm_pack_t, dec_pack_t, c0, stash, d_out, n_agents, n_samples):
     code = _lib.lib().sw_decode_bwd(_lib.ptr(_f32(lstm_pack_t)), _lib.ptr(_f32(dec_pack_t)), _lib.ptr(_f32(c0)),
                                     _lib.ptr(gates), _lib.ptr(stash["a1"]), _lib.ptr(stash["a2"]), _lib.ptr(d_out),
                                     _lib.ptr(g_gates), _lib.ptr(g_a1), _lib.ptr(g_a2), _lib.ptr(g_v), _lib.ptr(dh0),
-                                    _lib.ptr(dc0), n_agents, n_samples, t, sm_count(dev), _stream())
+                                    _lib.ptr(dc0), None, None, None, n_agents, n_samples, t, sm_count(dev), _stream())
     _lib.check(code, "sw_decode_bwd")
     return dict(gates=g_gates[:t - 1], a1=g_a1, a2=g_a2, v=g_v, dh0=dh0, dc0=dc0)
 

@@ -283,6 +283,11 @@ class Generator(nn.Module):
             self._pack_cache = (key, packs)
         return self._pack_cache[1]
 
+    def invalidate_packs(self):
+        """Drop the packed-weight cache: call after anything that rewrites the parameters without advancing their
+        version counters (CUDA-graph replay of an optimiser step, raw-pointer kernels)."""
+        self._pack_cache = None
+
     def scene_index(self, sub_batches, n_agents, device):
         if isinstance(sub_batches, ops.SceneIndex):
             return sub_batches

@@ -39,12 +39,14 @@ class SocialWaysTrainer:
         self.n_past, self.n_next = obsv.shape[1], pred.shape[1]
         self.n_train_samples = int(the_batches[self.train_size - 1][1])
         self.n_test_samples = obsv.shape[0] - self.n_train_samples
+        # train.py:96-107 slices both tables BEFORE the n_test_samples == 0 substitution: a single-scene dataset is
+        # trained on that scene and test() iterates over nothing (reports zeros)
+        self.train_batches = the_batches[:self.train_size]
+        self.test_batches = the_batches[self.train_size:]
         if self.n_test_samples == 0:
             self.n_test_samples = 1
             the_batches = np.array([the_batches[0], the_batches[0]])
         self.the_batches = the_batches
-        self.train_batches = the_batches[:self.train_size]
-        self.test_batches = the_batches[self.train_size:]
         self.scale = Scale()
         self.scale.max_x = max(np.max(obsv[:, :, 0]), np.max(pred[:, :, 0]))
         self.scale.min_x = min(np.min(obsv[:, :, 0]), np.min(pred[:, :, 0]))
@@ -319,6 +321,10 @@ class SocialWaysTrainer:
             stats_acc += st["stats"]
             n_iter += 1
             group, count = [], 0
+        # graph.replay() rewrites the parameters through raw pointers without advancing their version counters
+        # (neither capturable Adam nor FlatAdam's python-side increment_version runs on replay): the packed-weight cache
+        # Generator.packs() keys on (data_ptr, _version) would go stale, so test() would evaluate old weights
+        self.generator.invalidate_packs()
         if self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(stats_acc, op=dist.ReduceOp.SUM)
@@ -331,43 +337,158 @@ class SocialWaysTrainer:
             print(" Epc=%4d, Train ADE,FDE = (%.3f, %.3f) | time = %.1f" % (self.epoch, train_ADE, train_FDE, toc - tic))
         return train_ADE, train_FDE
 
+    # ------------------------------------------------------------------ native iteration (native_step.py)
+    def _minibatches(self):
+        """Mini-batch grouping of train() (train.py:446-461): yields (global lo, global hi, scene table rebased to lo)."""
+        group, count = [], 0
+        for ii, batch_i in enumerate(self.train_batches):
+            count += int(batch_i[1] - batch_i[0])
+            group.append(batch_i)
+            if ii >= self.train_size - 1 or count + (self.the_batches[ii + 1][1] - self.the_batches[ii + 1][0]) > self.batch_size:
+                lo, hi = int(group[0][0]), int(group[-1][1])
+                yield lo, hi, np.asarray(group) - lo
+                group, count = [], 0
+
+    def train_native(self, verbose=True, use_graph=True, log_losses=False):
+        """train() with the iteration executed by native_step.NativeStep: ~30 launches of this library's kernels per
+        iteration (no autograd, no cuBLAS, no ATen reductions), one CUDA graph per mini-batch shape.  Needs
+        fused_adam=True (flat parameter / gradient buffers).  Same RNG consumption and quirks as train()."""
+        if not self.fused_adam:
+            raise RuntimeError("train_native() needs fused_adam=True (flat parameter / gradient buffers)")
+        from .native_step import NativePacks, NativeStep
+        tic = time.perf_counter()
+        dev = self.device
+        if not hasattr(self, "_native_packs"):
+            self._native_packs, self._native_steps = NativePacks(self), {}
+            self._pin = {}
+        stats_acc = torch.zeros(8, device=dev, dtype=torch.float64)
+        n_iter = 0
+        for g_lo, g_hi, sub in self._minibatches():
+            global_bs = g_hi - g_lo
+            lo, hi = g_lo, g_hi
+            if self.world_size > 1:       # this rank's contiguous block of scenes
+                s_lo, s_hi, sub = swdist.shard_scenes(sub, self.world_size, self.rank)
+                if s_hi <= s_lo:
+                    raise RuntimeError("train_native(): a rank received no scene of this mini-batch; use train()")
+                lo, hi = g_lo + s_lo, g_lo + s_hi
+            bs = hi - lo
+            key = (global_bs, bs, lo - g_lo, sub.tobytes())
+            ent = self._native_steps.get(key)
+            if ent is None:
+                step = NativeStep(self, self._native_packs, bs, self.generator.scene_index(sub, bs, dev), global_bs)
+                ent = self._native_steps[key] = dict(step=step, graph=None, seen=0)
+            step = ent["step"]
+            # train.py:471-473: two numpy scalars, then the noise of the GLOBAL mini-batch from torch's CPU generator
+            t01 = (float(np.random.uniform(0, 0.1)), float(np.random.uniform(0.9, 1.0)))
+            noise = torch.rand(global_bs, self.noise_len)
+            pin = self._pin.get(global_bs)
+            if pin is None:
+                pin = self._pin[global_bs] = dict(noise=torch.empty(global_bs, self.noise_len).pin_memory(),
+                                                  t=torch.empty(2).pin_memory(), ev=torch.cuda.Event())
+            pin["ev"].synchronize()                           # the previous upload from these pinned buffers has finished
+            pin["noise"].copy_(noise)
+            pin["t"][0], pin["t"][1] = t01
+            step.obsv.copy_(self.dataset_obsv[lo:hi])
+            step.pred.copy_(self.dataset_pred[lo:hi])
+            step.noise.copy_(pin["noise"][lo - g_lo:hi - g_lo], non_blocking=True)
+            step.targets.copy_(pin["t"], non_blocking=True)
+            pin["ev"].record()
+            if use_graph and ent["graph"] is None and ent["seen"] >= 1:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    step.run()
+                ent["graph"] = g
+            if ent["graph"] is not None:
+                ent["graph"].replay()
+            else:
+                step.run()
+            ent["seen"] += 1
+            stats_acc += step.stats
+            if log_losses:                                    # tests: one host read per iteration
+                v = step.stats.tolist()
+                self.loss_log.append(dict(d_loss=v[2], d_fake=v[3], d_real=v[4], d_info=v[5], g_fool=v[6], g_info=v[7]))
+            n_iter += 1
+        self.generator.invalidate_packs()                     # parameters were rewritten through raw pointers
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(stats_acc, op=dist.ReduceOp.SUM)
+        vals = stats_acc.tolist()
+        for o in (self.predictor_optimizer, self.D_optimizer):
+            o.check_status()
+        train_ADE, train_FDE = vals[0] / self.n_train_samples, vals[1] / self.n_train_samples
+        self.last_epoch_mean_losses = dict(zip(("d_loss", "d_fake", "d_real", "d_info", "g_fool", "g_info"),
+                                               [v / max(1, n_iter) for v in vals[2:]]))
+        toc = time.perf_counter()
+        if verbose and self.rank == 0:
+            print(" Epc=%4d, Train ADE,FDE = (%.3f, %.3f) | time = %.1f" % (self.epoch, train_ADE, train_FDE, toc - tic))
+        return train_ADE, train_FDE
+
     # ------------------------------------------------------------------ train.py:563-616
+    def _test_noise(self, scenes, n_gen_samples):
+        """Noise of test() for `scenes` ([start, end) rows of the dataset), drawn from torch's CPU RNG in the reference's
+        order -- per scene, K consecutive torch.rand(bs, noise_len) calls (train.py:583-584).  Consecutive torch.rand calls
+        read consecutive values of ONE stream, so a single torch.rand(total) followed by a per-scene reshape yields
+        bit-identical values (tests/test_entry_points_cpu.py pins this) without scenes x K host calls.
+        Returns a pinned [K, rows, noise_len] tensor, rows relative to scenes[0][0]."""
+        K, nl = n_gen_samples, self.noise_len
+        sizes = np.asarray([int(b[1] - b[0]) for b in scenes], dtype=np.int64)
+        rows = int(sizes.sum())
+        flat = torch.rand(K * rows * nl)
+        noise = torch.empty(K, rows, nl).pin_memory() if self.device.type == "cuda" else torch.empty(K, rows, nl)
+        if len(sizes) and (sizes == sizes[0]).all():           # equal scenes: one permute
+            bs = int(sizes[0])
+            noise.copy_(flat.view(len(sizes), K, bs, nl).permute(1, 0, 2, 3).reshape(K, rows, nl))
+        else:
+            off, a = 0, 0
+            for bs in sizes.tolist():
+                noise[:, a:a + bs] = flat[off:off + K * bs * nl].view(K, bs, nl)
+                off += K * bs * nl
+                a += bs
+        return noise
+
+    def skip_test_rng(self, n_gen_samples=20, linear=False, write_to_file=None, just_one=False):
+        """Consume exactly the CPU random numbers test() would (ranks that do not evaluate call this, so every rank's
+        noise stream stays identical to rank 0's and to a single-GPU run)."""
+        if linear and not write_to_file:
+            return
+        scenes = self.test_batches[:1] if just_one else self.test_batches
+        rows = int(sum(int(b[1] - b[0]) for b in scenes))
+        if rows:
+            torch.rand(n_gen_samples * rows * self.noise_len)
+
     def test(self, n_gen_samples=20, linear=False, write_to_file=None, just_one=False, verbose=True):
-        ade_avg_12, fde_avg_12 = 0, 0
-        ade_min_12, fde_min_12 = 0, 0
-        for ii, batch_i in enumerate(self.test_batches):
-            obsv = self.dataset_obsv[batch_i[0]:batch_i[1]]
-            pred = self.dataset_pred[batch_i[0]:batch_i[1]]
-            current_t = self.dataset_t[batch_i[0]]
-            bs = int(batch_i[1] - batch_i[0])
+        """test() of the reference with ALL test scenes decoded by one predict_k call (the scenes are contiguous rows of the
+        dataset; pooling never crosses `sub_batches`), one best-of-K metrics kernel and ONE device->host read per call.  The
+        reference's loop order survives where it is observable: the noise stream (see _test_noise) and the dump files."""
+        scenes = self.test_batches[:1] if just_one else self.test_batches
+        sums = np.zeros(4)
+        if len(scenes):
+            lo, hi = int(scenes[0][0]), int(scenes[-1][1])
+            obsv, pred = self.dataset_obsv[lo:hi], self.dataset_pred[lo:hi]
             with torch.no_grad():
                 linear_preds = predict_cv(obsv, self.n_next)
                 if linear and not write_to_file:
                     all_preds = torch.cat([linear_preds, torch.zeros_like(linear_preds)], dim=2).unsqueeze(0)
                 else:
-                    # one torch.rand(bs, noise_len) per sample, in the reference's order (:583-584)
-                    noise = torch.stack([torch.rand(bs, self.noise_len) for _ in range(n_gen_samples)]).to(self.device)
-                    all_preds = self.generator.predict_k(obsv, noise, self.n_next)          # [K, bs, T, 4]
-                m = ops.bestofk_metrics(all_preds.contiguous(), pred.contiguous(), self.ss)  # :587,602-607
+                    noise = self._test_noise(scenes, n_gen_samples).to(self.device, non_blocking=True)
+                    sub = np.asarray(scenes, dtype=np.int64) - lo
+                    all_preds = self.generator.predict_k(obsv, noise, self.n_next, sub)      # [K, rows, T, 4]
+                m = ops.bestofk_metrics(all_preds.contiguous(), pred.contiguous(), self.ss)   # :587,602-607, per agent
+                sums = m.double().sum(dim=0).cpu().numpy()                                    # the call's one sync
                 if write_to_file:
-                    file_name = os.path.join(write_to_file, str(self.epoch) + '-' + str(current_t) + '.npz')
-                    print('saving to ', file_name)
-                    np.savez(file_name, timestamp=current_t,
-                             obsvs=self.scale.denormalize(obsv[:, :, :2].cpu().numpy()),
-                             preds_our=self.scale.denormalize(all_preds[:, :, :, :2].cpu().numpy()),
-                             preds_gtt=self.scale.denormalize(pred[:, :, :2].cpu().numpy()),
-                             preds_lnr=self.scale.denormalize(linear_preds[:, :, :2].cpu().numpy()))
-                sums = m.sum(dim=0).tolist()
-                ade_avg_12 += sums[0]
-                fde_avg_12 += sums[1]
-                ade_min_12 += sums[2]
-                fde_min_12 += sums[3]
-            if just_one:
-                break
-        ade_avg_12 /= self.n_test_samples
-        fde_avg_12 /= self.n_test_samples
-        ade_min_12 /= self.n_test_samples
-        fde_min_12 /= self.n_test_samples
+                    ours = self.scale.denormalize(all_preds[:, :, :, :2].cpu().numpy())
+                    o_np = self.scale.denormalize(obsv[:, :, :2].cpu().numpy())
+                    p_np = self.scale.denormalize(pred[:, :, :2].cpu().numpy())
+                    l_np = self.scale.denormalize(linear_preds[:, :, :2].cpu().numpy())
+                    for batch_i in scenes:
+                        a, b = int(batch_i[0]) - lo, int(batch_i[1]) - lo
+                        current_t = self.dataset_t[batch_i[0]]
+                        file_name = os.path.join(write_to_file, str(self.epoch) + '-' + str(current_t) + '.npz')
+                        print('saving to ', file_name)
+                        np.savez(file_name, timestamp=current_t, obsvs=o_np[a:b], preds_our=ours[:, a:b],
+                                 preds_gtt=p_np[a:b], preds_lnr=l_np[a:b])
+        ade_avg_12, fde_avg_12, ade_min_12, fde_min_12 = (float(v) / self.n_test_samples for v in sums)
         if verbose:
             print('Avg ADE,FDE (12)= (%.3f, %.3f) | Min(20) ADE,FDE (12)= (%.3f, %.3f)'
                   % (ade_avg_12, fde_avg_12, ade_min_12, fde_min_12))
@@ -392,6 +513,17 @@ class SocialWaysTrainer:
         self.predictor_optimizer.load_state_dict(checkpoint['pred_optimizer'])
         self.D.load_state_dict(checkpoint['D_dict'])
         self.D_optimizer.load_state_dict(checkpoint['D_optimizer'])
+        if self.cuda_graph and not self.fused_adam:
+            # Optimizer.load_state_dict() takes `capturable` (and the host-side `step`) from the checkpoint; reference and
+            # eager checkpoints store capturable=False, which fails torch's check at graph capture.  Restore what this
+            # trainer was built with: capturable groups, step counters as fp32 device tensors.
+            for o in (self.predictor_optimizer, self.D_optimizer):
+                for g in o.param_groups:
+                    g['capturable'] = True
+                for st in o.state.values():
+                    if 'step' in st:
+                        st['step'] = torch.as_tensor(st['step'], dtype=torch.float32).to(self.device)
+        self.generator.invalidate_packs()
         return checkpoint['epoch'] + 1
 
     def reference_weights(self):

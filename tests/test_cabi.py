@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, name), f"{name} declared in the header but not exported"
     assert sorted(_lib.exported_symbols()) == declared, "ctypes prototypes out of sync with the header"
     lib = _lib.lib()
-    assert lib.sw_abi_version() == 1
+    assert lib.sw_abi_version() == 2
     assert lib.sw_decode_pack_floats() == 160 * 160 + 160 + 160 * 80 + 80 + 160 + 2
     assert lib.sw_pool_pack_floats() == 128 + 64 * 32 + 64
     assert b"argument" in lib.sw_error_string(-1)
@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 def test_null_pointers_are_rejected_without_touching_the_gpu():
     from socialways_b200 import _lib
     lib = _lib.lib()
-    assert lib.sw_decode_fwd(*([None] * 12), 1, 1, 1, 148, None) == -1
+    assert lib.sw_decode_fwd(*([None] * 13), 1, 1, 1, 148, None) == -1
     assert lib.sw_pool_fwd(None, None, None, None, None, None, None, None, 1, 1, None) == -1
     assert lib.sw_bestofk_metrics(None, None, 1.0, 1, 1, 1, None, None) == -1
     assert lib.sw_lstm_seq_fwd(None, None, 2, 1, 8, *([None] * 8), 148, None) == -1
@@ -82,3 +82,31 @@ def test_null_pointers_are_rejected_by_the_new_entry_points():
     assert lib.sw_allreduce_adam(None, 0, 2, 4, 32, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, None) == -1
     assert lib.sw_pool_fwd_tcx(None, None, None, None, None, None, None, None, 1, 1, None) == -1
     assert lib.sw_pool_tcx_max_scene() == 64 and lib.sw_lsap_smem_bytes(20) == 20 * 42
+
+
+def test_training_step_entry_points_reject_bad_arguments():
+    """Round-2 entry points (native training iteration): argument checks only, nothing touches a GPU."""
+    import ctypes
+    from socialways_b200 import _lib
+    from socialways_b200.native_step import ContractJob
+    lib = _lib.lib()
+    assert lib.sw_gen_pack(None, *([None] * 7), None) == -1
+    assert lib.sw_gen_pack_bwd(None, None, None, None, None, 1, None) == -1
+    assert lib.sw_disc_pack(None, 48, None, None, None, None) == -1
+    assert lib.sw_disc_step(*([None] * 1), 48, 0, None, None, None, None, 8, None, 32, None, 1.0, 0.5, *([None] * 7), 4, 148, None) == -1
+    assert lib.sw_rows_linear(None, 64, None, None, None, None, None, 65, 4, 64, 65, None) == -1
+    assert lib.sw_train_stats(None, None, 4, 12, 1.0, None, 0, None, 0, 1.0, 0.5, None, None, None, 148, None) == -1
+    assert lib.sw_set_peer_wait_timeout_ms(0) == -1 and lib.sw_set_peer_wait_timeout_ms(60000) == 0
+    sizes = [ctypes.c_int() for _ in range(7)]
+    assert lib.sw_gen_pack_sizes(*[ctypes.byref(s) for s in sizes]) == 0
+    assert [s.value for s in sizes] == [69 * 256, 256 * 68, 38802, 23200, 2240, 65 * 65, 65 * 64]
+    xr, gr = ctypes.c_int(), ctypes.c_int()
+    assert lib.sw_disc_step_image_rows(48, ctypes.byref(xr), ctypes.byref(gr)) == 0 and (xr.value, gr.value) == (304, 196)
+    # contraction planning is host arithmetic: a job over many images is split into chunks with a partial-tile workspace
+    assert ctypes.sizeof(ContractJob) == 104
+    job = ContractJob(1 << 20, 1 << 21, 1 << 22, None, 68 * 32, 256 * 32, 0, 68, 0, 256, 5000, 5000 * 32, 0, 0, 256, 1, 0, 0, 1.0, 0)
+    ws, nc = ctypes.c_longlong(), ctypes.c_int()
+    assert lib.sw_contract_plan((ContractJob * 1)(job), 1, 148, ctypes.byref(ws), ctypes.byref(nc)) == 0
+    assert nc.value == 2 * 4 and ws.value > 0 and ws.value % 4096 == 0
+    bad = ContractJob(None, None, None, None, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0)
+    assert lib.sw_contract_plan((ContractJob * 1)(bad), 1, 148, ctypes.byref(ws), ctypes.byref(nc)) == -1

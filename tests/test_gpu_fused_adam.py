@@ -38,7 +38,7 @@ def test_flat_adam_matches_torch_adam():
     # round trip through the torch-layout state dict
     again = FlatAdam([torch.nn.Parameter(p.detach().clone()) for p in mine], lr=5e-4)
     again.load_state_dict(sd)
-    assert again.lr == 1e-3 and float(again.step_t.item()) == 25.0
+    assert again.lr == 1e-3 and float(again.step_t[0].item()) == 25.0
     assert torch.equal(again.exp_avg[:again.n], o_mine.exp_avg[:o_mine.n])
 
 

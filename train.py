@@ -9,7 +9,7 @@ Flags ADDED here (the reference hard-codes these as module constants / paths, tr
   --input-file      dataset npz (reference: '../hotel-8-12.npz')
   --model-file      checkpoint path (reference: '../trained_models/<model>-<dataset>.pt')
   --out-dir         where test() dumps go (reference: '../medium/<dataset>/<model>/<epoch>')
-  --seed            seeds numpy and torch (the reference seeds nothing)
+  --seed            seeds numpy and torch (the reference seeds nothing; under torchrun rank 0's seed is broadcast)
   --test-samples    K of the periodic test() call (reference: 128, train.py:668)
   --cuda-graph      replay the whole GAN iteration from a CUDA graph per batch shape (5x at batch 256)
   --fused-adam      one kernel per optimiser step on flat buffers (fused_optim.FlatAdam); under torchrun it also carries
@@ -60,12 +60,11 @@ def main():
     args = parser.parse_args()
     from socialways_b200.trainer import SocialWaysTrainer
     model_file = args.model_file or '../trained_models/' + args.model + '-' + args.dataset + '.pt'
-    if args.seed is not None:
-        np.random.seed(args.seed)
-        torch.manual_seed(args.seed)
     print(os.path.dirname(os.path.realpath(__file__)))
     device = "cuda"
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:                   # torchrun: one rank per GPU, scenes sharded
+    distributed = int(os.environ.get("WORLD_SIZE", "1")) > 1
+    seed = args.seed
+    if distributed:                                                  # torchrun: one rank per GPU, scenes sharded
         import torch.distributed as dist
         local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(local)
@@ -73,11 +72,23 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(device))
         if args.cuda_graph and not args.fused_adam:
             raise SystemExit("--cuda-graph under torchrun needs --fused-adam (NCCL calls are not captured)")
+        # the sharded step relies on IDENTICAL numpy / torch CPU RNG streams on every rank (labels and noise are drawn for
+        # the global mini-batch everywhere): without --seed rank 0 picks one and every rank adopts it
+        box = [int(np.random.SeedSequence().entropy % (2 ** 31)) if seed is None else seed]
+        dist.broadcast_object_list(box, src=0)
+        seed = box[0]
+    if seed is not None:
+        np.random.seed(seed)
+        torch.manual_seed(seed)
     data = np.load(args.input_file)
     tr = SocialWaysTrainer(data, batch_size=args.batch_size, hidden_size=args.hidden_size,
                            use_social=args.use_social, n_unrolling_steps=args.unrolling_steps,
                            lr_g=args.g_learning_rate, lr_d=args.d_learning_rate, cuda_graph=args.cuda_graph,
                            fused_adam=args.fused_adam, device=device)
+    if distributed:                                                  # replicas start from rank 0's parameters, whatever built them
+        for p in list(tr.generator.parameters()) + list(tr.D.parameters()):
+            dist.broadcast(p.data, src=0)
+        tr.generator.invalidate_packs()
     print(args.input_file, ' # Training samples: ', tr.n_train_samples)
     print('hidden dim = %d | lr(G) =  %.5f | lr(D) =  %.5f' % (args.hidden_size, args.g_learning_rate, args.d_learning_rate))
     if os.path.isfile(model_file):                                   # train.py:622-637
@@ -88,16 +99,21 @@ def main():
     for epoch in trange(start_epoch, args.epochs + 1):               # train.py:646-668
         tr.epoch = epoch
         (tr.train_graphed if args.cuda_graph else tr.train)()
-        if tr.rank != 0:                                            # replicas are bit-identical: rank 0 writes files
-            continue
-        if epoch % 50 == 0:
-            print('Saving model to file ...', model_file)
-            os.makedirs(os.path.dirname(os.path.abspath(model_file)), exist_ok=True)
-            torch.save(tr.state(), model_file)
-        if epoch % 5 == 0:
-            wr_dir = os.path.join(args.out_dir or ('../medium/' + args.dataset + '/' + args.model), str(epoch))
-            os.makedirs(wr_dir, exist_ok=True)
-            tr.test(args.test_samples, write_to_file=wr_dir, just_one=True)
+        if tr.rank == 0:                                            # replicas are bit-identical: rank 0 writes files
+            if epoch % 50 == 0:
+                print('Saving model to file ...', model_file)
+                os.makedirs(os.path.dirname(os.path.abspath(model_file)), exist_ok=True)
+                torch.save(tr.state(), model_file)
+            if epoch % 5 == 0:
+                wr_dir = os.path.join(args.out_dir or ('../medium/' + args.dataset + '/' + args.model), str(epoch))
+                os.makedirs(wr_dir, exist_ok=True)
+                tr.test(args.test_samples, write_to_file=wr_dir, just_one=True)
+        elif epoch % 5 == 0:
+            tr.skip_test_rng(args.test_samples, write_to_file=True, just_one=True)   # same CPU noise stream as rank 0
+        if distributed and (epoch % 5 == 0 or epoch % 50 == 0):
+            # nobody starts the next epoch (and spins on rank 0's flags inside the fused all-reduce kernel) while rank 0
+            # is still writing dumps or the checkpoint
+            dist.barrier()
 
 
 if __name__ == '__main__':
