@@ -21,6 +21,13 @@ pair x 12 steps.
             predict() calls, per-agent attention loop) on the host cores, bounded sample.
 `--impl reference`: the same CPU arm as its own JSON line (the reference is Python over torch and
             cannot travel to the GPU box; the oracle port restates it).
+`train_step`: the OTHER half of north_star -- the GAN training iteration (train(), reference train.py:439-560) on
+            BASELINE configs[3] (toy set scaled to 65 532 trajectories, 6-agent scenes, obs 2 / pred 2, use_social, unroll 1):
+            scenes of every mini-batch sharded over the N ranks, the iteration = ~30 launches of this library's kernels
+            replayed from one CUDA graph (socialways_b200/native_step.py), the gradient all-reduce done by peer loads over
+            NVLink inside the Adam kernel (csrc/flat_adam.cu).  Reported per global batch size: ms per iteration (device clock,
+            max over ranks), agents/s, launches per iteration, and `train_parity_max_abs` = the largest weight difference
+            between the N-rank native run and a single-GPU run of the autograd trainer from the same seeds.
 """
 import argparse
 import json
@@ -59,6 +66,28 @@ NOTE_OF = {"fp32": "fp32 FFMA path; CUDA-core fp32 peak is ~74 TFLOP/s",
 def make_scenes(n_scenes, seed):
     from golden_data import synthetic_scenes
     return synthetic_scenes([A_PER_SCENE] * n_scenes, n_past=N_PAST, n_next=N_NEXT, seed=seed)
+
+
+def normalised(data):
+    """Scale-normalised observations / ground truth with the package's own Scale (train.py:113-121)."""
+    from socialways_b200.scale import Scale
+    o, p = np.array(data["obsvs"], dtype=np.float32), np.array(data["preds"], dtype=np.float32)
+    sc = Scale()
+    sc.max_x, sc.min_x = max(o[..., 0].max(), p[..., 0].max()), min(o[..., 0].min(), p[..., 0].min())
+    sc.max_y, sc.min_y = max(o[..., 1].max(), p[..., 1].max()), min(o[..., 1].min(), p[..., 1].min())
+    sc.calc_scale(keep_ratio=True)
+    return sc.normalize(o), sc.normalize(p), float(sc.sx)
+
+
+def bind_to_gpu_numa(index):
+    """Pin this rank's host threads (and so its pinned staging buffers, first touch) to the CPUs local to its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:                                   # best effort: missing NVML / no permission changes nothing else
+        return None
 
 
 def peaks():
@@ -167,30 +196,155 @@ def workload_config(args, scenes):
             "l2_policy": "per-step inputs+outputs (noise 128 B + pred 192 B per trajectory) exceed the 126 MB L2"}
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# train_step: the GAN training iteration (reference train(), train.py:439-560) on BASELINE configs[3]
+# ------------------------------------------------------------------------------------------------------------------
+TOY_TO, TOY_TP, TOY_A = 2, 2, 6
+# algorithmic FLOPs per agent and iteration, SURVEY.md 8(d): 5 x predict-forward equivalents (3 fwd + 1 bwd ~ 2 fwd) +
+# 15 x discriminator-forward equivalents (5 fwd + 5 bwd), at the toy shapes (obs 2 / pred 2, 6-agent scenes)
+_PREDICT_FWD = TOY_TO * 66_048 + 8_192 + TOY_A * 12_736 + TOY_TP * 83_360 + (TOY_TP - 1) * 66_048
+_D_FWD = TOY_TO * 2 * (4 + 64) * 256 + 2 * (64 * 32 + 32 * 32 + 4 * TOY_TP * 32 + 32 * 32 + 64 * 32 + 32 + 64 * 32 + 64)
+TRAIN_FLOPS_PER_AGENT = 5 * _PREDICT_FWD + 15 * _D_FWD
+
+
+def toy_dataset(n):
+    from socialways_b200.toy import create_samples, pack_scenes
+    state = np.random.get_state()
+    np.random.seed(30)                                   # create_toy.py:145
+    samples, ts = create_samples(n, TOY_A, 3, n_per_batch=TOY_A)     # n_per_batch = n_conditions: 6-agent scenes
+    np.random.set_state(state)
+    o, p, t, b = pack_scenes(samples, ts)
+    return dict(obsvs=o, preds=p, times=t, batches=b)
+
+
+def train_cpu_baseline():
+    """The oracle port of the reference's train() on the host cores, bounded sample (toy 216 / batch 64, one epoch)."""
+    from oracle import socialways_oracle as so
+    torch.set_num_threads(os.cpu_count() or 1)
+    cpu = so.OracleTrainer(so.init_weights(n_next=2), toy_dataset(216), batch_size=64, use_social=True, pool="loop")
+    t0 = time.perf_counter()
+    cpu.train_epoch()
+    dt = time.perf_counter() - t0
+    return {"value": cpu.n_train / dt, "unit": "agents/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"toy 216 trajectories / 6-agent scenes, batch 64, one epoch of train() ({dt:.2f} s)"}
+
+
+def train_parity(world, rank, dev):
+    """N-rank native training vs ONE GPU running the autograd trainer (torch.optim.Adam, eager) from the same seeds on a
+    small ragged data set: largest weight difference, and whether every rank holds bit-identical weights."""
+    import torch.distributed as dist
+    from golden_data import synthetic_scenes
+    from socialways_b200.trainer import SocialWaysTrainer
+    rng = np.random.RandomState(3)
+    data = synthetic_scenes(list(rng.randint(1, 9, size=200)), seed=8)
+
+    def run(native):
+        torch.manual_seed(2)                                      # module construction draws the initial weights
+        tr = SocialWaysTrainer(data, batch_size=256, use_social=True, n_unrolling_steps=1, device=str(dev),
+                               world=None if native else (1, 0), fused_adam=native)
+        np.random.seed(5)
+        torch.manual_seed(5)
+        for _ in range(3):                                        # epoch 1 eager, epoch 2 captures the graphs, epoch 3 replays
+            (tr.train_native if native else tr.train)(verbose=False)
+        return tr.reference_weights()
+
+    w_n = run(True)
+    identical = True
+    if world > 1:
+        for k, v in w_n.items():
+            ref = v.clone()
+            dist.broadcast(ref, src=0)
+            identical = identical and bool(torch.equal(ref, v))
+        flag = torch.tensor([1.0 if identical else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        identical = flag.item() > 0
+    worst = None
+    if rank == 0:
+        w_1 = run(False)
+        worst = max((w_n[k] - w_1[k]).abs().max().item() for k in w_1)
+    return worst, identical
+
+
+def train_block(args, world, rank, dev):
+    import torch.distributed as dist
+    from socialways_b200.native_step import NativeStep
+    from socialways_b200.trainer import SocialWaysTrainer
+    parity, identical = train_parity(world, rank, dev)
+    data = toy_dataset(args.train_n)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    results = []
+    for gbs in [int(x) for x in args.train_batches.split(",")]:
+        np.random.seed(0)
+        torch.manual_seed(0)
+        tr = SocialWaysTrainer(data, batch_size=gbs, use_social=True, n_unrolling_steps=1, device=str(dev), fused_adam=True)
+        iters = sum(1 for _ in tr._minibatches())
+        for _ in range(3):                                        # eager pass, graph capture, one replayed epoch (warm-up)
+            tr.train_native(verbose=False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = ev(), ev()
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(args.train_epochs):
+            ade, fde = tr.train_native(verbose=False)
+        e1.record()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - w0
+        if world > 1:
+            dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1) * 1e-3, wall], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, wall_s = (float(x) / args.train_epochs for x in t.cpu())
+        results.append({"global_batch": gbs, "iterations_per_epoch": iters, "ms_per_iteration": 1e3 * dev_s / iters,
+                        "agents_per_s": tr.n_train_samples / dev_s, "epoch_device_s": dev_s, "epoch_wall_s": wall_s,
+                        "achieved_tflops_fp32": tr.n_train_samples * TRAIN_FLOPS_PER_AGENT / dev_s / 1e12,
+                        "cuda_graphs": sum(1 for e in tr._native_steps.values() if e["graph"] is not None),
+                        "train_ade": ade, "train_fde": fde})
+        del tr
+    out = None
+    if rank == 0:
+        out = {"workload": f"BASELINE configs[3]: toy set scaled to {args.train_n} trajectories (6 conditions x 3 modes, 6-agent scenes, "
+                           "obs 2 / pred 2), use_social=True, unroll 1 (2 D updates + 1 G update per iteration), 4/5 of the scenes train",
+               "mode": "native step (socialways_b200/native_step.py): own kernels only, one CUDA graph per mini-batch shape",
+               "n_gpus": world, "parallelism": f"scenes of every mini-batch sharded x{world}",
+               "collective": "none (1 GPU)" if world == 1 else
+                             "3 per iteration, each = peer loads over NVLink (symmetric memory) inside the Adam kernel, rank order; no NCCL call",
+               "launches_per_iteration": NativeStep.launches_per_iteration(True, 1),
+               "results": results,
+               "flops_per_agent_iteration_algorithmic": TRAIN_FLOPS_PER_AGENT,
+               "fp32_cuda_core_peak_tflops_nominal": 74.4,
+               "train_parity_max_abs": parity, "replicas_bit_identical": identical,
+               "train_parity_note": "largest |w_N-rank native - w_1-GPU autograd trainer| after 3 epochs of a 200-scene ragged set (batch 256) "
+                                    "(obs 8 / pred 12), same seeds; Adam amplifies fp32 rounding differences of the gradients"}
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = train_cpu_baseline()
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     import socialways_b200 as sw
     from socialways_b200 import ops
-    from oracle import socialways_oracle as so          # weights init + CPU baseline only
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpus = bind_to_gpu_numa(local)          # before any pinned allocation: staging buffers land on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    P = so.init_weights(seed=0)
-    gen = sw.Generator(use_social=True)
-    gen.load_state_dict({k: v for k, v in P.items() if not k.startswith("D.")})
-    gen = gen.to(dev)
+    torch.manual_seed(0)                    # random-init weights of the architecture (torch's default module init,
+    gen = sw.Generator(use_social=True).to(dev)     # the stream the reference's own constructors draw from, train.py:370-376)
 
     n_scenes = args.scenes
     data = make_scenes(n_scenes, seed=100 + rank)            # every rank its own shard of scenes
-    sc = so.IsoScale(data["obsvs"], data["preds"])
-    obsv_h = torch.from_numpy(sc.normalize(data["obsvs"])).pin_memory()
-    pred_h = torch.from_numpy(sc.normalize(data["preds"])).pin_memory()
+    obsv_n, pred_n, ss = normalised(data)
+    obsv_h = torch.from_numpy(obsv_n).pin_memory()
+    pred_h = torch.from_numpy(pred_n).pin_memory()
     n = obsv_h.shape[0]
     g = torch.Generator().manual_seed(7 + rank)
     noise_h = torch.rand(K_SAMPLES, n, 32, generator=g).pin_memory()
@@ -240,7 +394,7 @@ def run_ours(args):
         if timed:
             e1.record()
             events.append((e0, e1))
-        return ops.bestofk_metrics(out, pred_d, sc.sx)
+        return ops.bestofk_metrics(out, pred_d, ss)
 
     def barrier():
         if world > 1:
@@ -284,58 +438,73 @@ def run_ours(args):
                              dev=(out - ref_out).abs().max().item(), metrics=m_other.sum(0).cpu().numpy() / n)
 
     # ---------------- end-to-end: host buffers in, metrics out, copies inside the timed region ----------------
+    # Two variants of the public call Generator.predict_k:
+    #   device noise (headline `e2e`): predict_k(obsv, None, ..., seed=, k=) -- the K x N x 32 latent noise is drawn on the GPU
+    #       (Philox4x32-10, csrc/noise.cu); per step the host sends observations + ground truth and reads the metrics back.
+    #   host noise (`e2e_host_noise`): the reference's contract -- the caller draws the noise on the CPU (train.py:584) and
+    #       uploads it: 128 B per trajectory over PCIe, 94 % of the step's host->device bytes.
     copy_stream = torch.cuda.Stream()
     bufs = [dict(obsv=torch.empty_like(obsv_d), pred=torch.empty_like(pred_d), noise=torch.empty_like(noise_d),
                  ready=torch.cuda.Event(), free=torch.cuda.Event()) for _ in range(2)]
     res_h = [torch.empty(n, 4).pin_memory() for _ in range(2)]
     out2 = out
 
-    def upload(i):
+    def upload(i, with_noise):
         b = bufs[i % 2]
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(b["free"])
             b["obsv"].copy_(obsv_h, non_blocking=True)
             b["pred"].copy_(pred_h, non_blocking=True)
-            b["noise"].copy_(noise_h, non_blocking=True)
+            if with_noise:
+                b["noise"].copy_(noise_h, non_blocking=True)
             b["ready"].record(copy_stream)
 
-    def e2e_steps(count):
+    def e2e_steps(count, host_noise):
         main = torch.cuda.current_stream()
         for b in bufs:
             b["free"].record(main)
-        upload(0)
+        upload(0, host_noise)
         for i in range(count):
             b = bufs[i % 2]
             if i + 1 < count:
-                upload(i + 1)
+                upload(i + 1, host_noise)
             main.wait_event(b["ready"])
-            hat = gen.predict_k(b["obsv"], b["noise"], N_NEXT, scenes, out=out2, precision=args.precision)
-            met = ops.bestofk_metrics(hat, b["pred"], sc.sx)
+            if host_noise:
+                hat = gen.predict_k(b["obsv"], b["noise"], N_NEXT, scenes, out=out2, precision=args.precision)
+            else:
+                hat = gen.predict_k(b["obsv"], None, N_NEXT, scenes, out=out2, precision=args.precision, seed=(1234 + rank, i),
+                                    k=K_SAMPLES, noise_buf=b["noise"])
+            met = ops.bestofk_metrics(hat, b["pred"], ss)
             res_h[i % 2].copy_(met, non_blocking=True)
             b["free"].record(main)
         main.synchronize()
 
-    e2e_steps(max(2, min(args.warmup, 3)))
-    barrier()
-    w0 = time.perf_counter()
-    x0, x1 = ev(), ev()
-    x0.record()
-    e2e_steps(args.steps)
-    x1.record()
-    barrier()
-    e2e_wall = time.perf_counter() - w0
-    e2e_s = x0.elapsed_time(x1) * 1e-3          # device clock; the wall clock (below) must agree
+    e2e_res = {}
+    for host_noise in (False, True):
+        e2e_steps(max(2, min(args.warmup, 3)), host_noise)
+        barrier()
+        w0 = time.perf_counter()
+        x0, x1 = ev(), ev()
+        x0.record()
+        e2e_steps(args.steps, host_noise)
+        x1.record()
+        barrier()
+        e2e_res[host_noise] = dict(wall=time.perf_counter() - w0, dev=x0.elapsed_time(x1) * 1e-3)   # device clock; wall must agree
+    e2e_s, e2e_wall = e2e_res[False]["dev"], e2e_res[False]["wall"]
+    e2e_host_s = e2e_res[True]["dev"]
     clocks = sampler.stop() if rank == 0 else None
+
+    train = train_block(args, world, rank, dev) if not args.no_train else None
 
     if world > 1:
         names = sorted(others)
-        t = torch.tensor([ms, e2e_s, dec_ms] + [others[k]["ms"] for k in names] + [others[k]["dec_ms"] for k in names],
+        t = torch.tensor([ms, e2e_s, dec_ms, e2e_host_s] + [others[k]["ms"] for k in names] + [others[k]["dec_ms"] for k in names],
                          device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         vals = [float(x) for x in t.cpu()]
-        ms, e2e_s, dec_ms = vals[:3]
+        ms, e2e_s, dec_ms, e2e_host_s = vals[:4]
         for i, k in enumerate(names):
-            others[k]["ms"], others[k]["dec_ms"] = vals[3 + i], vals[3 + len(names) + i]
+            others[k]["ms"], others[k]["dec_ms"] = vals[4 + i], vals[4 + len(names) + i]
 
     if rank == 0:
         pk_ = peaks()
@@ -343,16 +512,27 @@ def run_ours(args):
         e2e_value = world * traj_per_step * args.steps / e2e_s
         ach = traj_per_step * FLOPS_PER_TRAJ / (dec_ms * 1e-3) / 1e12
         peak = pk_["bf16_sustained"]
-        h2d = obsv_h.numel() * 4 + pred_h.numel() * 4 + noise_h.numel() * 4
+        h2d_dev = obsv_h.numel() * 4 + pred_h.numel() * 4
+        h2d_host = h2d_dev + noise_h.numel() * 4
         line = {
             "metric": "predicted_trajectories_per_sec", "value": value, "unit": "traj/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF[args.precision],
             "data": "synthetic",
             "config": workload_config(args, n_scenes),
-            "e2e": {"value": e2e_value, "unit": "traj/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": n * 16,
-                    "wall_s": e2e_wall, "device_s": e2e_s},
+            "e2e": {"value": e2e_value, "unit": "traj/s", "h2d_bytes_per_step": h2d_dev, "d2h_bytes_per_step": n * 16,
+                    "wall_s": e2e_wall, "device_s": e2e_s,
+                    "noise": "drawn on the device (Philox4x32-10, predict_k(noise=None, seed=, k=)); same distribution as the "
+                             "reference's torch.rand, different stream"},
+            "e2e_host_noise": {"value": world * traj_per_step * args.steps / e2e_host_s, "unit": "traj/s",
+                               "h2d_bytes_per_step": h2d_host, "d2h_bytes_per_step": n * 16, "device_s": e2e_host_s,
+                               "h2d_gbs_per_gpu": h2d_host * args.steps / e2e_host_s / 1e9,
+                               "noise": "caller-supplied host tensor (the reference's contract, train.py:584): 128 B per "
+                                        "trajectory over PCIe -- the limiter of this variant when several GPUs share the "
+                                        "host's memory system (profiles/r1_h2d_probe.txt: 55 GB/s for one GPU alone)"},
             "gpu_launches": 4 * args.steps,
+            "host_cpu_affinity": None if cpus is None else f"{len(cpus)} cpus ({cpus[0]}-{cpus[-1]}), GPU-local (NVML)",
+            "train_step": train,
             "clocks": clocks,
             "roofline": {"kernel": KERNEL_OF[args.precision],
                          "bound": "tensor", "achieved": ach, "peak": peak,
@@ -411,6 +591,10 @@ def main():
     ap.add_argument("--scenes", type=int, default=16384, help="scenes per GPU per step")
     ap.add_argument("--cpu-scenes", type=int, default=384, help="scenes in the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the train_step block (GAN training iteration, configs[3])")
+    ap.add_argument("--train-n", type=int, default=65536 // 6 * 6, help="trajectories of the scaled toy set (configs[3])")
+    ap.add_argument("--train-batches", default="4096,49152", help="global mini-batch sizes of the train_step block")
+    ap.add_argument("--train-epochs", type=int, default=3, help="timed epochs per batch size")
     ap.add_argument("--precision", default="fp16x2", choices=["fp32", "fp16x2", "bf16"],
                     help="decode kernel of the headline line: fp16x2 = tcgen05 on fp16 hi/lo split operands "
                          "(fp32-faithful, default), fp32 = CUDA-core FFMA, bf16 = tcgen05 on bf16 operands (fast mode)")

@@ -91,6 +91,14 @@ class NativePacks:
         _lib.check(lib.sw_disc_pack_sizes(self.pred_dim, *[ctypes.byref(s) for s in sd]), "sw_disc_pack_sizes")
         self.d_lstm, self.d_lstm_t, self.d_heads = (torch.empty(s.value, device=dev) for s in sd)
         self.device = dev
+        # D.load(backup) (train.py:311-316): the nn.Linear parameters = every discriminator tensor after the LSTM's four
+        lin = self.disc_params[4:]
+        flat = trainer.D_optimizer.flat_p
+        off0 = (lin[0].data_ptr() - flat.data_ptr()) // 4
+        off1 = (lin[-1].data_ptr() - flat.data_ptr()) // 4 + lin[-1].numel()
+        if off1 - off0 != sum(p.numel() for p in lin):
+            raise _lib.SocialWaysCudaError("native step: the discriminator's Linear parameters are not contiguous in the flat buffer")
+        self.d_linear = flat[off0:off1]
 
     def pack_generator(self):
         _lib.check(_lib.lib().sw_gen_pack(_ptr_array(self.gen_params), self.enc.data_ptr(), self.enc_t.data_ptr(),
@@ -154,15 +162,7 @@ class NativeStep:
         self.stats_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         if self.social:
             _ = scenes.pair_offsets
-        # D.load(backup) (train.py:311-316): the nn.Linear parameters = every discriminator tensor after the LSTM's four
-        lin = packs.disc_params[4:]
-        first, last = lin[0], lin[-1]
-        flat = trainer.D_optimizer.flat_p
-        off0 = (first.data_ptr() - flat.data_ptr()) // 4
-        off1 = (last.data_ptr() - flat.data_ptr()) // 4 + last.numel()
-        if off1 - off0 != sum(p.numel() for p in lin):
-            raise _lib.SocialWaysCudaError("native step: the discriminator's Linear parameters are not contiguous in the flat buffer")
-        self.d_linear = flat[off0:off1]
+        self.d_linear = packs.d_linear
         self.backup = torch.empty_like(self.d_linear)
         self._build_jobs()
 

@@ -297,6 +297,16 @@ def disc_heads_bwd(pack, xrec, pred_dim, d_label, d_code, n_latent=2, want_dh=Tr
     return d_h, d_pred, grec
 
 
+def noise_uniform(shape, device, seed, offset=0, out=None):
+    """sw_noise_uniform: uniform [0, 1) fp32 noise drawn on the device (Philox4x32-10 keyed by seed, counter offset)."""
+    if out is None:
+        out = torch.empty(*shape, device=device)
+    code = _lib.lib().sw_noise_uniform(_lib.ptr(out), out.numel(), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1),
+                                       sm_count(out.device), _stream())
+    _lib.check(code, "sw_noise_uniform")
+    return out
+
+
 def bestofk_metrics(pred, gt, ss):
     """sw_bestofk_metrics.  pred [K,N,T,4], gt [N,T,2] -> [N,4] (avg ADE, avg FDE, min ADE, min FDE)."""
     pred, gt = _f32(pred), _f32(gt)

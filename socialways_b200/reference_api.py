@@ -301,16 +301,24 @@ class Generator(nn.Module):
         return self._scene_cache[key]
 
     @torch.no_grad()
-    def predict_k(self, obsv_p, noise, n_next, sub_batches=(), out=None, precision=None):
+    def predict_k(self, obsv_p, noise, n_next, sub_batches=(), out=None, precision=None, seed=None, k=None, noise_buf=None):
         """K-sample predict(): noise [K,N,32] -> [K,N,n_next,4].  The observation encoding and the
         pooled social vector do not depend on the sample and are computed once.
         precision: "fp32" = FFMA decode kernel; "fp16x2" = tcgen05 kernel on fp16 hi/lo split operands
-        (fp32-faithful, ~1e-6); "bf16" = tcgen05 kernel on bf16 operands (fast mode, ~2e-3)."""
+        (fp32-faithful, ~1e-6); "bf16" = tcgen05 kernel on bf16 operands (fast mode, ~2e-3).
+        noise=None, seed=s, k=K: the K x N x 32 latent noise is drawn ON THE DEVICE (Philox4x32-10, sw_noise_uniform) instead
+        of being supplied by the caller -- same distribution as the reference's torch.rand (train.py:584), a different
+        stream, and no 128 B / trajectory upload; `seed` may be an int or (seed, offset)."""
         if not obsv_p.is_cuda:
             raise SocialWaysCudaError("predict() runs on CUDA tensors only (no CPU fallback)")
         precision = precision or self.inference_precision
         pk = self.packs()
         n = obsv_p.shape[0]
+        if noise is None:
+            if seed is None or k is None:
+                raise ValueError("predict_k: give `noise`, or `seed` and `k` for device-side noise")
+            sd, off = (seed if isinstance(seed, tuple) else (seed, 0))
+            noise = ops.noise_uniform((k, n, self.noise_len), obsv_p.device, sd, off, out=noise_buf)
         if precision == "fp16x2":           # both recurrent kernels on the tensor cores (fp16 hi/lo split operands)
             enc = ops.lstm_seq_tcx(*pk["enc_tcx"], obsv_p)
         else:

@@ -349,6 +349,20 @@ class SocialWaysTrainer:
                 yield lo, hi, np.asarray(group) - lo
                 group, count = [], 0
 
+    def _native_empty_iteration(self):
+        """This rank holds no scene of the mini-batch: take part in the optimiser steps (their kernels carry the gradient
+        exchange) with zero gradients, including the Linear-only rollback of the unrolled discriminator."""
+        d_lin, backup = self._native_packs.d_linear, None
+        for u in range(self.n_unrolling_steps + 1):
+            self.D_optimizer.zero_grad()
+            self.D_optimizer.step()
+            if u == 0 and self.n_unrolling_steps > 0:
+                backup = d_lin.clone()
+        self.predictor_optimizer.zero_grad()
+        self.predictor_optimizer.step()
+        if backup is not None:
+            d_lin.copy_(backup)
+
     def train_native(self, verbose=True, use_graph=True, log_losses=False):
         """train() with the iteration executed by native_step.NativeStep: ~30 launches of this library's kernels per
         iteration (no autograd, no cuBLAS, no ATen reductions), one CUDA graph per mini-batch shape.  Needs
@@ -366,10 +380,15 @@ class SocialWaysTrainer:
         for g_lo, g_hi, sub in self._minibatches():
             global_bs = g_hi - g_lo
             lo, hi = g_lo, g_hi
+            # train.py:471-473: two numpy scalars, then the noise of the GLOBAL mini-batch from torch's CPU generator
+            t01 = (float(np.random.uniform(0, 0.1)), float(np.random.uniform(0.9, 1.0)))
+            noise = torch.rand(global_bs, self.noise_len)
             if self.world_size > 1:       # this rank's contiguous block of scenes
                 s_lo, s_hi, sub = swdist.shard_scenes(sub, self.world_size, self.rank)
-                if s_hi <= s_lo:
-                    raise RuntimeError("train_native(): a rank received no scene of this mini-batch; use train()")
+                if s_hi <= s_lo:          # more ranks than scenes: contribute zero gradients to the three all-reduces
+                    self._native_empty_iteration()
+                    n_iter += 1
+                    continue
                 lo, hi = g_lo + s_lo, g_lo + s_hi
             bs = hi - lo
             key = (global_bs, bs, lo - g_lo, sub.tobytes())
@@ -378,9 +397,6 @@ class SocialWaysTrainer:
                 step = NativeStep(self, self._native_packs, bs, self.generator.scene_index(sub, bs, dev), global_bs)
                 ent = self._native_steps[key] = dict(step=step, graph=None, seen=0)
             step = ent["step"]
-            # train.py:471-473: two numpy scalars, then the noise of the GLOBAL mini-batch from torch's CPU generator
-            t01 = (float(np.random.uniform(0, 0.1)), float(np.random.uniform(0.9, 1.0)))
-            noise = torch.rand(global_bs, self.noise_len)
             pin = self._pin.get(global_bs)
             if pin is None:
                 pin = self._pin[global_bs] = dict(noise=torch.empty(global_bs, self.noise_len).pin_memory(),

@@ -28,20 +28,21 @@ def main():
     data = synthetic_scenes(list(rng.randint(1, 9, size=60)), seed=8)
     W = so.init_weights(seed=2)
 
-    mode = os.environ.get("SW_CHECK_MODE", "nccl")      # nccl | fused (eager, peer-memory all-reduce + Adam) | fused_graph
-    fused, graph_n = mode != "nccl", mode == "fused_graph"
-    epochs = 3 if graph_n else 1                          # graph mode: epoch 1 eager, epoch 2 captures, epoch 3 replays
+    # nccl | fused (eager, peer-memory all-reduce + Adam) | fused_graph | native (own-kernel iteration, graph replay)
+    mode = os.environ.get("SW_CHECK_MODE", "nccl")
+    fused, graph_n, native = mode != "nccl", mode == "fused_graph", mode == "native"
+    epochs = 3 if (graph_n or native) else 1              # graph modes: epoch 1 eager, epoch 2 captures, epoch 3 replays
 
-    def run(w, graph=False, fused=False):
+    def run(w, graph=False, fused=False, native=False):
         tr = SocialWaysTrainer(data, batch_size=64, use_social=True, n_unrolling_steps=1, weights=W,
                                device=f"cuda:{local}", world=w, cuda_graph=graph, fused_adam=fused)
         np.random.seed(5)
         torch.manual_seed(5)
         for _ in range(epochs):
-            ade, fde = (tr.train_graphed if graph else tr.train)(verbose=False)
+            ade, fde = (tr.train_native if native else tr.train_graphed if graph else tr.train)(verbose=False)
         return tr.reference_weights(), ade, fde
 
-    w_n, ade_n, fde_n = run((world, rank), graph=graph_n, fused=fused)
+    w_n, ade_n, fde_n = run((world, rank), graph=graph_n, fused=fused, native=native)
     ok = True
     # all ranks hold identical weights
     for k, v in w_n.items():

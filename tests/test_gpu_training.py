@@ -160,8 +160,11 @@ def test_checkpoint_keys_match_reference():
         assert {k: tuple(v.shape) for k, v in st[key].items()} == want
 
 
-def test_sharded_training_matches_single_gpu():
-    """N-rank NCCL run of the sharded step vs one GPU (needs >= 2 visible GPUs; `gpurun --gpus 2`)."""
+@pytest.mark.parametrize("mode", ["nccl", "native"])
+def test_sharded_training_matches_single_gpu(mode):
+    """N-rank run of the sharded step vs one GPU (needs >= 2 visible GPUs; `gpurun --gpus 2`): NCCL all-reduce + torch Adam,
+    and the native iteration with the all-reduce inside the Adam kernel.  (On a single-GPU box the same comparison runs
+    inside `bench.py --gpus N` as train_step.train_parity_max_abs.)"""
     import os
     import subprocess
     import sys
@@ -170,7 +173,8 @@ def test_sharded_training_matches_single_gpu():
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29517",
-                        os.path.join(here, "multigpu_train_check.py")], capture_output=True, text=True, timeout=600)
+                        os.path.join(here, "multigpu_train_check.py")], capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, SW_CHECK_MODE=mode))
     assert "MULTIGPU_TRAIN_CHECK PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
