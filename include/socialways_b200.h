@@ -216,12 +216,18 @@ int sw_disc_step(const float* heads_work, int pred_dim, int mode, const float* o
                  float* loss_part, float* label_out, float* code_out, int n_agents, int sm_count, void* stream);
 
 /* All weight-gradient contractions of one backward pass in one launch (job descriptor: sw_contract.h).  Replaces the
- * grad_weight halves of autograd's Linear / LSTM nodes (train.py:495,538).  `workspace` (sw_contract_plan floats) holds
- * the partial tiles of jobs that are split over CTAs, `counters` (zero-initialised, restored by the kernel) one word per
- * output tile.  Deterministic: the summation order does not depend on scheduling. */
-int sw_contract_plan(const sw_contract_job* jobs, int n_jobs, int sm_count, long long* workspace_floats, int* n_counters);
+ * grad_weight / grad_bias halves of autograd's Linear / LSTM nodes (train.py:495,538).
+ *   sw_contract_tc: tcgen05.mma kind::tf32 on tf32-split fp32 operands (3 MMAs per product, fp32 accumulate in TMEM);
+ *   sw_contract:    fp32 FFMA register tiles (arithmetic reference of the former, A/B timing).
+ * `workspace` (sw_contract_plan floats, for the kernel chosen by `tensor_cores`) holds the partial slabs of jobs that are split
+ * over CTAs, `counters` (zero-initialised, restored by the kernel) one word per output slab.  Deterministic: the summation
+ * order does not depend on scheduling. */
+int sw_contract_plan(const sw_contract_job* jobs, int n_jobs, int sm_count, int tensor_cores, long long* workspace_floats,
+                     int* n_counters);
 int sw_contract(const sw_contract_job* jobs, int n_jobs, float* workspace, long long workspace_floats, unsigned* counters,
                 int n_counters, int sm_count, void* stream);
+int sw_contract_tc(const sw_contract_job* jobs, int n_jobs, float* workspace, long long workspace_floats, unsigned* counters,
+                   int n_counters, int sm_count, void* stream);
 
 /* out[row][n] = bias[n] + add1[row][n] + add2[row][n] + sum_k x[row][k] w[k][n]  (k_in, n_out <= 80; bias/add1/add2 may
  * be NULL; add1/add2 have row stride ldo).  (u | beta) = h.M + m0 (train.py:158,167-169,185 folded) and its adjoint. */

@@ -46,8 +46,9 @@ _PROTOTYPES = {
     "sw_disc_pack": (_I, [_P, _I, _P, _P, _P, _P]),
     "sw_disc_step_image_rows": (_I, [_I, _P, _P]),
     "sw_disc_step": (_I, [_P, _I, _I, _P, _P, _P, _P, _I, _P, _I, _P, _F, _F] + [_P] * 7 + [_I, _I, _P]),
-    "sw_contract_plan": (_I, [_P, _I, _I, _P, _P]),
+    "sw_contract_plan": (_I, [_P, _I, _I, _I, _P, _P]),
     "sw_contract": (_I, [_P, _I, _P, ctypes.c_longlong, _P, _I, _I, _P]),
+    "sw_contract_tc": (_I, [_P, _I, _P, ctypes.c_longlong, _P, _I, _I, _P]),
     "sw_rows_linear": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "sw_train_stats": (_I, [_P, _P, _I, _I, _F, _P, _I, _P, _I, _F, _F, _P, _P, _P, _I, _P]),
     "sw_noise_uniform": (_I, [_P, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_ulonglong, _I, _P]),

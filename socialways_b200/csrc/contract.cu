@@ -1,23 +1,32 @@
 // Weight-gradient contractions of the training step, batched: every parameter gradient of train()'s two backward
 // passes (reference train.py:495 d_loss.backward(), :538 g_loss.backward(); in the reference these are the
-// `grad_weight = grad_output^T . input` halves of autograd's Linear / LSTM nodes) is a sum over batch rows
-//        out[k][n] = sum_rows A[row][k] * B[row][n]
+// `grad_weight = grad_output^T . input` / grad_bias halves of autograd's Linear / LSTM nodes) is a sum over batch rows
+//        G[k][n] = sum_rows A[row][k] * B[row][n]
 // of a forward stash A against a gradient record B that the data-gradient kernels wrote.  ONE launch evaluates a whole
-// list of such jobs (all of D's, or all of G's): no library GEMM, no reduction kernels, bias gradients as a K = 1 job
-// against an all-ones operand.
+// list of such jobs (all of D's, or all of G's): no library GEMM, no reduction kernels; bias gradients ride along as an
+// all-ones row appended to A; a job scatters its result into up to three parameter tensors (sw_contract.h).
 //
-// Operand layouts: "tile image" [image][k][32 rows] (the shared-memory operand of the FFMA kernels, written with
-// coalesced float4 stores; padding rows of the gradient images are zero) or row-major records [row][ld].
-// Work item = (job, 64 x 64 output tile, chunk of images); 256 threads, 4 x 4 outputs per thread.  Reduction order is
-// FIXED: a chunk sums its images in order into registers, writes its partial tile to the workspace, and the CTA that
-// arrives last at the tile's counter adds the partials in chunk order -- the result does not depend on scheduling.
+// Two kernels behind the same job list:
+//   sw_contract_tc  tcgen05.mma kind::tf32 on fp32 operands SPLIT into two tf32 terms (x = hi + lo, hi = x with the low 13
+//                   mantissa bits cleared, lo = rna_tf32(x - hi)): A.B ~= Ahi.Bhi + Ahi.Blo + Alo.Bhi, fp32 accumulation in
+//                   TMEM over all images of a chunk -- fp32 exponent range (gradient records sit at 1e-3 .. 1e-9, far below
+//                   fp16's range, which rules out the fp16 split of the inference kernels), ~2^-21 per product.  One work
+//                   item = (job, 128-row slab of G, chunk of images); the batch rows are the MMA's K dimension (32 per
+//                   image = 4 MMAs of K = 8 per product).  Operands are staged fp32 -> (hi, lo) by all 256 threads into the
+//                   canonical K-major no-swizzle layout [K/4][rows][4] with a PADDED chunk stride (rows*16 + 16 bytes: the 8
+//                   chunk-consecutive lanes of a quarter-warp hit 8 different bank groups), double buffered: the MMAs of
+//                   image i run under the staging of image i + 1.  The kernel is bound by the operand read (each image is
+//                   read once), not by the tensor pipe.
+//   sw_contract     fp32 FFMA register tiles (64 x 64 of G per CTA, 4 x 4 per thread), the round-2 first version; kept as
+//                   the arithmetic reference of the tensor-core kernel (tests) and for A/B timing.
+// Reduction order is FIXED in both: a chunk sums its images in order, writes its partial slab to the workspace, and the
+// CTA that arrives last at the slab's counter adds the partials in chunk order -- results do not depend on scheduling.
 #include "sw_common.cuh"
 #include "sw_contract.h"
+#include "sw_umma.cuh"
 
 namespace sw {
 
-constexpr int CT_TILE = 64;        // output tile edge
-constexpr int CT_LD = 36;          // padded shared row: 32 rows + 4 (a float4 per lane, lane stride 36 -> conflict-free)
 constexpr int CT_MAX_JOBS = SW_CONTRACT_MAX_JOBS;
 
 struct ContractParams {
@@ -25,40 +34,65 @@ struct ContractParams {
     int first_cta[CT_MAX_JOBS + 1];   // prefix sum of CTAs per job
     int chunks[CT_MAX_JOBS];          // image chunks per output tile
     int ipc[CT_MAX_JOBS];             // images per chunk
-    int first_tile[CT_MAX_JOBS];      // index of the job's first output tile (counter / workspace slot base)
+    int first_tile[CT_MAX_JOBS];      // index of the job's first output tile (counter slot base)
     long long ws_off[CT_MAX_JOBS];    // workspace offset (floats) of the job's partial tiles
     int n_jobs;
 };
 
 __device__ __forceinline__ int gate_perm(int n) { return (n & 3) * 64 + (n >> 2); }   // n' = 4*unit + gate -> gate*64 + unit
 
-// stage rows [r0, r0 + 64) of one operand image into shared memory s[64][CT_LD] (zero beyond `rows` / `n_rows`)
-__device__ __forceinline__ void stage_operand(float* __restrict__ s, const float* __restrict__ base, long long stride, int r0,
-                                              int rows /*rows of the job from r0 on*/, int image, int kind, int total_rows) {
+// G[k][n] -> the segment that owns row k
+__device__ __forceinline__ void scatter(const sw_contract_job& J, int k, int n, float val) {
+#pragma unroll
+    for (int s = 0; s < SW_CONTRACT_MAX_SEGS; ++s) {
+        if (s >= J.n_segs) break;
+        const sw_contract_seg& S = J.seg[s];
+        const int kk = k - S.k_begin;
+        if (kk >= 0 && kk < S.k_count) {
+            const int gn = J.n_perm == SW_CONTRACT_PERM_GATES ? gate_perm(n) : n;
+            const size_t idx = (size_t)kk * S.out_sk + (size_t)gn * S.out_sn;
+            S.out[idx] = val;
+            if (S.out2) S.out2[idx] = val;
+        }
+    }
+}
+
+// =====================================================================================================================
+// FFMA kernel: 64 x 64 tiles of G
+// =====================================================================================================================
+constexpr int CT_TILE = 64;
+constexpr int CT_LD = 36;          // padded shared row: 32 rows + 4 (a float4 per lane, lane stride 36 -> conflict-free)
+
+// stage rows [r0, r0 + 64) of one operand image into shared memory s[64][CT_LD].  `rows` = operand rows of the job
+// (rows >= `rows`: the ones row at index `rows` when `ones`, zeros beyond).
+__device__ __forceinline__ void stage_operand(float* __restrict__ s, const float* __restrict__ base, long long stride, int k0,
+                                              int r0, int rows, bool ones, int image, int kind, int total_rows) {
     const int tid = threadIdx.x;
     if (kind == SW_CONTRACT_IMAGE) {
-        const float* img = base + (size_t)image * stride + (size_t)r0 * 32;
+        const float* img = base + (size_t)image * stride + (size_t)(k0 + r0) * 32;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             const int i = tid + q * 256, row = i >> 3, piece = i & 7;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row < rows) v = __ldg(reinterpret_cast<const float4*>(img + row * 32) + piece);
+            if (r0 + row < rows) v = __ldg(reinterpret_cast<const float4*>(img + row * 32) + piece);
+            else if (ones && r0 + row == rows) {
+                const long long g0 = (long long)image * 32 + piece * 4;
+                v = make_float4(g0 < total_rows ? 1.f : 0.f, g0 + 1 < total_rows ? 1.f : 0.f, g0 + 2 < total_rows ? 1.f : 0.f,
+                                g0 + 3 < total_rows ? 1.f : 0.f);
+            }
             *reinterpret_cast<float4*>(s + row * CT_LD + piece * 4) = v;
         }
-    } else if (kind == SW_CONTRACT_ROWS) {
-        // records [row][stride]: element (k, r) = base[(image*32 + r) * stride + r0 + k]; read k-fastest (coalesced)
+    } else {
+        // records [row][stride]: element (k, r) = base[(image*32 + r) * stride + k0 + r0 + k]; read k-fastest (coalesced)
         for (int i = tid; i < CT_TILE * 32; i += 256) {
             const int r = i >> 6, k = i & 63;
             const long long grow = (long long)image * 32 + r;
             float v = 0.0f;
-            if (k < rows && grow < total_rows) v = __ldg(base + (size_t)grow * stride + r0 + k);
+            if (grow < total_rows) {
+                if (r0 + k < rows) v = __ldg(base + (size_t)grow * stride + k0 + r0 + k);
+                else if (ones && r0 + k == rows) v = 1.0f;
+            }
             s[k * CT_LD + r] = v;
-        }
-    } else {   // SW_CONTRACT_ONES: k = 0 is the all-ones row (bias gradients); rows past the batch are zero
-        for (int i = tid; i < CT_TILE * 32; i += 256) {
-            const int r = i & 31, k = i >> 5;
-            const long long grow = (long long)image * 32 + r;
-            s[k * CT_LD + r] = (k == 0 && grow < total_rows) ? 1.0f : 0.0f;
         }
     }
 }
@@ -72,15 +106,14 @@ contract_kernel(const __grid_constant__ ContractParams P, float* __restrict__ ws
     while (j + 1 < P.n_jobs && (int)blockIdx.x >= P.first_cta[j + 1]) ++j;
     const sw_contract_job& J = P.job[j];
     const int local = blockIdx.x - P.first_cta[j];
+    const int rows_total = J.K + (J.ones_row ? 1 : 0);
     const int tiles_n = (J.N + CT_TILE - 1) / CT_TILE;
-    const int tiles_k = (J.K + CT_TILE - 1) / CT_TILE;
     const int C = P.chunks[j];
     const int chunk = local % C, tile = local / C;
     const int kt = tile / tiles_n, nt = tile % tiles_n;
-    (void)tiles_k;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const int img0 = chunk * P.ipc[j], img1 = min(img0 + P.ipc[j], J.n_images);
-    const int krows = min(CT_TILE, J.K - kt * CT_TILE), nrows = min(CT_TILE, J.N - nt * CT_TILE);
+    const int krows = min(CT_TILE, rows_total - kt * CT_TILE), nrows = min(CT_TILE, J.N - nt * CT_TILE);
 
     float acc[4][4];
 #pragma unroll
@@ -90,8 +123,8 @@ contract_kernel(const __grid_constant__ ContractParams P, float* __restrict__ ws
 
     for (int img = img0; img < img1; ++img) {
         __syncthreads();
-        stage_operand(sa, J.a, J.a_stride, J.a_k0 + kt * CT_TILE, krows, img, J.a_kind, J.n_rows);
-        stage_operand(sb, J.b, J.b_stride, J.b_n0 + nt * CT_TILE, nrows, img, J.b_kind, J.n_rows);
+        stage_operand(sa, J.a, J.a_stride, J.a_k0, kt * CT_TILE, J.K, J.ones_row != 0, img, J.a_kind, J.n_rows);
+        stage_operand(sb, J.b, J.b_stride, J.b_n0, nt * CT_TILE, J.N, false, img, J.b_kind, J.n_rows);
         __syncthreads();
 #pragma unroll
         for (int r4 = 0; r4 < 8; ++r4) {
@@ -119,14 +152,7 @@ contract_kernel(const __grid_constant__ ContractParams P, float* __restrict__ ws
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int k = ty + 16 * i, n = tx + 16 * q;
-                if (k < krows && n < nrows) {
-                    int gn = nt * CT_TILE + n;
-                    if (J.n_perm == SW_CONTRACT_PERM_GATES) gn = gate_perm(gn);
-                    float* o = J.out + (size_t)(kt * CT_TILE + k) * J.out_sk + (size_t)gn * J.out_sn;
-                    const float val = v[i][q] * J.scale;
-                    if (J.out2) J.out2[(size_t)(kt * CT_TILE + k) * J.out_sk + (size_t)gn * J.out_sn] = val;
-                    *o = J.accumulate ? *o + val : val;
-                }
+                if (k < krows && n < nrows) scatter(J, kt * CT_TILE + k, nt * CT_TILE + n, v[i][q]);
             }
     };
     if (C == 1) { store_out(acc); return; }
@@ -160,33 +186,237 @@ contract_kernel(const __grid_constant__ ContractParams P, float* __restrict__ ws
     if (tid == 0) counters[tile_id] = 0u;     // ready for the next launch (CUDA-graph replay included)
 }
 
+// =====================================================================================================================
+// tcgen05 kernel: 128 x N slabs of G, tf32 split operands
+// =====================================================================================================================
+constexpr int TC_M = 128, TC_NMAX = SW_CONTRACT_MAX_N, TC_THREADS = 256;
+constexpr int TC_A_CHUNK = TC_M * 4 + 4;        // floats per K-chunk of A (4 r's x 128 rows + 16 B pad)
+constexpr int TC_B_CHUNK = TC_NMAX * 4 + 4;     // floats per K-chunk of B
+constexpr uint32_t FMT_TF32 = 2;
+
+struct TcStage {
+    float a_hi[8 * TC_A_CHUNK], a_lo[8 * TC_A_CHUNK];
+    float b_hi[8 * TC_B_CHUNK], b_lo[8 * TC_B_CHUNK];
+};
+struct TcSmem {
+    TcStage st[2];
+    unsigned long long bar[2];
+    uint32_t tmem_base;
+    int last;
+};
+
+__device__ __forceinline__ void umma_issue_ss_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                   bool accumulate, bool leader) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate), "r"((uint32_t)leader)
+                 : "memory");
+}
+
+// x -> (hi, lo): hi = x with the 13 low mantissa bits cleared (exactly a tf32 number), lo = (x - hi) rounded to tf32
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    const float d = x - hi;
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
+    lo = __uint_as_float(r);
+}
+__device__ __forceinline__ void split_store(float* __restrict__ hi_dst, float* __restrict__ lo_dst, const float4 v) {
+    float4 h, l;
+    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+    *reinterpret_cast<float4*>(hi_dst) = h;
+    *reinterpret_cast<float4*>(lo_dst) = l;
+}
+
+// Stage `count` operand rows (row index `row0 + i` of the job's operand; index == rows -> the ones row when `ones`, larger ->
+// zeros) of image `image` as (hi, lo) into [8 chunks][chunk_stride floats]: chunk c holds r = 4c .. 4c+3 of every row.
+__device__ __forceinline__ void stage_split(float* __restrict__ hi, float* __restrict__ lo, int chunk_stride,
+                                            const float* __restrict__ base, long long stride, int k0, int row0, int count, int rows,
+                                            bool ones, int image, int kind, int total_rows) {
+    const int tid = threadIdx.x;
+    if (kind == SW_CONTRACT_IMAGE) {
+        const float* img = base + (size_t)image * stride + (size_t)(k0 + row0) * 32;
+        for (int i = tid; i < count * 8; i += TC_THREADS) {           // item = (row, chunk), chunk fastest: coalesced 128 B rows
+            const int row = i >> 3, c = i & 7;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + row < rows) v = __ldg(reinterpret_cast<const float4*>(img + row * 32) + c);
+            else if (ones && row0 + row == rows) {
+                const long long g0 = (long long)image * 32 + c * 4;
+                v = make_float4(g0 < total_rows ? 1.f : 0.f, g0 + 1 < total_rows ? 1.f : 0.f, g0 + 2 < total_rows ? 1.f : 0.f,
+                                g0 + 3 < total_rows ? 1.f : 0.f);
+            }
+            split_store(hi + c * chunk_stride + row * 4, lo + c * chunk_stride + row * 4, v);
+        }
+    } else {
+        for (int i = tid; i < count * 8; i += TC_THREADS) {           // item = (chunk, row), row fastest: coalesced along k
+            const int c = i / count, row = i - c * count;
+            const long long g0 = (long long)image * 32 + c * 4;
+            float t[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                t[q] = 0.0f;
+                if (g0 + q < total_rows) {
+                    if (row0 + row < rows) t[q] = __ldg(base + (size_t)(g0 + q) * stride + k0 + row0 + row);
+                    else if (ones && row0 + row == rows) t[q] = 1.0f;
+                }
+            }
+            split_store(hi + c * chunk_stride + row * 4, lo + c * chunk_stride + row * 4, make_float4(t[0], t[1], t[2], t[3]));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+contract_tc_kernel(const __grid_constant__ ContractParams P, float* __restrict__ ws, unsigned* __restrict__ counters) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int j = 0;
+    while (j + 1 < P.n_jobs && (int)blockIdx.x >= P.first_cta[j + 1]) ++j;
+    const sw_contract_job& J = P.job[j];
+    const int local = blockIdx.x - P.first_cta[j];
+    const int rows_total = J.K + (J.ones_row ? 1 : 0);
+    const int C = P.chunks[j];
+    const int chunk = local % C, mt = local / C;
+    const int img0 = chunk * P.ipc[j], img1 = min(img0 + P.ipc[j], J.n_images);
+    const int mrows = min(TC_M, rows_total - mt * TC_M);
+    const int n_pad = (J.N + 15) & ~15;                 // UMMA N: multiple of 16 for M = 128
+
+    if (warp == 0) {
+        ptx::tcgen05_alloc(ptx::cta_group_1, &s.tmem_base, 256u);
+        ptx::tcgen05_relinquish_alloc_permit(ptx::cta_group_1);
+    }
+    if (tid == 0) {
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[0]), 1);
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[1]), 1);
+        ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
+    }
+    // rows of the B operand between N and n_pad are never written by the staging: clear them once (both buffers)
+    if (n_pad > J.N)
+        for (int i = tid; i < (n_pad - J.N) * 8 * 2; i += TC_THREADS) {
+            const int b = i & 1, c = (i >> 1) & 7, row = J.N + (i >> 4);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(s.st[b].b_hi + c * TC_B_CHUNK + row * 4) = z;
+            *reinterpret_cast<float4*>(s.st[b].b_lo + c * TC_B_CHUNK + row * 4) = z;
+        }
+    ptx::tcgen05_fence_before_thread_sync();
+    __syncthreads();
+    ptx::tcgen05_fence_after_thread_sync();
+    const uint32_t tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0);
+    const uint32_t idesc = umma_idesc(n_pad, FMT_TF32);
+    uint32_t phase[2] = {0u, 0u};
+    int used[2] = {0, 0};
+
+    for (int img = img0; img < img1; ++img) {
+        const int b = (img - img0) & 1;
+        TcStage& S = s.st[b];
+        if (used[b]) { mbar_wait(&s.bar[b], phase[b]); phase[b] ^= 1u; }      // the MMAs that read this buffer have completed
+        stage_split(S.a_hi, S.a_lo, TC_A_CHUNK, J.a, J.a_stride, J.a_k0, mt * TC_M, mrows, J.K, J.ones_row != 0, img, J.a_kind, J.n_rows);
+        stage_split(S.b_hi, S.b_lo, TC_B_CHUNK, J.b, J.b_stride, J.b_n0, 0, J.N, J.N, false, img, J.b_kind, J.n_rows);
+        ptx::fence_proxy_async(ptx::space_shared);
+        ptx::tcgen05_fence_before_thread_sync();
+        __syncthreads();
+        if (warp == 0) {
+            ptx::tcgen05_fence_after_thread_sync();
+            const bool leader = lane == 0;
+            // canonical K-major, no swizzle: core matrix = 8 rows x 16 B; SBO (8-row group stride) = 128 B,
+            // LBO (K-chunk stride) = the padded chunk size; one tf32 MMA (K = 8) spans two chunks
+            const uint64_t ah = umma_desc_uniform(S.a_hi, TC_A_CHUNK * 4, 128), al = umma_desc_uniform(S.a_lo, TC_A_CHUNK * 4, 128);
+            const uint64_t bh = umma_desc_uniform(S.b_hi, TC_B_CHUNK * 4, 128), bl = umma_desc_uniform(S.b_lo, TC_B_CHUNK * 4, 128);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint64_t ao = (uint64_t)(ks * 2 * TC_A_CHUNK * 4 / 16), bo = (uint64_t)(ks * 2 * TC_B_CHUNK * 4 / 16);
+                umma_issue_ss_tf32(tmem, ah + ao, bh + bo, idesc, img > img0 || ks > 0, leader);
+                umma_issue_ss_tf32(tmem, ah + ao, bl + bo, idesc, true, leader);
+                umma_issue_ss_tf32(tmem, al + ao, bh + bo, idesc, true, leader);
+            }
+            umma_commit(&s.bar[b], leader);
+        }
+        used[b] = 1;
+    }
+    // drain: wait for the last commit of each buffer (MMAs complete in issue order)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+        if (used[b]) { mbar_wait(&s.bar[b], phase[b]); phase[b] ^= 1u; }
+    ptx::tcgen05_fence_after_thread_sync();
+
+    // ---- epilogue: thread = (G row m = TMEM lane, column half) ----
+    const int m = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int ncols = n_pad >> 1;                        // multiple of 8
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * ncols);
+    const int tile_id = P.first_tile[j] + mt;
+    float* part = ws + P.ws_off[j] + ((size_t)mt * C + chunk) * (size_t)(TC_M * n_pad);
+    for (int c0 = 0; c0 < ncols; c0 += 8) {
+        uint32_t v[8];
+        tmem_ld<8>(taddr + c0, v);
+        ptx::tcgen05_wait_ld();
+        if (C == 1) {
+            if (m < mrows)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int n = half * ncols + c0 + q;
+                    if (n < J.N) scatter(J, mt * TC_M + m, n, __uint_as_float(v[q]));
+                }
+        } else {
+            float* dst = part + (size_t)m * n_pad + half * ncols + c0;
+            *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<uint4*>(dst + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+        }
+    }
+    ptx::tcgen05_fence_before_thread_sync();
+    if (C > 1) __threadfence();
+    __syncthreads();
+    if (warp == 0) ptx::tcgen05_dealloc(ptx::cta_group_1, tmem, 256u);
+    if (C == 1) return;
+    if (tid == 0) s.last = atomicAdd(counters + tile_id, 1u) == (unsigned)(C - 1);
+    __syncthreads();
+    if (!s.last) return;
+    __threadfence();
+    const float* base = ws + P.ws_off[j] + (size_t)mt * C * (size_t)(TC_M * n_pad);
+    for (int e = tid; e < mrows * n_pad; e += TC_THREADS) {          // element-wise, chunk order: fixed summation order
+        const int mm = e / n_pad, n = e - mm * n_pad;
+        if (n >= J.N) continue;
+        float sum = 0.0f;
+        for (int c = 0; c < C; ++c) sum += __ldcg(base + (size_t)c * (TC_M * n_pad) + e);
+        scatter(J, mt * TC_M + mm, n, sum);
+    }
+    if (tid == 0) counters[tile_id] = 0u;
+}
+
+// =====================================================================================================================
 struct ContractPlan {
     ContractParams p;
     long long ws_floats;
     int n_tiles, n_ctas;
 };
 
-static int make_plan(const sw_contract_job* jobs, int n_jobs, int sm_count, ContractPlan& plan) {
+static int make_plan(const sw_contract_job* jobs, int n_jobs, int sm_count, bool tc, ContractPlan& plan) {
     if (!jobs || n_jobs <= 0 || n_jobs > CT_MAX_JOBS || sm_count <= 0) return SW_ERR_ARG;
+    auto tiles_of = [&](const sw_contract_job& J) {
+        const int rows = J.K + (J.ones_row ? 1 : 0);
+        return tc ? (rows + TC_M - 1) / TC_M : ((rows + CT_TILE - 1) / CT_TILE) * ((J.N + CT_TILE - 1) / CT_TILE);
+    };
+    auto tile_floats = [&](const sw_contract_job& J) { return tc ? (long long)TC_M * ((J.N + 15) & ~15) : (long long)CT_TILE * CT_TILE; };
     long long image_tiles = 0;
     for (int j = 0; j < n_jobs; ++j) {
         const sw_contract_job& J = jobs[j];
-        if (!J.b || !J.out || J.K <= 0 || J.N <= 0 || J.n_images <= 0 || J.n_rows <= 0) return SW_ERR_ARG;
-        if (J.a_kind != SW_CONTRACT_ONES && !J.a) return SW_ERR_ARG;
-        if (J.a_kind < 0 || J.a_kind > SW_CONTRACT_ONES || J.b_kind < 0 || J.b_kind > SW_CONTRACT_ROWS) return SW_ERR_ARG;
+        if (!J.a || !J.b || J.K <= 0 || J.N <= 0 || J.N > SW_CONTRACT_MAX_N || J.n_images <= 0 || J.n_rows <= 0) return SW_ERR_ARG;
+        if (J.a_kind < 0 || J.a_kind > SW_CONTRACT_ROWS || J.b_kind < 0 || J.b_kind > SW_CONTRACT_ROWS) return SW_ERR_ARG;
         if (J.n_perm == SW_CONTRACT_PERM_GATES && J.N != 256) return SW_ERR_ARG;
-        const int tiles = ((J.K + CT_TILE - 1) / CT_TILE) * ((J.N + CT_TILE - 1) / CT_TILE);
-        image_tiles += (long long)tiles * J.n_images;
+        if (J.n_segs <= 0 || J.n_segs > SW_CONTRACT_MAX_SEGS) return SW_ERR_ARG;
+        for (int s = 0; s < J.n_segs; ++s)
+            if (!J.seg[s].out || J.seg[s].k_begin < 0 || J.seg[s].k_count <= 0) return SW_ERR_ARG;
+        image_tiles += (long long)tiles_of(J) * J.n_images;
     }
-    // images per chunk: about 3 CTAs per SM in flight, at least 4 images per CTA (amortises the partial-tile round trip)
-    long long ipc = (image_tiles + 3LL * sm_count - 1) / (3LL * sm_count);
+    // images per chunk: a few CTAs per SM in flight, at least 4 images per CTA (amortises the partial-tile round trip)
+    const long long target = (tc ? 2LL : 3LL) * sm_count;
+    long long ipc = (image_tiles + target - 1) / target;
     if (ipc < 4) ipc = 4;
     plan.p.n_jobs = n_jobs;
     plan.ws_floats = 0;
     int cta = 0, tile0 = 0;
     for (int j = 0; j < n_jobs; ++j) {
         const sw_contract_job& J = jobs[j];
-        const int tiles = ((J.K + CT_TILE - 1) / CT_TILE) * ((J.N + CT_TILE - 1) / CT_TILE);
+        const int tiles = tiles_of(J);
         const int chunks = (int)((J.n_images + ipc - 1) / ipc);
         plan.p.job[j] = J;
         plan.p.first_cta[j] = cta;
@@ -194,7 +424,7 @@ static int make_plan(const sw_contract_job* jobs, int n_jobs, int sm_count, Cont
         plan.p.ipc[j] = (int)ipc;
         plan.p.first_tile[j] = tile0;
         plan.p.ws_off[j] = plan.ws_floats;
-        if (chunks > 1) plan.ws_floats += (long long)tiles * chunks * CT_TILE * CT_TILE;
+        if (chunks > 1) plan.ws_floats += (long long)tiles * chunks * tile_floats(J);
         cta += tiles * chunks;
         tile0 += tiles;
     }
@@ -206,25 +436,41 @@ static int make_plan(const sw_contract_job* jobs, int n_jobs, int sm_count, Cont
 
 }  // namespace sw
 
-extern "C" int sw_contract_plan(const sw_contract_job* jobs, int n_jobs, int sm_count, long long* workspace_floats,
-                                int* n_counters) {
+extern "C" int sw_contract_plan(const sw_contract_job* jobs, int n_jobs, int sm_count, int tensor_cores,
+                                long long* workspace_floats, int* n_counters) {
     if (!workspace_floats || !n_counters) return SW_ERR_ARG;
     sw::ContractPlan plan;
-    const int rc = sw::make_plan(jobs, n_jobs, sm_count, plan);
+    const int rc = sw::make_plan(jobs, n_jobs, sm_count, tensor_cores != 0, plan);
     if (rc != SW_OK) return rc;
     *workspace_floats = plan.ws_floats;
     *n_counters = plan.n_tiles;
     return SW_OK;
 }
 
-extern "C" int sw_contract(const sw_contract_job* jobs, int n_jobs, float* workspace, long long workspace_floats,
-                           unsigned* counters, int n_counters, int sm_count, void* stream) {
+static int contract_launch(const sw_contract_job* jobs, int n_jobs, float* workspace, long long workspace_floats,
+                           unsigned* counters, int n_counters, int sm_count, bool tc, void* stream) {
     sw::ContractPlan plan;
-    const int rc = sw::make_plan(jobs, n_jobs, sm_count, plan);
+    const int rc = sw::make_plan(jobs, n_jobs, sm_count, tc, plan);
     if (rc != SW_OK) return rc;
     if (plan.ws_floats > workspace_floats || plan.n_tiles > n_counters) return SW_ERR_ARG;
     if ((plan.ws_floats > 0 && !workspace) || !counters) return SW_ERR_ARG;
-    sw::contract_kernel<<<plan.n_ctas, 256, 0, (cudaStream_t)stream>>>(plan.p, workspace, counters);
+    if (tc) {
+        const int smem = (int)sizeof(sw::TcSmem);
+        SW_SET_MAX_SMEM(sw::contract_tc_kernel, smem);
+        sw::contract_tc_kernel<<<plan.n_ctas, sw::TC_THREADS, smem, (cudaStream_t)stream>>>(plan.p, workspace, counters);
+    } else {
+        sw::contract_kernel<<<plan.n_ctas, 256, 0, (cudaStream_t)stream>>>(plan.p, workspace, counters);
+    }
     SW_CUDA_TRY(cudaGetLastError());
     return SW_OK;
+}
+
+extern "C" int sw_contract(const sw_contract_job* jobs, int n_jobs, float* workspace, long long workspace_floats,
+                           unsigned* counters, int n_counters, int sm_count, void* stream) {
+    return contract_launch(jobs, n_jobs, workspace, workspace_floats, counters, n_counters, sm_count, false, stream);
+}
+
+extern "C" int sw_contract_tc(const sw_contract_job* jobs, int n_jobs, float* workspace, long long workspace_floats,
+                              unsigned* counters, int n_counters, int sm_count, void* stream) {
+    return contract_launch(jobs, n_jobs, workspace, workspace_floats, counters, n_counters, sm_count, true, stream);
 }

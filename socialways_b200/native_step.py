@@ -30,42 +30,58 @@ from .ops import _stream, sm_count
 H = 64
 
 
+class ContractSeg(ctypes.Structure):
+    """sw_contract_seg (include/sw_contract.h)."""
+    _fields_ = [("out", ctypes.c_void_p), ("out2", ctypes.c_void_p), ("k_begin", ctypes.c_int), ("k_count", ctypes.c_int),
+                ("out_sk", ctypes.c_int), ("out_sn", ctypes.c_int)]
+
+
 class ContractJob(ctypes.Structure):
     """sw_contract_job (include/sw_contract.h)."""
-    _fields_ = [("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("out", ctypes.c_void_p), ("out2", ctypes.c_void_p),
-                ("a_stride", ctypes.c_longlong), ("b_stride", ctypes.c_longlong),
+    _fields_ = [("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("a_stride", ctypes.c_longlong), ("b_stride", ctypes.c_longlong),
                 ("a_k0", ctypes.c_int), ("K", ctypes.c_int), ("b_n0", ctypes.c_int), ("N", ctypes.c_int),
                 ("n_images", ctypes.c_int), ("n_rows", ctypes.c_int), ("a_kind", ctypes.c_int), ("b_kind", ctypes.c_int),
-                ("out_sk", ctypes.c_int), ("out_sn", ctypes.c_int), ("n_perm", ctypes.c_int), ("accumulate", ctypes.c_int),
-                ("scale", ctypes.c_float), ("reserved", ctypes.c_int)]
+                ("ones_row", ctypes.c_int), ("n_perm", ctypes.c_int), ("n_segs", ctypes.c_int), ("reserved", ctypes.c_int),
+                ("seg", ContractSeg * 3)]
 
 
-IMAGE, ROWS, ONES = 0, 1, 2
+IMAGE, ROWS = 0, 1
 
 
-def _job(a, b, out, K, N, n_images, a_stride=0, b_stride=0, a_k0=0, b_n0=0, a_kind=IMAGE, b_kind=IMAGE, out_sk=0, out_sn=1,
-         perm=0, out2=None, n_rows=None):
-    p = lambda t: None if t is None else (t if isinstance(t, int) else t.data_ptr())
-    return ContractJob(p(a), p(b), p(out), p(out2), a_stride, b_stride, a_k0, K, b_n0, N, n_images,
-                       n_images * 32 if n_rows is None else n_rows, a_kind, b_kind, out_sk, out_sn, perm, 0, 1.0, 0)
+def _ptr(t):
+    return None if t is None else (t if isinstance(t, int) else t.data_ptr())
+
+
+def seg(out, k_begin, k_count, out_sk, out_sn, out2=None):
+    """Rows [k_begin, k_begin + k_count) of the job's result go to out[(k - k_begin) * out_sk + n * out_sn]."""
+    return ContractSeg(_ptr(out), _ptr(out2), k_begin, k_count, out_sk, out_sn)
+
+
+def _job(a, b, K, N, n_images, segs, a_stride=0, b_stride=0, a_k0=0, b_n0=0, a_kind=IMAGE, b_kind=IMAGE, ones=False, perm=0,
+         n_rows=None):
+    """G[k][n] = sum_rows A[row][a_k0 + k] B[row][b_n0 + n] (+ the all-ones row K when `ones`), scattered by `segs`."""
+    arr = (ContractSeg * 3)(*segs)
+    return ContractJob(_ptr(a), _ptr(b), a_stride, b_stride, a_k0, K, b_n0, N, n_images,
+                       n_images * 32 if n_rows is None else n_rows, a_kind, b_kind, 1 if ones else 0, perm, len(segs), 0, arr)
 
 
 class ContractPlan:
-    """A job list + its workspace, ready to launch (sw_contract)."""
+    """A job list + its workspace, ready to launch (sw_contract_tc, or the FFMA sw_contract)."""
 
-    def __init__(self, jobs, device):
-        self.n = len(jobs)
+    def __init__(self, jobs, device, tensor_cores=True):
+        self.n, self.tc = len(jobs), bool(tensor_cores)
         self.jobs = (ContractJob * self.n)(*jobs)
         ws, nc = ctypes.c_longlong(), ctypes.c_int()
-        _lib.check(_lib.lib().sw_contract_plan(self.jobs, self.n, sm_count(device), ctypes.byref(ws), ctypes.byref(nc)),
-                   "sw_contract_plan")
+        _lib.check(_lib.lib().sw_contract_plan(self.jobs, self.n, sm_count(device), 1 if self.tc else 0, ctypes.byref(ws),
+                                               ctypes.byref(nc)), "sw_contract_plan")
         self.ws = torch.empty(max(int(ws.value), 4), device=device)
         self.counters = torch.zeros(max(int(nc.value), 1), dtype=torch.int32, device=device)
         self.device = device
 
     def run(self):
-        _lib.check(_lib.lib().sw_contract(self.jobs, self.n, self.ws.data_ptr(), self.ws.numel(), self.counters.data_ptr(),
-                                          self.counters.numel(), sm_count(self.device), _stream()), "sw_contract")
+        fn = _lib.lib().sw_contract_tc if self.tc else _lib.lib().sw_contract
+        _lib.check(fn(self.jobs, self.n, self.ws.data_ptr(), self.ws.numel(), self.counters.data_ptr(), self.counters.numel(),
+                      sm_count(self.device), _stream()), "sw_contract_tc" if self.tc else "sw_contract")
 
 
 def _ptr_array(tensors):
@@ -170,47 +186,52 @@ class NativeStep:
     def _build_jobs(self):
         tr, pk, To, Tp, P, t32, t16 = self.tr, self.pk, self.To, self.Tp, self.P, self.t32, self.t16
         g = lambda p: p.grad
+        tc = self.tr.native_tensor_cores
         dp = pk.disc_params
-        n_l = To * t32
-        jobs = [
-            _job(self.d_xh, self.d_g_gates, g(dp[0]), 4, 256, n_l, 68 * 32, 256 * 32, out_sk=1, out_sn=4, perm=1),
-            _job(self.d_xh, self.d_g_gates, g(dp[1]), 64, 256, n_l, 68 * 32, 256 * 32, a_k0=4, out_sk=1, out_sn=64, perm=1),
-            _job(None, self.d_g_gates, g(dp[2]), 1, 256, n_l, 0, 256 * 32, a_kind=ONES, out_sn=1, perm=1, out2=g(dp[3])),
-        ]
+        # ---- discriminator: LSTM(4, 64) as ONE job (w_ih rows 0..3, w_hh rows 4..67, the ones row -> b_ih and b_hh) ----
+        jobs = [_job(self.d_xh, self.d_g_gates, 68, 256, To * t32,
+                     [seg(g(dp[0]), 0, 4, 1, 4), seg(g(dp[1]), 4, 64, 1, 64), seg(g(dp[2]), 68, 1, 0, 1, out2=g(dp[3]))],
+                     68 * 32, 256 * 32, ones=True, perm=1)]
         xs, gs = self.xr * 32, self.gr * 32
-        # (A rows offset, K, B rows offset, N, weight index) per Linear layer, rows per csrc/disc_layout.cuh
+        # (X-image rows offset, K, G-image rows offset, N, weight index) per Linear layer, rows per csrc/disc_layout.cuh
         heads = [(0, 64, 0, 32, 4), (64, 32, 32, 32, 6), (96, P, 64, 32, 8), (96 + P, 32, 96, 32, 10),
                  (128 + P, 64, 128, 32, 12), (192 + P, 32, 160, 1, 14), (128 + P, 64, 161, 32, 16), (224 + P, 32, 193, 2, 18)]
-        for a0, K, b0, N, wi in heads:
-            jobs.append(_job(self.x_img, self.g_img, g(dp[wi]), K, N, t16, xs, gs, a_k0=a0, b_n0=b0, out_sk=1, out_sn=K))
-            jobs.append(_job(None, self.g_img, g(dp[wi + 1]), 1, N, t16, 0, gs, b_n0=b0, a_kind=ONES, out_sn=1))
-        self.d_plan = ContractPlan(jobs, self.dev)
+        for a0, K, b0, N, wi in heads:          # weight [N][K] (torch [out][in]) + bias [N] from the ones row
+            jobs.append(_job(self.x_img, self.g_img, K, N, t16, [seg(g(dp[wi]), 0, K, 1, K), seg(g(dp[wi + 1]), K, 1, 0, 1)],
+                             xs, gs, a_k0=a0, b_n0=b0, ones=True))
+        self.d_plan = ContractPlan(jobs, self.dev, tc)
 
+        # ---- generator ----
         gp = pk.gen_params
         n_all = (To + Tp - 1) * t32
         dec_xh = self.xh_all[To:]
+        w1 = g(gp[14]).view(-1)
         jobs = [
-            _job(self.xh_all, self.g_gates_all, self.d_enc, 68, 256, n_all, 68 * 32, 256 * 32, out_sk=256, out_sn=1),
-            _job(None, self.g_gates_all, self.d_enc[68], 1, 256, n_all, 0, 256 * 32, a_kind=ONES, out_sn=1),
-            _job(dec_xh, self.g_a1, g(gp[14]), 64, 160, Tp * t32, 68 * 32, 160 * 32, a_k0=4, out_sk=1, out_sn=160),
-            _job(self.s_sz, self.g_a1sum, g(gp[14]).view(-1)[64:], 96, 160, t32, 96 * 32, 160 * 32, out_sk=1, out_sn=160),
-            _job(None, self.g_a1sum, g(gp[15]), 1, 160, t32, 0, 160 * 32, a_kind=ONES, out_sn=1),
-            _job(self.s_a1, self.g_a2, g(gp[16]), 160, 80, Tp * t32, 160 * 32, 80 * 32, out_sk=1, out_sn=160),
-            _job(None, self.g_a2, g(gp[17]), 1, 80, Tp * t32, 0, 80 * 32, a_kind=ONES, out_sn=1),
-            _job(self.s_a2, self.g_v, self.d_w34, 80, 2, Tp * t32, 80 * 32, 2 * 32, out_sk=2, out_sn=1),
-            _job(None, self.g_v, self.d_w34[160:], 1, 2, Tp * t32, 0, 2 * 32, a_kind=ONES, out_sn=1),
+            # encoder LSTM (observation pass + decode steps, one image sequence) -> d_enc [69][256] in pack layout (folds: sw_gen_pack_bwd)
+            _job(self.xh_all, self.g_gates_all, 68, 256, n_all, [seg(self.d_enc, 0, 69, 256, 1)], 68 * 32, 256 * 32, ones=True),
+            # DecoderFC layer 1: h columns per step; [S ; z] columns and b1 against sum_t da1pre
+            _job(dec_xh, self.g_a1, 64, 160, Tp * t32, [seg(w1, 0, 64, 1, 160)], 68 * 32, 160 * 32, a_k0=4),
+            _job(self.s_sz, self.g_a1sum, 96, 160, t32, [seg(w1[64:], 0, 96, 1, 160), seg(g(gp[15]), 96, 1, 0, 1)],
+                 96 * 32, 160 * 32, ones=True),
+            _job(self.s_a1, self.g_a2, 160, 80, Tp * t32, [seg(g(gp[16]), 0, 160, 1, 160), seg(g(gp[17]), 160, 1, 0, 1)],
+                 160 * 32, 80 * 32, ones=True),
+            # folded 80 -> 2 output layer -> d_w34 [80][2] | d_b34 [2] (folds: sw_gen_pack_bwd)
+            _job(self.s_a2, self.g_v, 80, 2, Tp * t32, [seg(self.d_w34, 0, 80, 2, 1), seg(self.d_w34[160:], 80, 1, 0, 1)],
+                 80 * 32, 2 * 32, ones=True),
         ]
         if self.social and self.n_pairs > 0:
-            npi, bs = (self.n_pairs + 31) // 32, self.bs
+            npi, bs, npairs = (self.n_pairs + 31) // 32, self.bs, self.n_pairs
             jobs += [
-                _job(self.st_f, self.st_g1, g(gp[2]), 3, 32, npi, 4, 32, a_kind=ROWS, b_kind=ROWS, out_sk=1, out_sn=3, n_rows=self.n_pairs),
-                _job(self.st_f, self.st_g1, g(gp[3]), 1, 32, npi, 4, 32, a_k0=3, a_kind=ROWS, b_kind=ROWS, out_sn=1, n_rows=self.n_pairs),
-                _job(self.st_a1, self.st_g2, g(gp[4]), 32, 64, npi, 32, 64, a_kind=ROWS, b_kind=ROWS, out_sk=1, out_sn=32, n_rows=self.n_pairs),
-                _job(None, self.st_g2, g(gp[5]), 1, 64, npi, 0, 64, a_kind=ONES, b_kind=ROWS, out_sn=1, n_rows=self.n_pairs),
-                _job(self.h, self.dub, self.d_m, 64, 65, (bs + 31) // 32, 64, 65, a_kind=ROWS, b_kind=ROWS, out_sk=65, out_sn=1, n_rows=bs),
-                _job(None, self.dub, self.d_m[64 * 65:], 1, 65, (bs + 31) // 32, 0, 65, a_kind=ONES, b_kind=ROWS, out_sn=1, n_rows=bs),
+                # pair MLP layer 1: records F = (dist, bearing, dca, 1) -> fc.0.weight [32][3] and fc.0.bias from the stored ones
+                _job(self.st_f, self.st_g1, 4, 32, npi, [seg(g(gp[2]), 0, 3, 1, 3), seg(g(gp[3]), 3, 1, 0, 1)], 4, 32,
+                     a_kind=ROWS, b_kind=ROWS, n_rows=npairs),
+                _job(self.st_a1, self.st_g2, 32, 64, npi, [seg(g(gp[4]), 0, 32, 1, 32), seg(g(gp[5]), 32, 1, 0, 1)], 32, 64,
+                     a_kind=ROWS, b_kind=ROWS, ones=True, n_rows=npairs),
+                # (u | beta) = h . M + m0 -> d_m [64][65] | d_m0 [65] (folds: sw_gen_pack_bwd)
+                _job(self.h, self.dub, 64, 65, (bs + 31) // 32, [seg(self.d_m, 0, 65, 65, 1)], 64, 65, a_kind=ROWS, b_kind=ROWS,
+                     ones=True, n_rows=bs),
             ]
-        self.g_plan = ContractPlan(jobs, self.dev)
+        self.g_plan = ContractPlan(jobs, self.dev, tc)
 
     # ---------------------------------------------------------------- launches
     def _lstm_fwd(self, pack, h, c, x_last, st_g, st_x):

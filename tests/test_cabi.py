@@ -102,11 +102,16 @@ def test_training_step_entry_points_reject_bad_arguments():
     assert [s.value for s in sizes] == [69 * 256, 256 * 68, 38802, 23200, 2240, 65 * 65, 65 * 64]
     xr, gr = ctypes.c_int(), ctypes.c_int()
     assert lib.sw_disc_step_image_rows(48, ctypes.byref(xr), ctypes.byref(gr)) == 0 and (xr.value, gr.value) == (304, 196)
-    # contraction planning is host arithmetic: a job over many images is split into chunks with a partial-tile workspace
-    assert ctypes.sizeof(ContractJob) == 104
-    job = ContractJob(1 << 20, 1 << 21, 1 << 22, None, 68 * 32, 256 * 32, 0, 68, 0, 256, 5000, 5000 * 32, 0, 0, 256, 1, 0, 0, 1.0, 0)
+    # contraction planning is host arithmetic: a job over many images is split into chunks with a partial-slab workspace
+    from socialways_b200.native_step import ContractSeg
+    assert ctypes.sizeof(ContractJob) == 176 and ctypes.sizeof(ContractSeg) == 32
+    segs = (ContractSeg * 3)(ContractSeg(1 << 22, None, 0, 69, 256, 1))
+    job = ContractJob(1 << 20, 1 << 21, 68 * 32, 256 * 32, 0, 68, 0, 256, 5000, 5000 * 32, 0, 0, 1, 0, 1, 0, segs)
     ws, nc = ctypes.c_longlong(), ctypes.c_int()
-    assert lib.sw_contract_plan((ContractJob * 1)(job), 1, 148, ctypes.byref(ws), ctypes.byref(nc)) == 0
-    assert nc.value == 2 * 4 and ws.value > 0 and ws.value % 4096 == 0
-    bad = ContractJob(None, None, None, None, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0)
-    assert lib.sw_contract_plan((ContractJob * 1)(bad), 1, 148, ctypes.byref(ws), ctypes.byref(nc)) == -1
+    assert lib.sw_contract_plan((ContractJob * 1)(job), 1, 148, 0, ctypes.byref(ws), ctypes.byref(nc)) == 0
+    assert nc.value == 2 * 4 and ws.value > 0 and ws.value % 4096 == 0           # FFMA: 64 x 64 tiles of the 69 x 256 result
+    assert lib.sw_contract_plan((ContractJob * 1)(job), 1, 148, 1, ctypes.byref(ws), ctypes.byref(nc)) == 0
+    assert nc.value == 1 and ws.value > 0 and ws.value % (128 * 256) == 0        # tcgen05: one 128-row slab
+    bad = ContractJob(None, None, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, (ContractSeg * 3)())
+    assert lib.sw_contract_plan((ContractJob * 1)(bad), 1, 148, 1, ctypes.byref(ws), ctypes.byref(nc)) == -1
+    assert lib.sw_contract_tc(None, 0, None, 0, None, 0, 148, None) == -1

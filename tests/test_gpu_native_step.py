@@ -23,46 +23,61 @@ def _images(rows_major):
     return pad.view(t, 32, k).transpose(1, 2).contiguous()
 
 
-def test_contract_kinds_permutation_and_split():
-    from socialways_b200.native_step import ContractPlan, _job, IMAGE, ROWS, ONES
+@pytest.mark.parametrize("tensor_cores", [False, True])
+def test_contract_kinds_permutation_and_split(tensor_cores):
+    """sw_contract (FFMA) and sw_contract_tc (tcgen05, tf32-split operands) against float64 matmuls: image and row-record
+    operands, the ones row (bias gradients), segments, the LSTM gate permutation, jobs split over CTAs, operands whose
+    magnitudes span 1e-9 .. 1 (gradient records)."""
+    from socialways_b200.native_step import ContractPlan, _job, seg, ROWS
     g = torch.Generator(device="cuda").manual_seed(1)
     rows = 32 * 700 - 5                      # many images: the jobs are split over CTAs (partials + fixed-order reduce)
     A = torch.randn(rows, 68, device="cuda", generator=g)
-    B = torch.randn(rows, 256, device="cuda", generator=g)
+    B = torch.randn(rows, 256, device="cuda", generator=g) * torch.logspace(-9, 0, 256, device="cuda")   # gradient-like range
     Ai, Bi = _images(A), _images(B)
     n_img = Ai.shape[0]
-    out_w = torch.zeros(256, 64, device="cuda")          # gate-permuted, transposed store: w_hh[R][k]
-    out_b = torch.zeros(256, device="cuda")
-    out_b2 = torch.zeros(256, device="cuda")
-    out_plain = torch.zeros(68, 256, device="cuda")
-    out_rows = torch.zeros(100, 3, device="cuda")        # rows-kind operands with column offsets, strided output
+    w_ih, w_hh = torch.zeros(256, 4, device="cuda"), torch.zeros(256, 64, device="cuda")
+    b_ih, b_hh = torch.zeros(256, device="cuda"), torch.zeros(256, device="cuda")
+    out_plain = torch.zeros(69, 256, device="cuda")
     small_a = torch.randn(777, 7, device="cuda", generator=g)
-    small_b = torch.randn(777, 130, device="cuda", generator=g)
+    small_b = torch.randn(777, 130, device="cuda", generator=g) * 1e-4
+    out_rows, out_rows_b = torch.zeros(100, 3, device="cuda"), torch.zeros(100, device="cuda")
+    wide_a = torch.randn(32 * 9, 160, device="cuda", generator=g)                                    # K > 128: two slabs
+    wide_b = torch.randn(32 * 9, 80, device="cuda", generator=g)
+    out_wide, out_wide_b = torch.zeros(80, 160, device="cuda"), torch.zeros(80, device="cuda")
     jobs = [
-        _job(Ai, Bi, out_w, 64, 256, n_img, 68 * 32, 256 * 32, a_k0=4, out_sk=1, out_sn=64, perm=1),
-        _job(None, Bi, out_b, 1, 256, n_img, 0, 256 * 32, a_kind=ONES, out_sn=1, perm=1, out2=out_b2),
-        _job(Ai, Bi, out_plain, 68, 256, n_img, 68 * 32, 256 * 32, out_sk=256, out_sn=1),
-        _job(small_a, small_b, out_rows, 3, 100, (777 + 31) // 32, 7, 130, a_k0=2, b_n0=30, a_kind=ROWS, b_kind=ROWS,
-             out_sk=1, out_sn=3, n_rows=777),
+        _job(Ai, Bi, 68, 256, n_img, [seg(w_ih, 0, 4, 1, 4), seg(w_hh, 4, 64, 1, 64), seg(b_ih, 68, 1, 0, 1, out2=b_hh)],
+             68 * 32, 256 * 32, ones=True, perm=1),
+        _job(Ai, Bi, 68, 256, n_img, [seg(out_plain, 0, 69, 256, 1)], 68 * 32, 256 * 32, ones=True),
+        _job(small_a, small_b, 3, 100, (777 + 31) // 32, [seg(out_rows, 0, 3, 1, 3), seg(out_rows_b, 3, 1, 0, 1)], 7, 130,
+             a_k0=2, b_n0=30, a_kind=ROWS, b_kind=ROWS, ones=True, n_rows=777),
+        _job(_images(wide_a), _images(wide_b), 160, 80, 9, [seg(out_wide, 0, 160, 1, 160), seg(out_wide_b, 160, 1, 0, 1)],
+             160 * 32, 80 * 32, ones=True),
     ]
-    plan = ContractPlan(jobs, torch.device("cuda"))
+    plan = ContractPlan(jobs, torch.device("cuda"), tensor_cores)
     assert plan.ws.numel() > 4, "the large jobs must be split over several CTAs"
-    for _ in range(2):                                   # second launch: the tile counters were restored
+    for _ in range(2):                                   # second launch: the slab counters were restored
         plan.run()
     torch.cuda.synchronize()
+    tol = 3e-6 if tensor_cores else 1e-6                 # relative to sum |a||b| of the element (tf32 split: ~2^-21 per product)
+
+    def check(got, want, bound):
+        assert ((got.double() - want).abs() <= tol * bound + 1e-30).all(), float(((got.double() - want).abs() / (bound + 1e-30)).max())
+
     ref = A.double().t() @ B.double()                    # [68, 256], columns n' = 4*unit + gate
+    bound = A.double().abs().t() @ B.double().abs()
+    bsum, bbound = B.double().sum(0), B.double().abs().sum(0)
     perm = torch.tensor([(n & 3) * 64 + (n >> 2) for n in range(256)], device="cuda")
-    want_w = torch.zeros(256, 64, device="cuda", dtype=torch.float64)
-    want_w[perm] = ref[4:68].t()
-    scale = ref.abs().max().item()
-    assert (out_w.double() - want_w).abs().max().item() < 2e-5 * scale
-    want_b = torch.zeros(256, device="cuda", dtype=torch.float64)
-    want_b[perm] = B.double().sum(0)
-    assert (out_b.double() - want_b).abs().max().item() < 2e-5 * B.double().sum(0).abs().max().item() + 1e-4
-    assert torch.equal(out_b, out_b2)
-    assert (out_plain.double() - ref).abs().max().item() < 2e-5 * scale
-    want_rows = (small_a[:, 2:5].double().t() @ small_b[:, 30:130].double()).t()
-    assert (out_rows.double() - want_rows).abs().max().item() < 2e-5 * want_rows.abs().max().item()
+    scat = lambda m: torch.zeros(256, m.shape[0], device="cuda", dtype=torch.float64).index_copy_(0, perm, m.t().contiguous())
+    check(w_ih, scat(ref[:4]), scat(bound[:4]))
+    check(w_hh, scat(ref[4:68]), scat(bound[4:68]))
+    check(b_ih, scat(bsum[None])[:, 0], scat(bbound[None])[:, 0])
+    assert torch.equal(b_ih, b_hh)
+    check(out_plain, torch.cat([ref, bsum[None]]), torch.cat([bound, bbound[None]]))
+    sa, sb = small_a[:, 2:5].double(), small_b[:, 30:130].double()
+    check(out_rows, (sa.t() @ sb).t(), (sa.abs().t() @ sb.abs()).t())
+    check(out_rows_b, sb.sum(0), sb.abs().sum(0))
+    check(out_wide, (wide_a.double().t() @ wide_b.double()).t(), (wide_a.double().abs().t() @ wide_b.double().abs()).t())
+    check(out_wide_b, wide_b.double().sum(0), wide_b.double().abs().sum(0))
     first = out_plain.clone()
     plan.run()
     torch.cuda.synchronize()
@@ -86,11 +101,13 @@ def test_rows_linear():
         assert (out.double() - want).abs().max().item() < 1e-4
 
 
-def _trainer(data, social=True, unroll=1, weights=None, n_next=12, batch=64, **kw):
+def _trainer(data, social=True, unroll=1, weights=None, n_next=12, batch=64, tensor_cores=True, **kw):
     from oracle import socialways_oracle as so
     from socialways_b200.trainer import SocialWaysTrainer
     W = weights if weights is not None else so.init_weights(seed=4, n_next=n_next)
-    return SocialWaysTrainer(data, batch_size=batch, use_social=social, n_unrolling_steps=unroll, weights=W, fused_adam=True, **kw)
+    tr = SocialWaysTrainer(data, batch_size=batch, use_social=social, n_unrolling_steps=unroll, weights=W, fused_adam=True, **kw)
+    tr.native_tensor_cores = tensor_cores
+    return tr
 
 
 def test_pack_kernels_match_packing_py():
@@ -123,7 +140,8 @@ def test_pack_kernels_match_packing_py():
 
 @pytest.mark.parametrize("social", [True, False])
 @pytest.mark.parametrize("shape", ["ragged_8_12", "toy_2_2"])
-def test_native_gradients_match_autograd_path(social, shape):
+@pytest.mark.parametrize("tensor_cores", [True, False])
+def test_native_gradients_match_autograd_path(social, shape, tensor_cores):
     """One D pass and one G pass: every parameter gradient of the native launch sequence vs the package's autograd path
     (which tests/test_gpu_training.py pins to the unmodified reference's gradients)."""
     from oracle import socialways_oracle as so
@@ -134,7 +152,7 @@ def test_native_gradients_match_autograd_path(social, shape):
     else:
         rng = np.random.RandomState(1)
         data, n_next = synthetic_scenes(list(rng.randint(1, 9, size=14)), seed=5), 12
-    tr = _trainer(data, social=social, n_next=n_next)
+    tr = _trainer(data, social=social, n_next=n_next, tensor_cores=tensor_cores)
     lo, hi, sub = next(iter(tr._minibatches()))
     bs = hi - lo
     step = NativeStep(tr, NativePacks(tr), bs, tr.generator.scene_index(sub, bs, tr.device), bs)
