@@ -280,25 +280,54 @@ def train_block(args, world, rank, dev):
         iters = sum(1 for _ in tr._minibatches())
         for _ in range(3):                                        # eager pass, graph capture, one replayed epoch (warm-up)
             tr.train_native(verbose=False)
+
+        def timed_epochs(**kw):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = ev(), ev()
+            w0 = time.perf_counter()
+            e0.record()
+            for _ in range(args.train_epochs):
+                res = tr.train_native(verbose=False, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - w0
+            if world > 1:
+                dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1) * 1e-3, wall], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            d, w = (float(x) / args.train_epochs for x in t.cpu())
+            return d, w, res
+
+        host_s, host_wall, (ade, fde) = timed_epochs()                        # the reference's RNG contract: CPU torch.rand noise
+        dev_s, dev_wall, _ = timed_epochs(device_noise_seed=1234)             # noise drawn on the GPU (Philox), same otherwise
+        # the GPU's own time for one iteration: the largest captured graph replayed back to back, nothing on the host between
+        ent = max(tr._native_steps.values(), key=lambda e: e["step"].bs)
+        r0, r1 = ev(), ev()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        e0, e1 = ev(), ev()
-        w0 = time.perf_counter()
-        e0.record()
-        for _ in range(args.train_epochs):
-            ade, fde = tr.train_native(verbose=False)
-        e1.record()
+        r0.record()
+        for _ in range(20):
+            ent["graph"].replay()
+        r1.record()
         torch.cuda.synchronize()
-        wall = time.perf_counter() - w0
-        if world > 1:
-            dist.barrier()
-        t = torch.tensor([e0.elapsed_time(e1) * 1e-3, wall], device=dev, dtype=torch.float64)
+        t = torch.tensor([r0.elapsed_time(r1) / 20], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_s, wall_s = (float(x) / args.train_epochs for x in t.cpu())
-        results.append({"global_batch": gbs, "iterations_per_epoch": iters, "ms_per_iteration": 1e3 * dev_s / iters,
-                        "agents_per_s": tr.n_train_samples / dev_s, "epoch_device_s": dev_s, "epoch_wall_s": wall_s,
+        replay_ms = float(t.item())
+        for o in (tr.predictor_optimizer, tr.D_optimizer):
+            o.check_status()
+        results.append({"global_batch": gbs, "iterations_per_epoch": iters,
+                        "ms_per_iteration": 1e3 * dev_s / iters, "agents_per_s": tr.n_train_samples / dev_s,
+                        "noise": "device (Philox4x32-10, train_native(device_noise_seed=)): same distribution as train.py:473, different stream",
+                        "host_noise": {"ms_per_iteration": 1e3 * host_s / iters, "agents_per_s": tr.n_train_samples / host_s,
+                                       "note": "reference RNG contract: every rank draws torch.rand(global_batch, 32) on the CPU per "
+                                               "iteration (train.py:473) -- the host generator, not the GPU, bounds this variant"},
+                        "gpu_ms_per_iteration_graph_replay": replay_ms, "rows_per_rank_in_largest_graph": ent["step"].bs,
+                        "epoch_device_s": dev_s, "epoch_wall_s": dev_wall,
                         "achieved_tflops_fp32": tr.n_train_samples * TRAIN_FLOPS_PER_AGENT / dev_s / 1e12,
                         "cuda_graphs": sum(1 for e in tr._native_steps.values() if e["graph"] is not None),
                         "train_ade": ade, "train_fde": fde})

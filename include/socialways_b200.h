@@ -242,10 +242,10 @@ int sw_train_stats(const float* pred_hat, const float* pred, int n_rows, int n_n
                    unsigned* counter, float* stats, int sm_count, void* stream);
 
 /* Device-side latent noise (optional replacement of the host-side torch.rand + upload of train.py:584,473): n uniform
- * [0, 1) floats from Philox4x32-10; group g = e / 4 of the output = Philox(counter = (g, offset), key = seed), values
- * (x >> 8) * 2^-24.  A different stream from torch's CPU generator: parity runs keep caller-supplied noise. */
-int sw_noise_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset, int sm_count,
-                     void* stream);
+ * [0, 1) floats from Philox4x32-10; group g = first_group + e / 4 of the output = Philox(counter = (g, offset), key = seed),
+ * values (x >> 8) * 2^-24.  A different stream from torch's CPU generator: parity runs keep caller-supplied noise. */
+int sw_noise_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                     unsigned long long first_group, int sm_count, void* stream);
 
 /* Best-of-K error metrics.  Replaces train.py:587 and :602-607 of test().
  *   pred [K][N][T][4], gt [N][T][2] (normalised), ss = Scale.sx (train.py:121)

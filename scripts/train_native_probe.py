@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--epochs", type=int, default=2)
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--shape", default="toy", choices=["toy", "eth"])
+    ap.add_argument("--ffma-contract", action="store_true", help="weight-gradient contractions on the FFMA kernel instead of tcgen05")
     args = ap.parse_args()
     from bench import toy_dataset
     from socialways_b200.trainer import SocialWaysTrainer
@@ -31,6 +32,7 @@ def main():
         from golden_data import synthetic_scenes
         data = synthetic_scenes([8] * (args.n // 8), seed=1)
     tr = SocialWaysTrainer(data, batch_size=args.batch, use_social=True, n_unrolling_steps=1, fused_adam=True)
+    tr.native_tensor_cores = not args.ffma_contract
     iters = sum(1 for _ in tr._minibatches())
     np.random.seed(0)
     torch.manual_seed(0)
@@ -45,7 +47,20 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    print(f"batch {args.batch} shape {args.shape} graph {args.graph}: {iters} iterations/epoch, "
+    if args.graph:      # pure GPU time of one iteration: replay the largest captured graph back to back (no host RNG / copies between)
+        ent = max(tr._native_steps.values(), key=lambda e: e["step"].bs)
+        if ent["graph"] is not None:
+            for _ in range(3):
+                ent["graph"].replay()
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for _ in range(20):
+                ent["graph"].replay()
+            r1.record()
+            torch.cuda.synchronize()
+            print(f"   graph replay only (bs {ent['step'].bs}): {r0.elapsed_time(r1) / 20:.4f} ms/iteration")
+    print(f"batch {args.batch} shape {args.shape} graph {args.graph} contraction {'ffma' if args.ffma_contract else 'tcgen05'}: {iters} iterations/epoch, "
           f"{e0.elapsed_time(e1) / args.epochs / iters:.4f} ms/iteration (device), {1e3 * wall / args.epochs / iters:.4f} ms (wall)")
 
 

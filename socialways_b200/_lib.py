@@ -51,7 +51,7 @@ _PROTOTYPES = {
     "sw_contract_tc": (_I, [_P, _I, _P, ctypes.c_longlong, _P, _I, _I, _P]),
     "sw_rows_linear": (_I, [_P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "sw_train_stats": (_I, [_P, _P, _I, _I, _F, _P, _I, _P, _I, _F, _F, _P, _P, _P, _I, _P]),
-    "sw_noise_uniform": (_I, [_P, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_ulonglong, _I, _P]),
+    "sw_noise_uniform": (_I, [_P, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_ulonglong, ctypes.c_ulonglong, _I, _P]),
     "sw_bestofk_metrics": (_I, [_P, _P, _F, _I, _I, _I, _P, _P]),
     "sw_traj_nn1_counts": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "sw_traj_emd_cost": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),

@@ -11,12 +11,13 @@
 //                   mantissa bits cleared, lo = rna_tf32(x - hi)): A.B ~= Ahi.Bhi + Ahi.Blo + Alo.Bhi, fp32 accumulation in
 //                   TMEM over all images of a chunk -- fp32 exponent range (gradient records sit at 1e-3 .. 1e-9, far below
 //                   fp16's range, which rules out the fp16 split of the inference kernels), ~2^-21 per product.  One work
-//                   item = (job, 128-row slab of G, chunk of images); the batch rows are the MMA's K dimension (32 per
+//                   item = (job, 128 x 128 slab of G, chunk of images); the batch rows are the MMA's K dimension (32 per
 //                   image = 4 MMAs of K = 8 per product).  Operands are staged fp32 -> (hi, lo) by all 256 threads into the
 //                   canonical K-major no-swizzle layout [K/4][rows][4] with a PADDED chunk stride (rows*16 + 16 bytes: the 8
-//                   chunk-consecutive lanes of a quarter-warp hit 8 different bank groups), double buffered: the MMAs of
-//                   image i run under the staging of image i + 1.  The kernel is bound by the operand read (each image is
-//                   read once), not by the tensor pipe.
+//                   chunk-consecutive lanes of a quarter-warp hit 8 different bank groups).  The loads of image i + 1 are
+//                   issued into registers right after the MMAs of image i, so they fly under those MMAs and under the wait
+//                   for them; 66 KB of shared memory and 128 TMEM columns per CTA -> 2 CTAs per SM interleave.  The kernel is
+//                   bound by the operand read (each image is read once per slab), not by the tensor pipe.
 //   sw_contract     fp32 FFMA register tiles (64 x 64 of G per CTA, 4 x 4 per thread), the round-2 first version; kept as
 //                   the arithmetic reference of the tensor-core kernel (tests) and for A/B timing.
 // Reduction order is FIXED in both: a chunk sums its images in order, writes its partial slab to the workspace, and the
@@ -187,20 +188,16 @@ contract_kernel(const __grid_constant__ ContractParams P, float* __restrict__ ws
 }
 
 // =====================================================================================================================
-// tcgen05 kernel: 128 x N slabs of G, tf32 split operands
+// tcgen05 kernel: 128 x 128 slabs of G, tf32 split operands
 // =====================================================================================================================
-constexpr int TC_M = 128, TC_NMAX = SW_CONTRACT_MAX_N, TC_THREADS = 256;
-constexpr int TC_A_CHUNK = TC_M * 4 + 4;        // floats per K-chunk of A (4 r's x 128 rows + 16 B pad)
-constexpr int TC_B_CHUNK = TC_NMAX * 4 + 4;     // floats per K-chunk of B
+constexpr int TC_M = 128, TC_N = 128, TC_THREADS = 256;
+constexpr int TC_CHUNK = 128 * 4 + 4;           // floats per K-chunk (4 r's x 128 rows + 16 B pad)
 constexpr uint32_t FMT_TF32 = 2;
 
-struct TcStage {
-    float a_hi[8 * TC_A_CHUNK], a_lo[8 * TC_A_CHUNK];
-    float b_hi[8 * TC_B_CHUNK], b_lo[8 * TC_B_CHUNK];
-};
 struct TcSmem {
-    TcStage st[2];
-    unsigned long long bar[2];
+    float a_hi[8 * TC_CHUNK], a_lo[8 * TC_CHUNK];
+    float b_hi[8 * TC_CHUNK], b_lo[8 * TC_CHUNK];
+    unsigned long long bar;
     uint32_t tmem_base;
     int last;
 };
@@ -221,51 +218,64 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(d));
     lo = __uint_as_float(r);
 }
-__device__ __forceinline__ void split_store(float* __restrict__ hi_dst, float* __restrict__ lo_dst, const float4 v) {
-    float4 h, l;
-    split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-    *reinterpret_cast<float4*>(hi_dst) = h;
-    *reinterpret_cast<float4*>(lo_dst) = l;
+
+// One operand slab of one image = up to 128 rows x 32 batch rows = 1024 float4 items (row, chunk c: r = 4c .. 4c+3), four per
+// thread.  fetch_operand pulls them into REGISTERS (so that the loads of image i + 1 are in flight while the MMAs of image i
+// run and while the CTA waits for them); put_operand splits them into (hi, lo) and writes the canonical K-major layout
+// [8 chunks][TC_CHUNK].  Row index == rows -> the all-ones row when `ones`, larger -> zeros.
+struct OperandRegs { float4 v[4]; };
+
+__device__ __forceinline__ void item_of(int i, int count, int kind, int& row, int& c) {
+    if (kind == SW_CONTRACT_IMAGE) { row = i >> 3; c = i & 7; }      // chunk fastest: a warp reads whole 128-byte rows
+    else { c = i / count; row = i - c * count; }                      // row (= record column) fastest: coalesced along k
 }
 
-// Stage `count` operand rows (row index `row0 + i` of the job's operand; index == rows -> the ones row when `ones`, larger ->
-// zeros) of image `image` as (hi, lo) into [8 chunks][chunk_stride floats]: chunk c holds r = 4c .. 4c+3 of every row.
-__device__ __forceinline__ void stage_split(float* __restrict__ hi, float* __restrict__ lo, int chunk_stride,
-                                            const float* __restrict__ base, long long stride, int k0, int row0, int count, int rows,
-                                            bool ones, int image, int kind, int total_rows) {
-    const int tid = threadIdx.x;
-    if (kind == SW_CONTRACT_IMAGE) {
-        const float* img = base + (size_t)image * stride + (size_t)(k0 + row0) * 32;
-        for (int i = tid; i < count * 8; i += TC_THREADS) {           // item = (row, chunk), chunk fastest: coalesced 128 B rows
-            const int row = i >> 3, c = i & 7;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + row < rows) v = __ldg(reinterpret_cast<const float4*>(img + row * 32) + c);
-            else if (ones && row0 + row == rows) {
-                const long long g0 = (long long)image * 32 + c * 4;
+__device__ __forceinline__ void fetch_operand(OperandRegs& R, const float* __restrict__ base, long long stride, int k0, int row0,
+                                              int count, int rows, bool ones, int image, int kind, int total_rows) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = threadIdx.x + q * TC_THREADS;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < count * 8) {
+            int row, c;
+            item_of(i, count, kind, row, c);
+            const long long g0 = (long long)image * 32 + c * 4;
+            if (row0 + row < rows) {
+                if (kind == SW_CONTRACT_IMAGE) {
+                    v = __ldg(reinterpret_cast<const float4*>(base + (size_t)image * stride + (size_t)(k0 + row0 + row) * 32) + c);
+                } else {
+                    const float* p = base + (size_t)g0 * stride + k0 + row0 + row;
+                    if (g0 < total_rows) v.x = __ldg(p);
+                    if (g0 + 1 < total_rows) v.y = __ldg(p + stride);
+                    if (g0 + 2 < total_rows) v.z = __ldg(p + 2 * stride);
+                    if (g0 + 3 < total_rows) v.w = __ldg(p + 3 * stride);
+                }
+            } else if (ones && row0 + row == rows) {
                 v = make_float4(g0 < total_rows ? 1.f : 0.f, g0 + 1 < total_rows ? 1.f : 0.f, g0 + 2 < total_rows ? 1.f : 0.f,
                                 g0 + 3 < total_rows ? 1.f : 0.f);
             }
-            split_store(hi + c * chunk_stride + row * 4, lo + c * chunk_stride + row * 4, v);
         }
-    } else {
-        for (int i = tid; i < count * 8; i += TC_THREADS) {           // item = (chunk, row), row fastest: coalesced along k
-            const int c = i / count, row = i - c * count;
-            const long long g0 = (long long)image * 32 + c * 4;
-            float t[4];
+        R.v[q] = v;
+    }
+}
+
+__device__ __forceinline__ void put_operand(const OperandRegs& R, float* __restrict__ hi, float* __restrict__ lo, int count, int kind) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                t[q] = 0.0f;
-                if (g0 + q < total_rows) {
-                    if (row0 + row < rows) t[q] = __ldg(base + (size_t)(g0 + q) * stride + k0 + row0 + row);
-                    else if (ones && row0 + row == rows) t[q] = 1.0f;
-                }
-            }
-            split_store(hi + c * chunk_stride + row * 4, lo + c * chunk_stride + row * 4, make_float4(t[0], t[1], t[2], t[3]));
+    for (int q = 0; q < 4; ++q) {
+        const int i = threadIdx.x + q * TC_THREADS;
+        if (i < count * 8) {
+            int row, c;
+            item_of(i, count, kind, row, c);
+            float4 h, l;
+            split_tf32(R.v[q].x, h.x, l.x); split_tf32(R.v[q].y, h.y, l.y);
+            split_tf32(R.v[q].z, h.z, l.z); split_tf32(R.v[q].w, h.w, l.w);
+            *reinterpret_cast<float4*>(hi + c * TC_CHUNK + row * 4) = h;
+            *reinterpret_cast<float4*>(lo + c * TC_CHUNK + row * 4) = l;
         }
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 contract_tc_kernel(const __grid_constant__ ContractParams P, float* __restrict__ ws, unsigned* __restrict__ counters) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TcSmem& s = *reinterpret_cast<TcSmem*>(smem_raw);
@@ -275,43 +285,46 @@ contract_tc_kernel(const __grid_constant__ ContractParams P, float* __restrict__
     const sw_contract_job& J = P.job[j];
     const int local = blockIdx.x - P.first_cta[j];
     const int rows_total = J.K + (J.ones_row ? 1 : 0);
+    const int tiles_n = (J.N + TC_N - 1) / TC_N;
     const int C = P.chunks[j];
-    const int chunk = local % C, mt = local / C;
+    const int chunk = local % C, tile = local / C;
+    const int mt = tile / tiles_n, nt = tile % tiles_n;
     const int img0 = chunk * P.ipc[j], img1 = min(img0 + P.ipc[j], J.n_images);
     const int mrows = min(TC_M, rows_total - mt * TC_M);
-    const int n_pad = (J.N + 15) & ~15;                 // UMMA N: multiple of 16 for M = 128
+    const int ncols = min(TC_N, J.N - nt * TC_N);
+    const int n_pad = (ncols + 15) & ~15;               // UMMA N: multiple of 16 for M = 128
+    const bool a_ones = J.ones_row != 0;
+
+    OperandRegs ra, rb;                                  // the first image's loads fly under the TMEM / barrier set-up
+    fetch_operand(ra, J.a, J.a_stride, J.a_k0, mt * TC_M, mrows, J.K, a_ones, img0, J.a_kind, J.n_rows);
+    fetch_operand(rb, J.b, J.b_stride, J.b_n0, nt * TC_N, ncols, J.N, false, img0, J.b_kind, J.n_rows);
 
     if (warp == 0) {
-        ptx::tcgen05_alloc(ptx::cta_group_1, &s.tmem_base, 256u);
+        ptx::tcgen05_alloc(ptx::cta_group_1, &s.tmem_base, 128u);
         ptx::tcgen05_relinquish_alloc_permit(ptx::cta_group_1);
     }
     if (tid == 0) {
-        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[0]), 1);
-        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[1]), 1);
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar), 1);
         ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
     }
-    // rows of the B operand between N and n_pad are never written by the staging: clear them once (both buffers)
-    if (n_pad > J.N)
-        for (int i = tid; i < (n_pad - J.N) * 8 * 2; i += TC_THREADS) {
-            const int b = i & 1, c = (i >> 1) & 7, row = J.N + (i >> 4);
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(s.st[b].b_hi + c * TC_B_CHUNK + row * 4) = z;
-            *reinterpret_cast<float4*>(s.st[b].b_lo + c * TC_B_CHUNK + row * 4) = z;
-        }
+    // rows of the B operand between ncols and n_pad are never written by the staging: clear them once
+    for (int i = tid; i < (n_pad - ncols) * 8; i += TC_THREADS) {
+        const int c = i & 7, row = ncols + (i >> 3);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(s.b_hi + c * TC_CHUNK + row * 4) = z;
+        *reinterpret_cast<float4*>(s.b_lo + c * TC_CHUNK + row * 4) = z;
+    }
     ptx::tcgen05_fence_before_thread_sync();
     __syncthreads();
     ptx::tcgen05_fence_after_thread_sync();
     const uint32_t tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0);
     const uint32_t idesc = umma_idesc(n_pad, FMT_TF32);
-    uint32_t phase[2] = {0u, 0u};
-    int used[2] = {0, 0};
+    uint32_t phase = 0u;
 
     for (int img = img0; img < img1; ++img) {
-        const int b = (img - img0) & 1;
-        TcStage& S = s.st[b];
-        if (used[b]) { mbar_wait(&s.bar[b], phase[b]); phase[b] ^= 1u; }      // the MMAs that read this buffer have completed
-        stage_split(S.a_hi, S.a_lo, TC_A_CHUNK, J.a, J.a_stride, J.a_k0, mt * TC_M, mrows, J.K, J.ones_row != 0, img, J.a_kind, J.n_rows);
-        stage_split(S.b_hi, S.b_lo, TC_B_CHUNK, J.b, J.b_stride, J.b_n0, 0, J.N, J.N, false, img, J.b_kind, J.n_rows);
+        if (img > img0) { mbar_wait(&s.bar, phase); phase ^= 1u; }    // the MMAs of the previous image have read the operands
+        put_operand(ra, s.a_hi, s.a_lo, mrows, J.a_kind);
+        put_operand(rb, s.b_hi, s.b_lo, ncols, J.b_kind);
         ptx::fence_proxy_async(ptx::space_shared);
         ptx::tcgen05_fence_before_thread_sync();
         __syncthreads();
@@ -320,44 +333,41 @@ contract_tc_kernel(const __grid_constant__ ContractParams P, float* __restrict__
             const bool leader = lane == 0;
             // canonical K-major, no swizzle: core matrix = 8 rows x 16 B; SBO (8-row group stride) = 128 B,
             // LBO (K-chunk stride) = the padded chunk size; one tf32 MMA (K = 8) spans two chunks
-            const uint64_t ah = umma_desc_uniform(S.a_hi, TC_A_CHUNK * 4, 128), al = umma_desc_uniform(S.a_lo, TC_A_CHUNK * 4, 128);
-            const uint64_t bh = umma_desc_uniform(S.b_hi, TC_B_CHUNK * 4, 128), bl = umma_desc_uniform(S.b_lo, TC_B_CHUNK * 4, 128);
+            const uint64_t ah = umma_desc_uniform(s.a_hi, TC_CHUNK * 4, 128), al = umma_desc_uniform(s.a_lo, TC_CHUNK * 4, 128);
+            const uint64_t bh = umma_desc_uniform(s.b_hi, TC_CHUNK * 4, 128), bl = umma_desc_uniform(s.b_lo, TC_CHUNK * 4, 128);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t ao = (uint64_t)(ks * 2 * TC_A_CHUNK * 4 / 16), bo = (uint64_t)(ks * 2 * TC_B_CHUNK * 4 / 16);
-                umma_issue_ss_tf32(tmem, ah + ao, bh + bo, idesc, img > img0 || ks > 0, leader);
-                umma_issue_ss_tf32(tmem, ah + ao, bl + bo, idesc, true, leader);
-                umma_issue_ss_tf32(tmem, al + ao, bh + bo, idesc, true, leader);
+                const uint64_t off = (uint64_t)(ks * 2 * TC_CHUNK * 4 / 16);
+                umma_issue_ss_tf32(tmem, ah + off, bh + off, idesc, img > img0 || ks > 0, leader);
+                umma_issue_ss_tf32(tmem, ah + off, bl + off, idesc, true, leader);
+                umma_issue_ss_tf32(tmem, al + off, bh + off, idesc, true, leader);
             }
-            umma_commit(&s.bar[b], leader);
+            umma_commit(&s.bar, leader);
         }
-        used[b] = 1;
+        if (img + 1 < img1) {                                         // next image's loads: in flight during the MMAs + the wait
+            fetch_operand(ra, J.a, J.a_stride, J.a_k0, mt * TC_M, mrows, J.K, a_ones, img + 1, J.a_kind, J.n_rows);
+            fetch_operand(rb, J.b, J.b_stride, J.b_n0, nt * TC_N, ncols, J.N, false, img + 1, J.b_kind, J.n_rows);
+        }
     }
-    // drain: wait for the last commit of each buffer (MMAs complete in issue order)
-#pragma unroll
-    for (int b = 0; b < 2; ++b)
-        if (used[b]) { mbar_wait(&s.bar[b], phase[b]); phase[b] ^= 1u; }
+    mbar_wait(&s.bar, phase);
     ptx::tcgen05_fence_after_thread_sync();
 
-    // ---- epilogue: thread = (G row m = TMEM lane, column half) ----
+    // ---- epilogue: thread = (G row m = TMEM lane, column half of the slab) ----
     const int m = (warp & 3) * 32 + lane, half = warp >> 2;
-    const int ncols = n_pad >> 1;                        // multiple of 8
-    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * ncols);
-    const int tile_id = P.first_tile[j] + mt;
-    float* part = ws + P.ws_off[j] + ((size_t)mt * C + chunk) * (size_t)(TC_M * n_pad);
-    for (int c0 = 0; c0 < ncols; c0 += 8) {
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int tile_id = P.first_tile[j] + tile;
+    float* part = ws + P.ws_off[j] + ((size_t)tile * C + chunk) * (size_t)(TC_M * TC_N);
+    for (int c0 = half * 64; c0 < min(n_pad, half * 64 + 64); c0 += 8) {
         uint32_t v[8];
         tmem_ld<8>(taddr + c0, v);
         ptx::tcgen05_wait_ld();
         if (C == 1) {
             if (m < mrows)
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int n = half * ncols + c0 + q;
-                    if (n < J.N) scatter(J, mt * TC_M + m, n, __uint_as_float(v[q]));
-                }
+                for (int q = 0; q < 8; ++q)
+                    if (c0 + q < ncols) scatter(J, mt * TC_M + m, nt * TC_N + c0 + q, __uint_as_float(v[q]));
         } else {
-            float* dst = part + (size_t)m * n_pad + half * ncols + c0;
+            float* dst = part + (size_t)m * TC_N + c0;
             *reinterpret_cast<uint4*>(dst) = make_uint4(v[0], v[1], v[2], v[3]);
             *reinterpret_cast<uint4*>(dst + 4) = make_uint4(v[4], v[5], v[6], v[7]);
         }
@@ -365,19 +375,36 @@ contract_tc_kernel(const __grid_constant__ ContractParams P, float* __restrict__
     ptx::tcgen05_fence_before_thread_sync();
     if (C > 1) __threadfence();
     __syncthreads();
-    if (warp == 0) ptx::tcgen05_dealloc(ptx::cta_group_1, tmem, 256u);
+    if (warp == 0) ptx::tcgen05_dealloc(ptx::cta_group_1, tmem, 128u);
     if (C == 1) return;
     if (tid == 0) s.last = atomicAdd(counters + tile_id, 1u) == (unsigned)(C - 1);
     __syncthreads();
     if (!s.last) return;
     __threadfence();
-    const float* base = ws + P.ws_off[j] + (size_t)mt * C * (size_t)(TC_M * n_pad);
-    for (int e = tid; e < mrows * n_pad; e += TC_THREADS) {          // element-wise, chunk order: fixed summation order
-        const int mm = e / n_pad, n = e - mm * n_pad;
-        if (n >= J.N) continue;
-        float sum = 0.0f;
-        for (int c = 0; c < C; ++c) sum += __ldcg(base + (size_t)c * (TC_M * n_pad) + e);
-        scatter(J, mt * TC_M + mm, n, sum);
+    // last arrival: add the partial slabs in chunk order (fixed summation order), four columns per thread and step
+    const float* base = ws + P.ws_off[j] + (size_t)tile * C * (size_t)(TC_M * TC_N);
+    const int quads = n_pad >> 2;
+    for (int e = tid; e < mrows * quads; e += TC_THREADS) {
+        const int mm = e / quads, n4 = (e - mm * quads) * 4;
+        const float* src = base + (size_t)mm * TC_N + n4;
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        int c = 0;
+        for (; c + 4 <= C; c += 4) {                                  // four independent loads in flight
+            const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(c + 0) * (TC_M * TC_N)));
+            const float4 v1 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(c + 1) * (TC_M * TC_N)));
+            const float4 v2 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(c + 2) * (TC_M * TC_N)));
+            const float4 v3 = __ldcg(reinterpret_cast<const float4*>(src + (size_t)(c + 3) * (TC_M * TC_N)));
+            sum.x = ((sum.x + v0.x) + v1.x) + v2.x + v3.x; sum.y = ((sum.y + v0.y) + v1.y) + v2.y + v3.y;
+            sum.z = ((sum.z + v0.z) + v1.z) + v2.z + v3.z; sum.w = ((sum.w + v0.w) + v1.w) + v2.w + v3.w;
+        }
+        for (; c < C; ++c) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)c * (TC_M * TC_N)));
+            sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        const float t[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (n4 + q < ncols) scatter(J, mt * TC_M + mm, nt * TC_N + n4 + q, t[q]);
     }
     if (tid == 0) counters[tile_id] = 0u;
 }
@@ -393,9 +420,10 @@ static int make_plan(const sw_contract_job* jobs, int n_jobs, int sm_count, bool
     if (!jobs || n_jobs <= 0 || n_jobs > CT_MAX_JOBS || sm_count <= 0) return SW_ERR_ARG;
     auto tiles_of = [&](const sw_contract_job& J) {
         const int rows = J.K + (J.ones_row ? 1 : 0);
-        return tc ? (rows + TC_M - 1) / TC_M : ((rows + CT_TILE - 1) / CT_TILE) * ((J.N + CT_TILE - 1) / CT_TILE);
+        return tc ? ((rows + TC_M - 1) / TC_M) * ((J.N + TC_N - 1) / TC_N)
+                  : ((rows + CT_TILE - 1) / CT_TILE) * ((J.N + CT_TILE - 1) / CT_TILE);
     };
-    auto tile_floats = [&](const sw_contract_job& J) { return tc ? (long long)TC_M * ((J.N + 15) & ~15) : (long long)CT_TILE * CT_TILE; };
+    auto tile_floats = [&](const sw_contract_job&) { return tc ? (long long)TC_M * TC_N : (long long)CT_TILE * CT_TILE; };
     long long image_tiles = 0;
     for (int j = 0; j < n_jobs; ++j) {
         const sw_contract_job& J = jobs[j];
@@ -407,10 +435,11 @@ static int make_plan(const sw_contract_job* jobs, int n_jobs, int sm_count, bool
             if (!J.seg[s].out || J.seg[s].k_begin < 0 || J.seg[s].k_count <= 0) return SW_ERR_ARG;
         image_tiles += (long long)tiles_of(J) * J.n_images;
     }
-    // images per chunk: a few CTAs per SM in flight, at least 4 images per CTA (amortises the partial-tile round trip)
-    const long long target = (tc ? 2LL : 3LL) * sm_count;
+    // images per chunk: a few CTAs per SM in flight, at least 8 images per CTA (amortises the set-up and the partial-slab
+    // round trip; small problems stay unsplit and store directly)
+    const long long target = (tc ? 4LL : 3LL) * sm_count;
     long long ipc = (image_tiles + target - 1) / target;
-    if (ipc < 4) ipc = 4;
+    if (ipc < 8) ipc = 8;
     plan.p.n_jobs = n_jobs;
     plan.ws_floats = 0;
     int cta = 0, tile0 = 0;

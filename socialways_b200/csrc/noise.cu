@@ -5,9 +5,11 @@
 // need the reference's exact noise stream can let the GPU draw it (Generator.predict_k(noise=None, seed=...)): same
 // distribution (24-bit uniform grid, like torch.rand for float32), a DIFFERENT stream -- parity tests keep host noise.
 //
-// Stream definition (so that any implementation can reproduce it): element e of the output belongs to group g = e / 4;
-// the four values of group g are Philox4x32-10(counter = (g_lo, g_hi, offset_lo, offset_hi), key = (seed_lo, seed_hi)),
-// each mapped to float by (x >> 8) * 2^-24.  tests/test_gpu_noise.py checks it against a numpy restatement.
+// Stream definition (so that any implementation can reproduce it): element e of the output belongs to group
+// g = first_group + e / 4; the four values of group g are Philox4x32-10(counter = (g_lo, g_hi, offset_lo, offset_hi),
+// key = (seed_lo, seed_hi)), each mapped to float by (x >> 8) * 2^-24.  `first_group` lets a rank draw exactly its rows of a
+// larger logical tensor (sharded training: same noise whatever the number of GPUs).  tests/test_gpu_noise.py checks the
+// stream against a numpy restatement.
 #include "sw_common.cuh"
 
 namespace sw {
@@ -26,12 +28,13 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 }
 
 __global__ void __launch_bounds__(256)
-noise_uniform_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset) {
+noise_uniform_kernel(float* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset,
+                     unsigned long long first_group) {
     const uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
     const long long groups = (n + 3) >> 2;
     for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (long long)gridDim.x * blockDim.x) {
-        const uint4 r = philox4x32_10(make_uint4((unsigned)g, (unsigned)((unsigned long long)g >> 32), (unsigned)offset,
-                                                 (unsigned)(offset >> 32)), key);
+        const unsigned long long gg = first_group + (unsigned long long)g;
+        const uint4 r = philox4x32_10(make_uint4((unsigned)gg, (unsigned)(gg >> 32), (unsigned)offset, (unsigned)(offset >> 32)), key);
         const float4 v = make_float4((r.x >> 8) * 5.9604644775390625e-8f, (r.y >> 8) * 5.9604644775390625e-8f,
                                      (r.z >> 8) * 5.9604644775390625e-8f, (r.w >> 8) * 5.9604644775390625e-8f);
         if (4 * g + 3 < n) {
@@ -45,13 +48,13 @@ noise_uniform_kernel(float* __restrict__ out, long long n, unsigned long long se
 
 }  // namespace sw
 
-extern "C" int sw_noise_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset, int sm_count,
-                                void* stream) {
+extern "C" int sw_noise_uniform(float* out, long long n, unsigned long long seed, unsigned long long offset,
+                                unsigned long long first_group, int sm_count, void* stream) {
     if (!out || n <= 0 || sm_count <= 0) return SW_ERR_ARG;
     if (((uintptr_t)out & 15u) != 0) return SW_ERR_ARG;
     long long blocks = ((n + 3) / 4 + 255) / 256;
     if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
-    sw::noise_uniform_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset);
+    sw::noise_uniform_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, first_group);
     SW_CUDA_TRY(cudaGetLastError());
     return SW_OK;
 }

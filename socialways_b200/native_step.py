@@ -143,6 +143,8 @@ class NativeStep:
         # inputs (filled by the caller before every launch / replay)
         self.obsv, self.pred = f(bs, To, 2), f(bs, Tp, 2)
         self.noise, self.targets = f(bs, trainer.noise_len), f(2)
+        self._targets_pin = [torch.empty(2).pin_memory() for _ in range(4)]     # rotating: an upload may still be in flight
+        self._targets_i = 0
         # generator forward + stash; observation pass and decode steps share one image sequence so that the LSTM weight
         # gradient is ONE contraction job
         self.h, self.c, self.x_last = f(bs, H), f(bs, H), f(bs, 4)
@@ -181,6 +183,13 @@ class NativeStep:
         self.d_linear = packs.d_linear
         self.backup = torch.empty_like(self.d_linear)
         self._build_jobs()
+
+    def set_targets(self, zeros_value, ones_value):
+        """The smoothed labels of the iteration (train.py:471-472) -> device, without a host synchronisation."""
+        t = self._targets_pin[self._targets_i & 3]
+        self._targets_i += 1
+        t[0], t[1] = zeros_value, ones_value
+        self.targets.copy_(t, non_blocking=True)
 
     # ---------------------------------------------------------------- contraction job lists
     def _build_jobs(self):

@@ -297,12 +297,15 @@ def disc_heads_bwd(pack, xrec, pred_dim, d_label, d_code, n_latent=2, want_dh=Tr
     return d_h, d_pred, grec
 
 
-def noise_uniform(shape, device, seed, offset=0, out=None):
-    """sw_noise_uniform: uniform [0, 1) fp32 noise drawn on the device (Philox4x32-10 keyed by seed, counter offset)."""
+def noise_uniform(shape, device, seed, offset=0, out=None, first_element=0):
+    """sw_noise_uniform: uniform [0, 1) fp32 noise drawn on the device (Philox4x32-10 keyed by seed, counter offset).
+    first_element (multiple of 4): the output is the slice [first_element, first_element + n) of the logical stream."""
     if out is None:
         out = torch.empty(*shape, device=device)
+    if first_element % 4:
+        raise ValueError("noise_uniform: first_element must be a multiple of 4")
     code = _lib.lib().sw_noise_uniform(_lib.ptr(out), out.numel(), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1),
-                                       sm_count(out.device), _stream())
+                                       first_element // 4, sm_count(out.device), _stream())
     _lib.check(code, "sw_noise_uniform")
     return out
 

@@ -365,10 +365,13 @@ class SocialWaysTrainer:
         if backup is not None:
             d_lin.copy_(backup)
 
-    def train_native(self, verbose=True, use_graph=True, log_losses=False):
+    def train_native(self, verbose=True, use_graph=True, log_losses=False, device_noise_seed=None):
         """train() with the iteration executed by native_step.NativeStep: ~30 launches of this library's kernels per
         iteration (no autograd, no cuBLAS, no ATen reductions), one CUDA graph per mini-batch shape.  Needs
-        fused_adam=True (flat parameter / gradient buffers).  Same RNG consumption and quirks as train()."""
+        fused_adam=True (flat parameter / gradient buffers).  Same RNG consumption and quirks as train().
+        device_noise_seed=s: the per-iteration latent noise (train.py:473: torch.rand on the CPU, ~1 ms per 4 096 agents --
+        more than the GPU needs for the whole iteration) is drawn on the device instead (Philox4x32-10, sw_noise_uniform): same
+        distribution, a different stream, identical for any number of ranks.  The two label scalars stay on numpy's RNG."""
         if not self.fused_adam:
             raise RuntimeError("train_native() needs fused_adam=True (flat parameter / gradient buffers)")
         from .native_step import NativePacks, NativeStep
@@ -380,11 +383,20 @@ class SocialWaysTrainer:
         stats_acc = torch.zeros(8, device=dev, dtype=torch.float64)
         n_iter = 0
         for g_lo, g_hi, sub in self._minibatches():
+            self._native_iteration = getattr(self, "_native_iteration", 0) + 1
             global_bs = g_hi - g_lo
             lo, hi = g_lo, g_hi
             # train.py:471-473: two numpy scalars, then the noise of the GLOBAL mini-batch from torch's CPU generator
             t01 = (float(np.random.uniform(0, 0.1)), float(np.random.uniform(0.9, 1.0)))
-            noise = torch.rand(global_bs, self.noise_len)
+            pin = None
+            if device_noise_seed is None:
+                pins = self._pin.get(global_bs)
+                if pins is None:
+                    pins = self._pin[global_bs] = [dict(noise=torch.empty(global_bs, self.noise_len).pin_memory(),
+                                                        ev=torch.cuda.Event()) for _ in range(2)]
+                pin = pins[n_iter & 1]
+                pin["ev"].synchronize()                       # the upload that last read this pinned buffer has finished
+                torch.rand(global_bs, self.noise_len, out=pin["noise"])     # same stream as torch.rand(bs, noise_len)
             if self.world_size > 1:       # this rank's contiguous block of scenes
                 s_lo, s_hi, sub = swdist.shard_scenes(sub, self.world_size, self.rank)
                 if s_hi <= s_lo:          # more ranks than scenes: contribute zero gradients to the three all-reduces
@@ -399,18 +411,15 @@ class SocialWaysTrainer:
                 step = NativeStep(self, self._native_packs, bs, self.generator.scene_index(sub, bs, dev), global_bs)
                 ent = self._native_steps[key] = dict(step=step, graph=None, seen=0)
             step = ent["step"]
-            pin = self._pin.get(global_bs)
-            if pin is None:
-                pin = self._pin[global_bs] = dict(noise=torch.empty(global_bs, self.noise_len).pin_memory(),
-                                                  t=torch.empty(2).pin_memory(), ev=torch.cuda.Event())
-            pin["ev"].synchronize()                           # the previous upload from these pinned buffers has finished
-            pin["noise"].copy_(noise)
-            pin["t"][0], pin["t"][1] = t01
             step.obsv.copy_(self.dataset_obsv[lo:hi])
             step.pred.copy_(self.dataset_pred[lo:hi])
-            step.noise.copy_(pin["noise"][lo - g_lo:hi - g_lo], non_blocking=True)
-            step.targets.copy_(pin["t"], non_blocking=True)
-            pin["ev"].record()
+            if pin is not None:
+                step.noise.copy_(pin["noise"][lo - g_lo:hi - g_lo], non_blocking=True)
+                pin["ev"].record()
+            else:                                             # rows [lo - g_lo, hi - g_lo) of the iteration's logical [global_bs, 32] noise
+                ops.noise_uniform(None, dev, device_noise_seed, offset=self._native_iteration, out=step.noise,
+                                  first_element=(lo - g_lo) * self.noise_len)
+            step.set_targets(*t01)
             if use_graph and ent["graph"] is None and ent["seen"] >= 1:
                 g = torch.cuda.CUDAGraph()
                 torch.cuda.synchronize()

@@ -111,7 +111,7 @@ def test_training_step_entry_points_reject_bad_arguments():
     assert lib.sw_contract_plan((ContractJob * 1)(job), 1, 148, 0, ctypes.byref(ws), ctypes.byref(nc)) == 0
     assert nc.value == 2 * 4 and ws.value > 0 and ws.value % 4096 == 0           # FFMA: 64 x 64 tiles of the 69 x 256 result
     assert lib.sw_contract_plan((ContractJob * 1)(job), 1, 148, 1, ctypes.byref(ws), ctypes.byref(nc)) == 0
-    assert nc.value == 1 and ws.value > 0 and ws.value % (128 * 256) == 0        # tcgen05: one 128-row slab
+    assert nc.value == 2 and ws.value > 0 and ws.value % (128 * 128) == 0        # tcgen05: two 128 x 128 slabs
     bad = ContractJob(None, None, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, (ContractSeg * 3)())
     assert lib.sw_contract_plan((ContractJob * 1)(bad), 1, 148, 1, ctypes.byref(ws), ctypes.byref(nc)) == -1
     assert lib.sw_contract_tc(None, 0, None, 0, None, 0, 148, None) == -1

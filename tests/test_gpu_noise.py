@@ -33,6 +33,28 @@ def test_noise_matches_numpy_philox(n):
     assert 0.0 <= got.min() and got.max() < 1.0 and (n < 10000 or abs(got.mean() - 0.5) < 0.01)
 
 
+def test_noise_slices_of_one_stream():
+    """first_element: a rank draws exactly its rows of the iteration's logical noise tensor (sharded training)."""
+    from socialways_b200 import ops
+    dev = torch.device("cuda")
+    full = ops.noise_uniform((4096, 32), dev, 99, offset=7)
+    part = ops.noise_uniform((1000, 32), dev, 99, offset=7, first_element=517 * 32)
+    assert torch.equal(part, full[517:1517])
+    assert not torch.equal(ops.noise_uniform((4096, 32), dev, 99, offset=8), full)
+
+
+def test_native_training_with_device_noise_runs_and_learns():
+    import numpy as np
+    from oracle import socialways_oracle as so
+    from socialways_b200.trainer import SocialWaysTrainer
+    tr = SocialWaysTrainer(so.toy_samples(216, 6), batch_size=64, use_social=True, weights=so.init_weights(seed=1, n_next=2),
+                           fused_adam=True)
+    np.random.seed(0)
+    res = [tr.train_native(verbose=False, device_noise_seed=5) for _ in range(4)]
+    assert all(np.isfinite(r).all() for r in res) and res[0] != res[-1]
+    assert all(np.isfinite(v) for v in tr.last_epoch_mean_losses.values())
+
+
 def test_predict_k_with_device_noise():
     import socialways_b200 as sw
     from socialways_b200 import ops
