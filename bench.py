@@ -401,7 +401,7 @@ def run_ours(args):
             enc = ops.lstm_seq(pk["enc"], obsv_d, want_x_last=True)
         if timed and headline:
             s1.record()
-        ub = torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])
+        ub = ops.rows_linear(enc["h"], pk["pool_m"], pk["pool_m0"])
         if timed and headline:
             s2.record()
         if precision == "fp16x2" and A_PER_SCENE <= ops.pool_tcx_max_scene():
@@ -559,7 +559,7 @@ def run_ours(args):
                                "noise": "caller-supplied host tensor (the reference's contract, train.py:584): 128 B per "
                                         "trajectory over PCIe -- the limiter of this variant when several GPUs share the "
                                         "host's memory system (profiles/r1_h2d_probe.txt: 55 GB/s for one GPU alone)"},
-            "gpu_launches": 4 * args.steps,
+            "gpu_launches": 5 * args.steps,          # encoder, (u | beta) map, pooling, decode, best-of-K metrics: all own kernels
             "host_cpu_affinity": None if cpus is None else f"{len(cpus)} cpus ({cpus[0]}-{cpus[-1]}), GPU-local (NVML)",
             "train_step": train,
             "clocks": clocks,

@@ -297,6 +297,20 @@ def disc_heads_bwd(pack, xrec, pred_dim, d_label, d_code, n_latent=2, want_dh=Tr
     return d_h, d_pred, grec
 
 
+def rows_linear(x, w, bias=None, add1=None, add2=None, out=None):
+    """sw_rows_linear: out[row] = bias + add1[row] + add2[row] + x[row] @ w   (x [N,K], w [K,M] row-major, K, M <= 80)."""
+    x, w = _f32(x), _f32(w)
+    n, k = x.shape
+    m = w.shape[1]
+    if out is None:
+        out = torch.empty(n, m, device=x.device)
+    code = _lib.lib().sw_rows_linear(_lib.ptr(x), k, _lib.ptr(w), _lib.ptr(None if bias is None else _f32(bias)),
+                                     _lib.ptr(None if add1 is None else _f32(add1)), _lib.ptr(None if add2 is None else _f32(add2)),
+                                     _lib.ptr(out), m, n, k, m, _stream())
+    _lib.check(code, "sw_rows_linear")
+    return out
+
+
 def noise_uniform(shape, device, seed, offset=0, out=None, first_element=0):
     """sw_noise_uniform: uniform [0, 1) fp32 noise drawn on the device (Philox4x32-10 keyed by seed, counter offset).
     first_element (multiple of 4): the output is the slice [first_element, first_element + n) of the logical stream."""

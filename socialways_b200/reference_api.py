@@ -326,7 +326,7 @@ class Generator(nn.Module):
         pooled = None
         if self.use_social:                                                    # train.py:408-413
             scenes = self.scene_index(sub_batches, n, obsv_p.device)
-            ub = torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])
+            ub = ops.rows_linear(enc["h"], pk["pool_m"], pk["pool_m0"])        # (u | beta) = h . M + m0, own kernel
             if precision == "fp16x2" and scenes.max_scene <= ops.pool_tcx_max_scene():
                 pooled = ops.pool_tcx(pk["pool"], pk["pool_tcx"], enc["x_last"], enc["h"], ub, scenes)   # layer 2 on tcgen05
             else:
