@@ -144,10 +144,13 @@ int sw_decode_tc_pack_sizes(int* n_bf16, int* n_f32);
 
 /* fp32-faithful tensor-core variant of sw_decode_fwd: tcgen05.mma on fp16 hi/lo split operands (x = hi + lo,
  * A.B ~= Ahi.Bhi + Ahi.Blo + Alo.Bhi, fp32 accumulate in TMEM; a1/a2 live in TMEM as the A operand of the next
- * layer).  Packs from packing.pack_decoder_tcx; sizes via sw_decode_tcx_pack_sizes. */
+ * layer).  Packs from packing.pack_decoder_tcx; sizes via sw_decode_tcx_pack_sizes.
+ * status (device int, may be NULL): bit 0 is set when an emitted (p, v) leaves fp16's exponent range or is not finite --
+ * i.e. when an operand of the split overflowed (layer-1 activations > 65 504, states > 6e4): the result is then not
+ * trustworthy and the caller should use sw_decode_fwd (fp32 FFMA) for these inputs / weights. */
 int sw_decode_fwd_tcx(const void* tcx_w16, const void* tcx_wsz16, const float* tcx_f32, const float* h0,
                       const float* c0, const float* pooled, const float* noise, const float* x_last, float* out,
-                      int n_agents, int n_samples, int n_next, int sm_count, void* stream);
+                      int* status, int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 int sw_decode_tcx_pack_sizes(int* n_w16, int* n_wsz16, int* n_f32);
 
 /* Discriminator FC heads (train.py:281-292, 300-309), one thread per trajectory, all 8 Linear layers fused.

@@ -33,7 +33,7 @@ _PROTOTYPES = {
     "sw_decode_bwd": (_I, [_P] * 16 + [_I, _I, _I, _I, _P]),
     "sw_decode_fwd_tc": (_I, [_P] * 8 + [_I, _I, _I, _I, _P]),
     "sw_decode_tc_pack_sizes": (_I, [_P, _P]),
-    "sw_decode_fwd_tcx": (_I, [_P] * 9 + [_I, _I, _I, _I, _P]),
+    "sw_decode_fwd_tcx": (_I, [_P] * 10 + [_I, _I, _I, _I, _P]),
     "sw_decode_tcx_pack_sizes": (_I, [_P, _P, _P]),
     "sw_disc_heads_pack_floats": (_I, [_I, _I]),
     "sw_disc_heads_record_dims": (_I, [_I, _I, _P, _P]),

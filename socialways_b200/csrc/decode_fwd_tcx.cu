@@ -28,6 +28,7 @@
 // TMEM columns: [0,160) c1 | [160,320) L1 acc -> a1 hi|lo ; later gates half 1 | [320,480) L2 acc (hi | lo weight halves) ;
 //               later gates half 0.  MMAs execute in issue order, so the gates MMAs are queued right behind the
 //               last reader of the region they overwrite and run under the epilogues.
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "sw_common.cuh"
@@ -55,6 +56,8 @@ struct TcxSmem {
     float f32[XF_TOTAL];
     float vpart[8 * X_ROWS];                // partial velocities [quarter][component][row]
     unsigned long long bar[3];
+    unsigned long long bar_w;               // TMA: weights (once per CTA)
+    unsigned long long bar_z;               // TMA: the tile's noise block (prefetched one tile ahead)
     uint32_t tmem_base;
 };
 
@@ -141,37 +144,54 @@ __device__ __forceinline__ void output_epilogue(uint32_t t_acc, const float* __r
 }
 
 __global__ void __launch_bounds__(X_THREADS, 1)
-decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__ wsz16, const float* __restrict__ wf32,
+decode_fwd_tcx_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][32] fp32, box 128 x 32, 128-byte swizzle */,
+                      const __half* __restrict__ w16, const __half* __restrict__ wsz16, const float* __restrict__ wf32,
                       const float* __restrict__ h0, const float* __restrict__ c0, const float* __restrict__ pooled,
                       const float* __restrict__ noise, const float* __restrict__ x_last, float* __restrict__ out,
-                      int n_agents, long long n_rows, int n_next, int n_tiles) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+                      int* __restrict__ status, int n_agents, long long n_rows, int n_next, int n_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
     TcxSmem& s = *reinterpret_cast<TcxSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lq = warp & 3, cq = warp >> 2;
     const int r = lq * 32 + lane;
     const bool leader = lane == 0;          // lane of warp 0 that issues the MMAs
 
-    for (int i = tid * 8; i < XW_TOTAL; i += X_THREADS * 8)
-        *reinterpret_cast<uint4*>(s.w + i) = __ldg(reinterpret_cast<const uint4*>(w16 + i));
-    for (int i = tid; i < XF_TOTAL; i += X_THREADS) s.f32[i] = __ldg(wf32 + i);
     if (warp == 0) {
         ptx::tcgen05_alloc(ptx::cta_group_1, &s.tmem_base, 512u);
         ptx::tcgen05_relinquish_alloc_permit(ptx::cta_group_1);
     }
+    // noise block of a tile: [128 rows][32] fp32 = 16 KB -> ONE tensor-map TMA copy into the hoist staging buffer (free from
+    // the end of a tile's hoist to the next tile's prologue), issued one tile ahead.  128-byte swizzle: the 16-byte piece q of
+    // row r lands at piece q ^ (r & 7), so the row-per-lane reads below are conflict free; rows past the batch arrive as zeros.
+    auto prefetch_noise = [&](int tile) {
+        mbar_expect_tx(&s.bar_z, X_ROWS * SW_Z * 4);
+        tma_load_2d(s.stage, &noise_map, 0, tile * X_ROWS, &s.bar_z);
+    };
     if (tid == 0) {
         ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[0]), 1);
         ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[1]), 1);
         ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar[2]), 1);
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar_w), 1);
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar_z), 1);
         ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
+        // all step weights (hi | lo fp16, 162 KB, already in the UMMA operand layout) + the fp32 tail: TMA, once per CTA
+        constexpr uint32_t W_BYTES = XW_TOTAL * 2, W_PIECE = W_BYTES / 4, F_BYTES = XF_TOTAL * 4;
+        static_assert(W_PIECE % 16 == 0 && F_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+        mbar_expect_tx(&s.bar_w, W_BYTES + F_BYTES);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            tma_load_1d(reinterpret_cast<unsigned char*>(s.w) + q * W_PIECE, reinterpret_cast<const unsigned char*>(w16) + q * W_PIECE,
+                        W_PIECE, &s.bar_w);
+        tma_load_1d(s.f32, wf32, F_BYTES, &s.bar_w);
+        if ((int)blockIdx.x < n_tiles) prefetch_noise(blockIdx.x);
     }
-    ptx::fence_proxy_async(ptx::space_shared);
     ptx::tcgen05_fence_before_thread_sync();
     __syncthreads();
     ptx::tcgen05_fence_after_thread_sync();
+    mbar_wait(&s.bar_w, 0u);                // weights have landed (async proxy -> visible to every thread and to the MMAs)
     const uint32_t tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0);   // warp-uniform for the compiler (uniform datapath)
     const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);       // this thread's lane, column 0
-    uint32_t ph0 = 0, ph1 = 0;              // parities: bar0 (hoist, L1, L2) | bar1 / bar2 (gate halves)
+    uint32_t ph0 = 0, ph1 = 0, phz = 0;     // parities: bar0 (hoist, L1, L2) | bar1 / bar2 (gate halves) | bar_z (noise block)
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const long long row0 = (long long)tile * X_ROWS;
@@ -191,7 +211,7 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
 #pragma unroll
         for (int q = 0; q < 3; ++q)
             if (tid + q * X_THREADS < CHUNK_U4) wreg[q] = __ldg(wsz4 + tid + q * X_THREADS);
-        float4 sreg[4], zreg[2], hreg[2][2];
+        float4 sreg[4], hreg[2][2];
         float2 xl = make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                                     // S tile [128][16 pieces]: piece g = tid + 512 i
@@ -200,12 +220,7 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             if (pooled && row0 + row < n_rows)
                 sreg[i] = __ldg(reinterpret_cast<const float4*>(pooled + (size_t)((abase + row) % n_agents) * SW_H) + piece);
         }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {                                     // z tile [128][8 pieces]
-            const int g = tid + i * X_THREADS, row = g >> 3, piece = g & 7;
-            zreg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row0 + row < n_rows) zreg[i] = __ldg(reinterpret_cast<const float4*>(noise + (size_t)(row0 + row) * SW_Z) + piece);
-        }
+        // (the z tile [128][8 pieces] arrives by TMA in the staging buffer: prefetched during the previous tile)
         const int hrow = warp * 8 + (lane & 7);                           // h0 items: (row, chunk = (lane >> 3) + 4 i)
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
@@ -219,17 +234,13 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
         if (cq == 1 && valid) xl = __ldg(reinterpret_cast<const float2*>(x_last + (size_t)agent * 4));
         {
             float4* sS = reinterpret_cast<float4*>(s.h);                  // [128 rows][16 pieces], piece' = piece ^ (row & 7)
-            float4* sZ = reinterpret_cast<float4*>(s.stage);              // [128 rows][8 pieces],  piece' = piece ^ (row & 7)
+            const float4* sZ = reinterpret_cast<const float4*>(s.stage);  // [128 rows][8 pieces], piece' = piece ^ (row & 7) (TMA swizzle)
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int g = tid + i * X_THREADS, row = g >> 4, piece = g & 15;
                 sS[row * 16 + (piece ^ (row & 7))] = sreg[i];
             }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int g = tid + i * X_THREADS, row = g >> 3, piece = g & 7;
-                sZ[row * 8 + (piece ^ (row & 7))] = zreg[i];
-            }
+            mbar_wait(&s.bar_z, phz); phz ^= 1;                           // this tile's noise block has landed
             __syncthreads();
             // [S ; z] (K = 96): this thread owns K 24cq .. 24cq+23 of its row = pieces 6cq .. 6cq+5 (S: 0..15, z: 16..23)
             // -> hi|lo TMEM A operand in R1: hi columns [160,208), lo [208,256)
@@ -265,6 +276,7 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
         float c[16] = {cq4[0].x, cq4[0].y, cq4[0].z, cq4[0].w, cq4[1].x, cq4[1].y, cq4[1].z, cq4[1].w,
                        cq4[2].x, cq4[2].y, cq4[2].z, cq4[2].w, cq4[3].x, cq4[3].y, cq4[3].z, cq4[3].w};
         float p0 = xl.x, p1 = xl.y;
+        bool out_of_range = false;          // fp16 range guard (see the row finish below), one predicate per thread
         // c1 = [S ; z] . W1[S,z rows]^T accumulated into TMEM [0,160): three K = 32 chunks of streamed weights
         for (int ch = 0; ch < 3; ++ch) {
 #pragma unroll
@@ -287,6 +299,8 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;       // staging buffer is free again / c1 complete
             ptx::tcgen05_fence_after_thread_sync();
         }
+        // the staging buffer is idle until the next tile's prologue: fetch that tile's noise block now (12 steps ahead of its use)
+        if (tid == 0 && tile + (int)gridDim.x < n_tiles) prefetch_noise(tile + gridDim.x);
         {   // b1 joins c1 (the columns this thread reads back in the layer-1 epilogue)
             const int col0 = (cq < 2) ? cq * 48 : 96 + (cq - 2) * 32;
             if (cq < 2) fold_bias_into_c1<3>(tl + XC_C1 + col0, s.f32 + XF_B1 + col0);
@@ -344,6 +358,11 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
                 const float v0 = s.vpart[0 * X_ROWS + r] + s.vpart[2 * X_ROWS + r] + s.vpart[4 * X_ROWS + r] + s.vpart[6 * X_ROWS + r] + s.f32[XF_B34];
                 const float v1 = s.vpart[1 * X_ROWS + r] + s.vpart[3 * X_ROWS + r] + s.vpart[5 * X_ROWS + r] + s.vpart[7 * X_ROWS + r] + s.f32[XF_B34 + 1];
                 p0 += v0; p1 += v1;
+                // fp16 range guard: the operands of the split (x here, a1 upstream) live in fp16's exponent range; a layer-1
+                // activation beyond 65 504 turns into inf -> NaN and reaches this velocity, a state beyond it would overflow
+                // the next step's x block.  One predicate update per row and step (no branch in the step loop); the word is
+                // raised once per tile, the host reads it when it next synchronises.
+                out_of_range |= !(fmaxf(fmaxf(fabsf(p0), fabsf(p1)), fmaxf(fabsf(v0), fabsf(v1))) <= 6.0e4f);
                 if (feed_back) {
                     uint32_t hp, lp, hv, lv;
                     split2(p0, p1, hp, lp);
@@ -411,6 +430,7 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
             }
             ph1 ^= 1;
         }
+        if (out_of_range && valid && status) atomicOr(status, 1);
     }
     ptx::tcgen05_fence_before_thread_sync();
     __syncthreads();
@@ -419,19 +439,45 @@ decode_fwd_tcx_kernel(const __half* __restrict__ w16, const __half* __restrict__
 
 }  // namespace sw
 
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no link-time dependency on libcuda)
+static int encode_noise_map(CUtensorMap* map, const float* noise, long long n_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        SW_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !fn) return SW_ERR_UNSUPPORTED;
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)SW_Z, (cuuint64_t)n_rows};         // innermost first: 32 floats per row
+    const cuuint64_t strides[1] = {(cuuint64_t)SW_Z * 4};                       // bytes between rows
+    const cuuint32_t box[2] = {(cuuint32_t)SW_Z, (cuuint32_t)sw::X_ROWS}, elem[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(noise), dims, strides, box, elem,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SW_OK : SW_ERR_ARG;
+}
+
 extern "C" int sw_decode_fwd_tcx(const void* tcx_w16, const void* tcx_wsz16, const float* tcx_f32, const float* h0,
                                  const float* c0, const float* pooled, const float* noise, const float* x_last, float* out,
-                                 int n_agents, int n_samples, int n_next, int sm_count, void* stream) {
+                                 int* status, int n_agents, int n_samples, int n_next, int sm_count, void* stream) {
     if (!tcx_w16 || !tcx_wsz16 || !tcx_f32 || !h0 || !c0 || !noise || !x_last || !out) return SW_ERR_ARG;
     if (n_agents <= 0 || n_samples <= 0 || n_next <= 0 || sm_count <= 0) return SW_ERR_ARG;
     const long long n_rows = (long long)n_agents * n_samples;
     const long long tiles = (n_rows + sw::X_ROWS - 1) / sw::X_ROWS;
     if (tiles > 0x7fffffffLL) return SW_ERR_UNSUPPORTED;
+    if (((uintptr_t)noise & 15u) != 0) return SW_ERR_ARG;         // TMA: 16-byte aligned global address
+    CUtensorMap noise_map;
+    const int rc = encode_noise_map(&noise_map, noise, n_rows);
+    if (rc != SW_OK) return rc;
     const int smem = (int)sizeof(sw::TcxSmem);
     SW_SET_MAX_SMEM(sw::decode_fwd_tcx_kernel, smem);
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     sw::decode_fwd_tcx_kernel<<<grid, sw::X_THREADS, smem, (cudaStream_t)stream>>>(
-        (const __half*)tcx_w16, (const __half*)tcx_wsz16, tcx_f32, h0, c0, pooled, noise, x_last, out, n_agents, n_rows,
+        noise_map, (const __half*)tcx_w16, (const __half*)tcx_wsz16, tcx_f32, h0, c0, pooled, noise, x_last, out, status, n_agents, n_rows,
         n_next, (int)tiles);
     SW_CUDA_TRY(cudaGetLastError());
     return SW_OK;

@@ -39,6 +39,24 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
         if (spins > (1u << 24)) __trap();
 }
 
+// TMA (bulk asynchronous copy engine), 1-D form: `bytes` (multiple of 16, both addresses 16-byte aligned) from global to this
+// CTA's shared memory; completion is signalled on `bar` as transaction bytes.  One thread arms the barrier with
+// mbar_expect_tx(total bytes) and issues the copies; consumers wait on the barrier's phase (mbar_wait).
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    ptx::mbarrier_arrive_expect_tx(ptx::sem_release, ptx::scope_cta, ptx::space_shared, reinterpret_cast<uint64_t*>(bar), bytes);
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, unsigned long long* bar) {
+    ptx::cp_async_bulk(ptx::space_cluster, ptx::space_global, smem_dst, gmem_src, bytes, reinterpret_cast<uint64_t*>(bar));
+}
+
+// 2-D tiled form through a tensor map (cuTensorMapEncodeTiled on the host, passed as a __grid_constant__ kernel parameter):
+// box (c0 .. , c1 ..) -> shared memory, out-of-bounds elements zero-filled, optional 128-byte hardware swizzle (16-byte chunk
+// index XOR (row & 7): row-per-lane reads of a [rows][128 B] box are then bank-conflict free).  Destination 1024-byte aligned.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tensor_map, int c0, int c1, unsigned long long* bar) {
+    const int32_t coords[2] = {c0, c1};
+    ptx::cp_async_bulk_tensor(ptx::space_cluster, ptx::space_global, smem_dst, tensor_map, coords, reinterpret_cast<uint64_t*>(bar));
+}
+
 // MMA / commit issue.  Called by ALL 32 lanes of the issuing warp (convergent code: descriptors stay in uniform
 // registers); `leader` predicates the instruction itself so that exactly one lane issues it.
 __device__ __forceinline__ void umma_commit(unsigned long long* bar, bool leader) {

@@ -225,8 +225,9 @@ def _tcx_pack_sizes():
     return _TCX_SIZES
 
 
-def decode_tcx(w16, wsz16, f32, h0, c0, pooled, noise, x_last, n_next, out=None):
-    """sw_decode_fwd_tcx: tcgen05 decode kernel on fp16 hi/lo split operands (fp32-faithful)."""
+def decode_tcx(w16, wsz16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, status=None):
+    """sw_decode_fwd_tcx: tcgen05 decode kernel on fp16 hi/lo split operands (fp32-faithful).  status: device int32[1] that
+    receives bit 0 when an operand left fp16's exponent range (then the result is not trustworthy)."""
     noise = _f32(noise)
     k, n, z = noise.shape
     if z != Z or h0.shape != (n, H):
@@ -241,7 +242,8 @@ def decode_tcx(w16, wsz16, f32, h0, c0, pooled, noise, x_last, n_next, out=None)
         out = torch.empty(k, n, n_next, 4, device=noise.device)
     code = _lib.lib().sw_decode_fwd_tcx(w16.data_ptr(), wsz16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(_f32(h0)),
                                         _lib.ptr(_f32(c0)), _lib.ptr(None if pooled is None else _f32(pooled)),
-                                        _lib.ptr(noise), _lib.ptr(_f32(x_last)), _lib.ptr(out), n, k, n_next,
+                                        _lib.ptr(noise), _lib.ptr(_f32(x_last)), _lib.ptr(out),
+                                        None if status is None else status.data_ptr(), n, k, n_next,
                                         sm_count(noise.device), _stream())
     _lib.check(code, "sw_decode_fwd_tcx")
     return out

@@ -259,6 +259,7 @@ class Generator(nn.Module):
         self.inference_precision = "fp16x2"
         self._pack_cache = None
         self._scene_cache = {}
+        self._fp16_status = None        # device int32[1]: set by the fp16-split kernels when an operand left fp16's range
 
     def optimizer_parameters(self):
         """Parameter order of train.py:379-380 (attention, feature_embedder, encoder, decoder)."""
@@ -280,8 +281,28 @@ class Generator(nn.Module):
                 packs["tcx"] = packing.pack_decoder_tcx(packs["enc"], packs["dec"])
                 packs["enc_tcx"] = packing.pack_encoder_tcx(packs["enc"])
                 packs["pool_tcx"] = packing.pack_pool_tcx(fe[2].weight)
+                # weights beyond fp16's range (|w| > 65 504 -> inf in the hi part) poison the split: raise the status word now
+                bad = torch.stack([torch.isinf(t).any() for t in (*packs["tcx"][:2], packs["enc_tcx"][0], packs["pool_tcx"])]).any()
+                self._status_word(packs["enc"].device).bitwise_or_(bad.to(torch.int32))
             self._pack_cache = (key, packs)
         return self._pack_cache[1]
+
+    def _status_word(self, device):
+        if self._fp16_status is None or self._fp16_status.device != device:
+            self._fp16_status = torch.zeros(1, dtype=torch.int32, device=device)
+        return self._fp16_status
+
+    def fp16_overflowed(self, reset=True):
+        """True when a tensor-core (fp16 hi/lo split) kernel saw a weight, state or activation outside fp16's exponent
+        range since the last reset: its output for those inputs is not trustworthy -- use precision="fp32" (the FFMA
+        kernels; trainer.test() does that automatically).  Synchronises."""
+        if self._fp16_status is None:
+            return False
+        flag = bool(self._fp16_status.item())
+        if reset and flag:
+            self._fp16_status.zero_()
+            self._pack_cache = None          # a weight-range flag is raised again when the packs are rebuilt
+        return flag
 
     def invalidate_packs(self):
         """Drop the packed-weight cache: call after anything that rewrites the parameters without advancing their
@@ -334,7 +355,8 @@ class Generator(nn.Module):
         if precision == "bf16":
             return ops.decode_tc(pk["tc_w16"], pk["tc_f32"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
         if precision == "fp16x2":
-            return ops.decode_tcx(*pk["tcx"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
+            return ops.decode_tcx(*pk["tcx"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out,
+                                  status=self._status_word(obsv_p.device))
         if precision != "fp32":
             raise ValueError("precision must be 'fp32', 'fp16x2' or 'bf16'")
         return ops.decode(pk["enc"], pk["dec"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)

@@ -503,6 +503,13 @@ class SocialWaysTrainer:
                     all_preds = self.generator.predict_k(obsv, noise, self.n_next, sub)      # [K, rows, T, 4]
                 m = ops.bestofk_metrics(all_preds.contiguous(), pred.contiguous(), self.ss)   # :587,602-607, per agent
                 sums = m.double().sum(dim=0).cpu().numpy()                                    # the call's one sync
+                if not (linear and not write_to_file) and self.generator.fp16_overflowed():
+                    # weights / states left fp16's exponent range: the fp16-split tensor-core kernels are not valid for this
+                    # checkpoint -- same call on the fp32 FFMA kernels (no silent inf / NaN)
+                    print("socialways_b200: operands outside fp16's range, test() falls back to the fp32 kernels")
+                    all_preds = self.generator.predict_k(obsv, noise, self.n_next, sub, precision="fp32")
+                    m = ops.bestofk_metrics(all_preds.contiguous(), pred.contiguous(), self.ss)
+                    sums = m.double().sum(dim=0).cpu().numpy()
                 if write_to_file:
                     ours = self.scale.denormalize(all_preds[:, :, :, :2].cpu().numpy())
                     o_np = self.scale.denormalize(obsv[:, :, :2].cpu().numpy())

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import golden_weights, load_golden
 from golden_data import synthetic_scenes
 
 pytestmark = pytest.mark.gpu
@@ -171,3 +172,92 @@ def test_pool_tcx_rejects_scenes_beyond_its_limit():
     z = torch.zeros(n, 64, device="cuda")
     with pytest.raises(SocialWaysCudaError):
         ops.pool_tcx(pk["pool"], pk["pool_tcx"], torch.zeros(n, 4, device="cuda"), z, torch.zeros(n, 65, device="cuda"), scenes)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fp16 hi/lo split hardening: trained checkpoints, inputs far from the normalised range, the overflow guard
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["train_toy_216.npz", "train_ragged.npz"])
+def test_fp16x2_on_trained_weights(case):
+    """Trained weights, not random init: for the toy case the post-training weights the unmodified reference produced
+    (tests/golden/train_toy_216.npz `w1.*`); for the obs 8 / pred 12 case the weights after the golden number of epochs of
+    this package's trainer from the golden start (test_gpu_training pins those to the reference's norms).  Tensor-core
+    K-sample inference vs the fp32 FFMA kernels and vs the CPU oracle."""
+    import socialways_b200 as sw
+    from golden_data import case_data
+    from oracle import socialways_oracle as so
+    from socialways_b200.trainer import SocialWaysTrainer
+    g = load_golden(case)
+    data = so.toy_samples(216, 6) if case == "train_toy_216.npz" else case_data(case)
+    if case == "train_toy_216.npz":
+        W = golden_weights(g, "w1.")
+    else:
+        tr = SocialWaysTrainer(data, batch_size=int(g["batch_size"]), use_social=True, n_unrolling_steps=int(g["unroll"]),
+                               weights=golden_weights(g, "w0."), fused_adam=True)
+        np.random.seed(int(g["seed"][0]))
+        torch.manual_seed(int(g["seed"][0]))
+        for _ in range(int(g["epochs"]) + 2):
+            tr.train_native(verbose=False)
+        W = {k: v.cpu() for k, v in tr.reference_weights().items()}
+    assert "encoder.embed.weight" in W
+    sc = so.IsoScale(data["obsvs"], data["preds"])
+    obsv = torch.from_numpy(sc.normalize(np.array(data["obsvs"], dtype=np.float32)))
+    n_next = data["preds"].shape[1]
+    gen = sw.Generator(use_social=True)
+    gen.load_state_dict({k: v for k, v in W.items() if not k.startswith("D.")})
+    gen = gen.cuda()
+    torch.manual_seed(3)
+    noise = torch.rand(5, obsv.shape[0], 32)
+    a = gen.predict_k(obsv.cuda(), noise.cuda(), n_next, data["batches"], precision="fp16x2")
+    b = gen.predict_k(obsv.cuda(), noise.cuda(), n_next, data["batches"], precision="fp32")
+    assert not gen.fp16_overflowed()
+    assert (a - b).abs().max().item() < 2e-5
+    ref = torch.stack([so.predict(W, obsv, noise[k], n_next, data["batches"], True, "closed") for k in range(5)])
+    assert (a.cpu() - ref).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("scale", [1e3, 1e-4])
+def test_fp16x2_on_inputs_far_from_the_normalised_range(scale):
+    """Coordinates 1 000 x larger (metres instead of Scale-normalised) or 10 000 x smaller: positions are integrated in
+    fp32 and enter the split as one K block, so the tensor-core path must track the FFMA path relative to the magnitude."""
+    import socialways_b200 as sw
+    from golden_data import synthetic_scenes
+    torch.manual_seed(1)
+    gen = sw.Generator(use_social=True).cuda()
+    d = synthetic_scenes([8, 3, 1, 6, 8, 8, 2, 7], seed=4)
+    obsv = (torch.from_numpy(d["obsvs"]) * 0.05 * scale).cuda()
+    noise = torch.rand(4, obsv.shape[0], 32).cuda()
+    a = gen.predict_k(obsv, noise, 12, d["batches"], precision="fp16x2")
+    b = gen.predict_k(obsv, noise, 12, d["batches"], precision="fp32")
+    assert not gen.fp16_overflowed()
+    tol = 2e-5 * max(1.0, b.abs().max().item())
+    assert torch.isfinite(a).all() and (a - b).abs().max().item() < tol
+
+
+def test_fp16_overflow_is_flagged_and_test_falls_back_to_fp32(capsys):
+    """An operand beyond fp16's range (here: a layer-1 bias that pushes a1 past 65 504) must never pass silently: the
+    status word is raised, and SocialWaysTrainer.test() reruns on the fp32 kernels and reports the fp32 numbers."""
+    import socialways_b200 as sw
+    from oracle import socialways_oracle as so
+    from socialways_b200.trainer import SocialWaysTrainer
+    W = so.init_weights(seed=2, n_next=2)
+    W["decoder.fc1.0.bias"] = W["decoder.fc1.0.bias"].clone()
+    W["decoder.fc1.0.bias"][:8] = 3.0e5
+    tr = SocialWaysTrainer(so.toy_samples(216, 6), batch_size=64, use_social=True, weights=W)
+    torch.manual_seed(0)
+    state = torch.get_rng_state()
+    tr.generator.inference_precision = "fp16x2"
+    m_tc = tr.test(5, verbose=False)
+    assert "falls back to the fp32 kernels" in capsys.readouterr().out
+    torch.set_rng_state(state)
+    tr.generator.inference_precision = "fp32"
+    m_32 = tr.test(5, verbose=False)
+    assert all(np.isfinite(v) for v in m_32.values())
+    assert all(abs(m_tc[k] - m_32[k]) <= 1e-6 * max(1.0, abs(m_32[k])) for k in m_32)
+    # weights beyond fp16's range are caught when the operand packs are built
+    gen = sw.Generator(use_social=True)
+    with torch.no_grad():
+        gen.encoder.lstm.weight_hh_l0[0, 0] = 1.0e6
+    gen = gen.cuda()
+    gen.packs()
+    assert gen.fp16_overflowed()
