@@ -85,11 +85,14 @@ int sw_pool_fwd(const float* pool_pack, const float* x_last, const float* h, con
                 int n_agents, int max_scene, void* stream);
 /* Same contract, inference only (no attention record), with layer 2 of the pair MLP (32 -> 64, 93 % of the pair's
  * arithmetic) on the tcgen05 tensor cores: 128 ordered pairs per MMA tile, fp16 hi|lo split operands, fp32 accumulate in
- * TMEM (~1e-6 of sw_pool_fwd).  pool_w16 = packing.pack_pool_tcx (fp16 [4096]).  Scenes of up to
- * sw_pool_tcx_max_scene() agents; larger scenes use sw_pool_fwd. */
+ * TMEM (~1e-6 of sw_pool_fwd).  pool_w16 = packing.pack_pool_tcx (fp16 [4096]).
+ * units [n_units][2] = (first row, rows <= 64): work units of consecutive rows whose span (all agents of the scenes they touch)
+ * is at most max_unit_span agents and whose ordered pairs number at most max_unit_pairs -- whole scenes packed up to 64 rows,
+ * scenes above 64 agents cut into units of <= 32 / 16 rows (ops.SceneIndex.pool_units).  units == NULL: 64 consecutive rows per
+ * unit, scenes of up to 64 agents.  Scenes of up to sw_pool_tcx_max_scene() agents; larger scenes use sw_pool_fwd. */
 int sw_pool_fwd_tcx(const float* pool_pack, const void* pool_w16, const float* x_last, const float* h, const float* ub,
-                    const int* scene_offsets, const int* agent_scene, float* pooled, int n_agents, int max_scene,
-                    void* stream);
+                    const int* scene_offsets, const int* agent_scene, float* pooled, const int* units, int n_units,
+                    int max_unit_span, int max_unit_pairs, int n_agents, int max_scene, void* stream);
 int sw_pool_tcx_max_scene(void);
 
 /* Backward of sw_pool_fwd.  Replaces autograd through AttentionPooling.forward / EmbedSocialFeatures.fc

@@ -27,7 +27,7 @@ _PROTOTYPES = {
     "sw_lstm_seq_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "sw_pool_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "sw_pool_bwd": (_I, [_P] * 17 + [_I, _I, _P]),
-    "sw_pool_fwd_tcx": (_I, [_P] * 8 + [_I, _I, _P]),
+    "sw_pool_fwd_tcx": (_I, [_P] * 9 + [_I, _I, _I, _I, _I, _P]),
     "sw_pool_tcx_max_scene": (_I, []),
     "sw_decode_fwd": (_I, [_P] * 13 + [_I, _I, _I, _I, _P]),
     "sw_decode_bwd": (_I, [_P] * 16 + [_I, _I, _I, _I, _P]),

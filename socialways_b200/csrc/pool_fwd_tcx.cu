@@ -12,8 +12,12 @@
 // sigma_ij = relu(a2_ij + b2) . u_j + beta_j read straight from the accumulator's TMEM lane, the -1000 self mask,
 // the per-row softmax and the weighted sum of the raw h.
 //
-// Work unit = 64 consecutive agent rows; the agents of every scene they touch are staged in shared memory exactly as in
-// pool_fwd.cu; the unit's ordered pairs are enumerated row-major ([row][j]) and processed 128 at a time.
+// Work unit = a run of consecutive agent rows from a host-built table (ops.SceneIndex.pool_units): whole scenes packed up to
+// 64 rows while scenes are small, <= 32 (16) rows of ONE scene when a scene has more than 64 agents -- so a unit's span (the
+// agents its rows attend to) is the unit itself or that one scene.  x and (u | beta) of the span are staged in shared memory;
+// h too when it fits (scenes up to ~256 agents), else the weighted sum reads it through L1/L2 (every row of the unit reads
+// the same scene).  The unit's ordered pairs are enumerated row-major ([row][j]) and processed 128 at a time.  Without a
+// table (NULL) units are 64 consecutive rows, scenes <= 64 agents (the round-1 scheme).
 #include <cuda_fp16.h>
 
 #include "sw_common.cuh"
@@ -27,7 +31,8 @@ constexpr int PT_THREADS = 128;      // thread p = pair p of the current tile = 
 #endif
 constexpr int PT_ROWS = SW_PT_ROWS;
 constexpr int PT_LD = 65;
-constexpr int PT_A_MAX = 64;         // largest scene this kernel takes (larger ones go to pool_fwd_kernel)
+constexpr int PT_A_MAX = 512;        // largest scene this kernel takes (larger ones go to pool_fwd_kernel)
+constexpr int PT_A_LEGACY = 64;      // largest scene of the table-less unit scheme
 constexpr int PT_PP_P1 = 0, PT_PP_B2 = 128 + 64 * 32;      // offsets inside pool_pack (pool_fwd.cu)
 
 __device__ __forceinline__ void split2_pt(float a, float b, uint32_t& hi, uint32_t& lo) {
@@ -43,6 +48,7 @@ __global__ void __launch_bounds__(PT_THREADS)
 pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restrict__ w2_16 /* canonical [4][64][8] hi | lo */,
                     const float* __restrict__ x_last, const float* __restrict__ h, const float* __restrict__ ub,
                     const int* __restrict__ scene_offsets, const int* __restrict__ agent_scene, float* __restrict__ pooled,
+                    const int* __restrict__ units /*[n_units][2] = (first row, rows) or null*/, int stage_h,
                     int n_agents, int span_cap, int pair_cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __half* w2 = reinterpret_cast<__half*>(smem_raw);                       // [2][2048]           8 KB
@@ -50,8 +56,8 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
     float* p1 = reinterpret_cast<float*>(a1s + 2 * 4096);                   // [32][4]
     float* b2 = p1 + 128;                                                   // [64]
     float* sx = b2 + 64;                                                    // [span][4]
-    float* sh = sx + span_cap * 4;                                          // [span][64] (read lane <-> column only)
-    float* su_raw = sh + span_cap * SW_H;                                   // [span][65] (col 64 = beta) + 4 floats of slack
+    float* sh = sx + span_cap * 4;                                          // [span][64] (read lane <-> column only), if staged
+    float* su_raw = sh + (stage_h ? span_cap * SW_H : 0);                   // [span][65] (col 64 = beta) + 4 floats of slack
     float* sig = su_raw + span_cap * PT_LD + 4;                             // [pair_cap]
     int* off = reinterpret_cast<int*>(sig + pair_cap);                      // [PT_ROWS + 1] pair offsets of the unit's rows
     int* sstart = off + PT_ROWS + 1;                                        // [PT_ROWS] first agent of the row's scene
@@ -60,8 +66,8 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool leader = lane == 0;
 
-    const int row0 = blockIdx.x * PT_ROWS;
-    const int row1 = min(row0 + PT_ROWS, n_agents);
+    const int row0 = units ? units[2 * blockIdx.x] : blockIdx.x * PT_ROWS;
+    const int row1 = units ? row0 + units[2 * blockIdx.x + 1] : min(row0 + PT_ROWS, n_agents);
     const int R = row1 - row0;
     const int span0 = scene_offsets[agent_scene[row0]];
     const int span1 = scene_offsets[agent_scene[row1 - 1] + 1];
@@ -73,8 +79,9 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
     if (tid < 64) b2[tid] = __ldg(pool_pack + PT_PP_B2 + tid);
     for (int i = tid; i < span; i += PT_THREADS)
         *reinterpret_cast<float4*>(sx + i * 4) = __ldg(reinterpret_cast<const float4*>(x_last) + span0 + i);
-    for (int i = tid; i < span * 16; i += PT_THREADS)                       // flat copy: same [.][64] layout on both sides
-        reinterpret_cast<float4*>(sh)[i] = __ldg(reinterpret_cast<const float4*>(h) + (size_t)span0 * 16 + i);
+    if (stage_h)
+        for (int i = tid; i < span * 16; i += PT_THREADS)                   // flat copy: same [.][64] layout on both sides
+            reinterpret_cast<float4*>(sh)[i] = __ldg(reinterpret_cast<const float4*>(h) + (size_t)span0 * 16 + i);
     // (u | beta) rows keep the global [.][65] layout; the copy is flat too.  The shared copy starts at the same offset
     // modulo 4 floats as the global one, so the 16-byte aligned body moves as float4 on both sides.
     const float* ug = ub + (size_t)span0 * 65;
@@ -213,7 +220,7 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
             __syncwarp(gmask);
             for (int jj = gl; jj < A; jj += G) s[jj] = s[jj] / sum;
             __syncwarp(gmask);
-            const float* hp = sh + (size_t)(sstart[r] - span0) * SW_H + gl;
+            const float* hp = (stage_h ? sh + (size_t)(sstart[r] - span0) * SW_H : h + (size_t)sstart[r] * SW_H) + gl;
             float acc[SW_H / G];
 #pragma unroll
             for (int k = 0; k < SW_H / G; ++k) acc[k] = 0.0f;
@@ -234,28 +241,37 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
 }  // namespace sw
 
 // Same contract as sw_pool_fwd (inference: no attention record) plus the fp16 hi|lo operand pack of layer 2
-// (packing.pack_pool_tcx: fc.2.weight [64][32] as canonical [4][64][8] hi block, then lo block = 4096 halves).
-// Takes scenes of up to sw_pool_tcx_max_scene() agents; the caller uses sw_pool_fwd beyond that.
+// (packing.pack_pool_tcx: fc.2.weight [64][32] as canonical [4][64][8] hi block, then lo block = 4096 halves) and the work-unit
+// table: units [n_units][2] = (first row, rows <= 64), every unit's rows consecutive, its span (all agents of the scenes it
+// touches) <= max_unit_span agents and its ordered pairs <= max_unit_pairs (ops.SceneIndex.pool_units builds it: whole scenes
+// packed to <= 64 rows, scenes above 64 agents cut into units of <= 32 / 16 rows).  units == NULL: 64 consecutive rows per
+// unit, scenes of up to 64 agents.  Takes scenes of up to sw_pool_tcx_max_scene() agents; the caller uses sw_pool_fwd beyond.
 extern "C" int sw_pool_tcx_max_scene(void) { return sw::PT_A_MAX; }
 
 extern "C" int sw_pool_fwd_tcx(const float* pool_pack, const void* pool_w16, const float* x_last, const float* h, const float* ub,
-                               const int* scene_offsets, const int* agent_scene, float* pooled, int n_agents, int max_scene,
-                               void* stream) {
+                               const int* scene_offsets, const int* agent_scene, float* pooled, const int* units, int n_units,
+                               int max_unit_span, int max_unit_pairs, int n_agents, int max_scene, void* stream) {
     if (!pool_pack || !pool_w16 || !x_last || !h || !ub || !scene_offsets || !agent_scene || !pooled) return SW_ERR_ARG;
     if (n_agents <= 0 || max_scene <= 0) return SW_ERR_ARG;
-    if (max_scene > sw::PT_A_MAX) return SW_ERR_UNSUPPORTED;
-    const int span_cap = sw::PT_ROWS + 2 * (max_scene - 1);
-    const int pair_cap = (sw::PT_ROWS * max_scene + 3) & ~3;
-    const size_t smem = 2 * 2048 * 2 + 2 * 4096 * 2 + (size_t)(128 + 64 + span_cap * (4 + SW_H + sw::PT_LD) + 4 + pair_cap) * 4 +
-                        (size_t)(2 * sw::PT_ROWS + 2) * 4 + 16;
-    const int grid = (n_agents + sw::PT_ROWS - 1) / sw::PT_ROWS;
+    if (max_scene > sw::PT_A_MAX || (!units && max_scene > sw::PT_A_LEGACY)) return SW_ERR_UNSUPPORTED;
+    if (units && (n_units <= 0 || max_unit_span <= 0 || max_unit_pairs <= 0)) return SW_ERR_ARG;
+    // multiple of 4: keeps every shared-memory array behind the (u | beta) rows (65 floats each) 16-byte aligned, the mbarrier 8
+    const int span_cap = units ? (max_unit_span + 3) & ~3 : sw::PT_ROWS + 2 * (max_scene - 1);
+    const int pair_cap = ((units ? max_unit_pairs : sw::PT_ROWS * max_scene) + 3) & ~3;
+    const size_t fixed = 2 * 2048 * 2 + 2 * 4096 * 2 + (size_t)(128 + 64 + 4) * 4 + (size_t)(2 * sw::PT_ROWS + 2) * 4 + 16;
+    const size_t no_h = fixed + (size_t)(span_cap * (4 + sw::PT_LD) + pair_cap) * 4;
+    const size_t with_h = no_h + (size_t)span_cap * SW_H * 4;
+    const int stage_h = with_h <= 200 * 1024 ? 1 : 0;               // h of the span in shared memory when it fits
+    const size_t smem = stage_h ? with_h : no_h;
+    if (smem > 227 * 1024) return SW_ERR_UNSUPPORTED;
+    const int grid = units ? n_units : (n_agents + sw::PT_ROWS - 1) / sw::PT_ROWS;
     cudaStream_t st = (cudaStream_t)stream;
 #define SW_POOL_TCX_LAUNCH(GG)                                                                                              \
     do {                                                                                                                    \
         SW_SET_MAX_SMEM(sw::pool_fwd_tcx_kernel<GG>, (int)smem);                                                            \
         sw::pool_fwd_tcx_kernel<GG><<<grid, sw::PT_THREADS, smem, st>>>(pool_pack, (const __half*)pool_w16, x_last, h, ub,  \
-                                                                        scene_offsets, agent_scene, pooled, n_agents, span_cap, \
-                                                                        pair_cap);                                           \
+                                                                        scene_offsets, agent_scene, pooled, units, stage_h, \
+                                                                        n_agents, span_cap, pair_cap);                      \
     } while (0)
     if (max_scene <= 8) SW_POOL_TCX_LAUNCH(8);
     else if (max_scene <= 16) SW_POOL_TCX_LAUNCH(16);

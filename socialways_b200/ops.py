@@ -56,7 +56,39 @@ class SceneIndex:
         self.n_pairs = int(pairs[-1])
         self._pairs_np = pairs
         self._pair_offsets = None
+        self._pool_units = None
         self.device = device
+
+    def pool_units(self):
+        """Work units of sw_pool_fwd_tcx: (device int32 [n_units, 2] = (first row, rows), max span, max ordered pairs).
+        Whole scenes are packed into units of up to 64 rows; a scene with more than 64 agents is cut into units of up to
+        32 rows (16 beyond 256 agents) of that scene alone, so a unit's span is the unit itself or one scene."""
+        if self._pool_units is None:
+            big_rows = 32 if self.max_scene <= 256 else 16
+            units, span, pairs = [], 1, 1
+            start, rows, npairs = 0, 0, 0
+            offs = np.concatenate([[0], np.cumsum(self.sizes)])
+            for s_i, a in enumerate(self.sizes.tolist()):
+                if a > 64:
+                    if rows:
+                        units.append((start, rows)); span, pairs = max(span, rows), max(pairs, npairs)
+                        rows, npairs = 0, 0
+                    for r0 in range(0, a, big_rows):
+                        r = min(big_rows, a - r0)
+                        units.append((int(offs[s_i]) + r0, r)); span, pairs = max(span, a), max(pairs, r * a)
+                    start = int(offs[s_i + 1])
+                    continue
+                if rows + a > 64:
+                    units.append((start, rows)); span, pairs = max(span, rows), max(pairs, npairs)
+                    start, rows, npairs = int(offs[s_i]), 0, 0
+                if rows == 0:
+                    start = int(offs[s_i])
+                rows += a
+                npairs += a * a
+            if rows:
+                units.append((start, rows)); span, pairs = max(span, rows), max(pairs, npairs)
+            self._pool_units = (torch.tensor(units, dtype=torch.int32, device=self.device).contiguous(), span, pairs)
+        return self._pool_units
 
     @property
     def pair_offsets(self):
@@ -143,9 +175,11 @@ def pool_tcx(pool_pack, pool_w16, x_last, h, ub, scenes):
     if pool_w16.dtype != torch.float16 or not pool_w16.is_contiguous() or pool_w16.numel() != 4096:
         raise ValueError("pool_tcx: pool_w16 must be the contiguous fp16 [4096] pack of packing.pack_pool_tcx")
     pooled = torch.empty(n, H, device=h.device)
+    units, span, pairs = scenes.pool_units()
     code = _lib.lib().sw_pool_fwd_tcx(_lib.ptr(_f32(pool_pack)), pool_w16.data_ptr(), _lib.ptr(_f32(x_last)), _lib.ptr(_f32(h)),
                                       _lib.ptr(_f32(ub)), _lib.ptr(scenes.offsets), _lib.ptr(scenes.agent_scene),
-                                      _lib.ptr(pooled), n, scenes.max_scene, _stream())
+                                      _lib.ptr(pooled), units.data_ptr(), units.shape[0], span, pairs, n, scenes.max_scene,
+                                      _stream())
     _lib.check(code, "sw_pool_fwd_tcx")
     return pooled
 

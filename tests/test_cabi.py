@@ -80,8 +80,8 @@ def test_null_pointers_are_rejected_by_the_new_entry_points():
     assert lib.sw_lsap_solve(None, 4, 1, None, None, None) == -1
     assert lib.sw_adam_flat(None, None, None, None, None, 4, 1e-3, 0.9, 0.999, 1e-8, 148, None) == -1
     assert lib.sw_allreduce_adam(None, 0, 2, 4, 32, None, None, None, None, None, 1e-3, 0.9, 0.999, 1e-8, None) == -1
-    assert lib.sw_pool_fwd_tcx(None, None, None, None, None, None, None, None, 1, 1, None) == -1
-    assert lib.sw_pool_tcx_max_scene() == 64 and lib.sw_lsap_smem_bytes(20) == 20 * 42
+    assert lib.sw_pool_fwd_tcx(None, None, None, None, None, None, None, None, None, 0, 0, 0, 1, 1, None) == -1
+    assert lib.sw_pool_tcx_max_scene() == 512 and lib.sw_lsap_smem_bytes(20) == 20 * 42
 
 
 def test_training_step_entry_points_reject_bad_arguments():

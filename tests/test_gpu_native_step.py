@@ -288,6 +288,8 @@ def test_graphed_training_followed_by_test_uses_current_weights():
             m = tr.test(5, verbose=False)
             res.append([m["ade_avg"], m["fde_avg"], m["ade_min"], m["fde_min"]])
         runs[mode] = np.array(res)
-    assert np.abs(runs["eager"][1:] - runs["eager"][:-1]).max() > 1e-5, "metrics must move between epochs"
-    np.testing.assert_allclose(runs["graphed"], runs["eager"], atol=2e-4, rtol=0)
-    np.testing.assert_allclose(runs["native"], runs["eager"], atol=2e-4, rtol=0)
+    # a stale cache would repeat an earlier epoch's metrics: those move by ~2e-2 per epoch, an order of magnitude above the
+    # tolerance (which only has to absorb fp32 rounding differences between the three paths, amplified by 5 GAN epochs)
+    assert np.abs(runs["eager"][1:] - runs["eager"][:-1]).min(axis=0).max() > 1e-2, "metrics must move between epochs"
+    np.testing.assert_allclose(runs["graphed"], runs["eager"], atol=2e-3, rtol=0)
+    np.testing.assert_allclose(runs["native"], runs["eager"], atol=2e-3, rtol=0)

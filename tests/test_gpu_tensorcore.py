@@ -134,7 +134,8 @@ def test_config3_zara_shape_bf16_fast_mode():
     assert ((m - ref).abs() / ref).max().item() < 0.02
 
 
-@pytest.mark.parametrize("sizes", [[8] * 40, [1, 2, 6, 8, 5, 3, 1, 1, 9], [32, 31, 33, 32, 7], [64, 1, 63, 20], [3] * 100 + [64]])
+@pytest.mark.parametrize("sizes", [[8] * 40, [1, 2, 6, 8, 5, 3, 1, 1, 9], [32, 31, 33, 32, 7], [64, 1, 63, 20], [3] * 100 + [64],
+                                   [65, 3, 100, 1, 8, 8, 70], [256, 5, 256], [400, 2, 129], [512, 7]])
 def test_pool_tcx_matches_ffma_pool_and_oracle(sizes):
     """Pooling kernel with layer 2 on tcgen05 (fp16 hi/lo split) vs the FFMA kernel and the fp32 oracle (closed form)."""
     import socialways_b200 as sw
@@ -151,7 +152,8 @@ def test_pool_tcx_matches_ffma_pool_and_oracle(sizes):
     pk = gen.packs()
     enc = ops.lstm_seq(pk["enc"], obsv.cuda(), want_x_last=True)
     scenes = gen.scene_index(data["batches"], n, torch.device("cuda"))
-    ub = torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])
+    ub = ops.rows_linear(enc["h"], pk["pool_m"], pk["pool_m0"])
+    assert (ub - torch.addmm(pk["pool_m0"], enc["h"], pk["pool_m"])).abs().max().item() < 1e-5
     ref = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
     got = ops.pool_tcx(pk["pool"], pk["pool_tcx"], enc["x_last"], enc["h"], ub, scenes)
     err = (got - ref).abs().max().item()
