@@ -1,7 +1,8 @@
-"""Small invocation of every kernel added or changed in this round, for compute-sanitizer:
+"""Small invocation of every kernel added or changed in rounds 1-2, for compute-sanitizer:
     compute-sanitizer --tool memcheck python scripts/sanitize_target.py
-tcx decode (coalesced prologue, x-feedback K block), tensor-core pooling, tensor-core encoder, statistics kernels
-(1-NN, EMD cost, assignment), flat Adam."""
+tcx decode (TMA weights / noise tile, x-feedback K block, range guard), tensor-core pooling (unit table, scenes > 64),
+tensor-core encoder, device noise, statistics kernels (1-NN, EMD cost, assignment), flat Adam, and one native training
+iteration (pack kernels, fused D heads, tcgen05 + FFMA weight-gradient contractions, rows_linear, stats)."""
 import os, sys
 import numpy as np
 import torch
@@ -13,13 +14,22 @@ from socialways_b200 import statistics as st
 from socialways_b200.fused_optim import FlatAdam
 from golden_data import synthetic_scenes
 
-data = synthetic_scenes([8, 1, 5, 33, 2, 64, 7, 3], seed=0)
+data = synthetic_scenes([8, 1, 5, 33, 2, 64, 7, 3, 70, 130], seed=0)
 obsv = torch.from_numpy(data["obsvs"]).cuda() * 0.1
 n = obsv.shape[0]
 gen = sw.Generator(use_social=True).cuda().requires_grad_(False)
 noise = torch.rand(3, n, 32, device="cuda")
 out = gen.predict_k(obsv, noise, 12, data["batches"], precision="fp16x2")
 assert torch.isfinite(out).all()
+out2 = gen.predict_k(obsv, None, 12, data["batches"], precision="fp16x2", seed=3, k=2)
+assert torch.isfinite(out2).all() and not gen.fp16_overflowed()
+from socialways_b200.trainer import SocialWaysTrainer
+small = synthetic_scenes([3, 8, 1, 5, 6, 2, 7, 4, 9, 3, 2, 6], seed=1)
+for tc in (True, False):
+    tr = SocialWaysTrainer(small, batch_size=32, use_social=True, fused_adam=True)
+    tr.native_tensor_cores = "force" if tc else False
+    np.random.seed(0); torch.manual_seed(0)
+    print("native epoch", tc, tr.train_native(verbose=False, use_graph=False))
 rng = np.random.RandomState(0)
 reals = rng.normal(0, 1, size=(9, 7, 14, 2)).astype(np.float32)
 fakes = (reals[::-1] + rng.normal(0, 0.3, size=reals.shape)).astype(np.float32)

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--epochs", type=int, default=2)
     ap.add_argument("--graph", action="store_true")
     ap.add_argument("--shape", default="toy", choices=["toy", "eth"])
+    ap.add_argument("--force-tc", action="store_true", help="tcgen05 contractions even for tiny problems")
     ap.add_argument("--ffma-contract", action="store_true", help="weight-gradient contractions on the FFMA kernel instead of tcgen05")
     args = ap.parse_args()
     from bench import toy_dataset
@@ -32,7 +33,7 @@ def main():
         from golden_data import synthetic_scenes
         data = synthetic_scenes([8] * (args.n // 8), seed=1)
     tr = SocialWaysTrainer(data, batch_size=args.batch, use_social=True, n_unrolling_steps=1, fused_adam=True)
-    tr.native_tensor_cores = not args.ffma_contract
+    tr.native_tensor_cores = False if args.ffma_contract else ("force" if args.force_tc else True)
     iters = sum(1 for _ in tr._minibatches())
     np.random.seed(0)
     torch.manual_seed(0)

@@ -19,6 +19,7 @@
 // the same scene).  The unit's ordered pairs are enumerated row-major ([row][j]) and processed 128 at a time.  Without a
 // table (NULL) units are 64 consecutive rows, scenes <= 64 agents (the round-1 scheme).
 #include <cuda_fp16.h>
+#include <cstdlib>
 
 #include "sw_common.cuh"
 #include "sw_umma.cuh"
@@ -261,7 +262,8 @@ extern "C" int sw_pool_fwd_tcx(const float* pool_pack, const void* pool_w16, con
     const size_t fixed = 2 * 2048 * 2 + 2 * 4096 * 2 + (size_t)(128 + 64 + 4) * 4 + (size_t)(2 * sw::PT_ROWS + 2) * 4 + 16;
     const size_t no_h = fixed + (size_t)(span_cap * (4 + sw::PT_LD) + pair_cap) * 4;
     const size_t with_h = no_h + (size_t)span_cap * SW_H * 4;
-    const int stage_h = with_h <= 200 * 1024 ? 1 : 0;               // h of the span in shared memory when it fits
+    const char* knob = getenv("SW_POOL_STAGE_H");                   // A/B knob (profiles/): default = measured best
+    const int stage_h = knob ? (atoi(knob) != 0 && with_h <= 200 * 1024) : (with_h <= 200 * 1024 ? 1 : 0);
     const size_t smem = stage_h ? with_h : no_h;
     if (smem > 227 * 1024) return SW_ERR_UNSUPPORTED;
     const int grid = units ? n_units : (n_agents + sw::PT_ROWS - 1) / sw::PT_ROWS;

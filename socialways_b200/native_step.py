@@ -68,8 +68,14 @@ def _job(a, b, K, N, n_images, segs, a_stride=0, b_stride=0, a_k0=0, b_n0=0, a_k
 class ContractPlan:
     """A job list + its workspace, ready to launch (sw_contract_tc, or the FFMA sw_contract)."""
 
+    # below this many 32-row images in the largest job the launch is latency-bound and the FFMA kernel (3 small CTAs per SM,
+    # no TMEM set-up) is quicker: measured crossover between 16 images (batch 256: 0.40 vs 0.43 ms per iteration) and 256
+    # images (batch 4 096: 0.62 vs 0.56 ms), profiles/r2_train_probe.txt
+    TC_MIN_IMAGES = 96
+
     def __init__(self, jobs, device, tensor_cores=True):
-        self.n, self.tc = len(jobs), bool(tensor_cores)
+        self.n = len(jobs)
+        self.tc = tensor_cores == "force" or (bool(tensor_cores) and max(j.n_images for j in jobs) >= self.TC_MIN_IMAGES)
         self.jobs = (ContractJob * self.n)(*jobs)
         ws, nc = ctypes.c_longlong(), ctypes.c_int()
         _lib.check(_lib.lib().sw_contract_plan(self.jobs, self.n, sm_count(device), 1 if self.tc else 0, ctypes.byref(ws),

@@ -83,7 +83,8 @@ class SocialWaysTrainer:
             self.predictor_optimizer = opt.Adam(self.generator.optimizer_parameters(), lr=lr_g, betas=(0.9, 0.999), **extra)
             self.D_optimizer = opt.Adam(self.D.parameters(), lr=lr_d, betas=(0.9, 0.999), **extra)
         self.mse_loss = nn.MSELoss()
-        # weight-gradient contractions of train_native(): tcgen05 (tf32-split operands) or the FFMA reference kernel
+        # weight-gradient contractions of train_native(): True = tcgen05 (tf32-split operands) when the problem is large enough to
+        # pay for it, else the FFMA kernel; "force" = always tcgen05; False = always FFMA
         self.native_tensor_cores = True
         self.epoch = 1
         self.loss_log = []

@@ -106,7 +106,7 @@ def _trainer(data, social=True, unroll=1, weights=None, n_next=12, batch=64, ten
     from socialways_b200.trainer import SocialWaysTrainer
     W = weights if weights is not None else so.init_weights(seed=4, n_next=n_next)
     tr = SocialWaysTrainer(data, batch_size=batch, use_social=social, n_unrolling_steps=unroll, weights=W, fused_adam=True, **kw)
-    tr.native_tensor_cores = tensor_cores
+    tr.native_tensor_cores = "force" if tensor_cores else False      # small test batches: force the tcgen05 kernel
     return tr
 
 
@@ -238,6 +238,7 @@ def test_native_training_epochs_vs_reference_golden(case, social, graph, capsys)
     seed = int(g["seed"][0])
     tr = SocialWaysTrainer(data, batch_size=int(g["batch_size"]), use_social=social, n_unrolling_steps=int(g["unroll"]),
                            weights=golden_weights(g, "w0."), fused_adam=True)
+    tr.native_tensor_cores = "force" if graph else True      # both contraction kernels see the golden runs
     np.random.seed(seed)
     torch.manual_seed(seed)
     for ep in range(1, int(g["epochs"]) + 1):
