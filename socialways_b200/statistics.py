@@ -119,7 +119,8 @@ def dump_samples(path, k, n_past, n_next):
 def calc_and_store_stats(main_dir, real_samples, n_past, n_next, stats_file=None, device=None, verbose=True):
     """calc_statistics.py:70-120: walk `main_dir/<epoch>/*.npz`, average the 1-NN accuracy and the EMD over the files of
     each epoch, store the two lists.  `real_samples` is the [K, nPed, n_past+n_next, 2] array the reference builds at
-    :200-208.  All files of an epoch with the same pedestrian count are evaluated in one batch of launches."""
+    :200-208.  Every pedestrian of a file is one problem of ONE launch per statistic (distance matrices, 1-NN counts, assignment);
+    the files of an epoch are evaluated one after another, with one host read per statistic and file."""
     stats_1nn, stats_wst = {}, {}
     k = real_samples.shape[0]
     for dirpath, dirnames, filenames in sorted(os.walk(main_dir)):

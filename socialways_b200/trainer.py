@@ -383,10 +383,27 @@ class SocialWaysTrainer:
             self._pin = {}
         stats_acc = torch.zeros(8, device=dev, dtype=torch.float64)
         n_iter = 0
-        for g_lo, g_hi, sub in self._minibatches():
+        if not hasattr(self, "_native_plan"):
+            # the mini-batch grouping, this rank's shard of every mini-batch and its launch sequence are the same every
+            # epoch: walk the scene table once (the reference re-walks it in Python every epoch -- ~1 us per scene, more than
+            # the GPU needs for the whole epoch at large batches)
+            self._native_plan = []
+            for g_lo, g_hi, sub in self._minibatches():
+                lo, hi = g_lo, g_hi
+                if self.world_size > 1:       # this rank's contiguous block of scenes
+                    s_lo, s_hi, sub = swdist.shard_scenes(sub, self.world_size, self.rank)
+                    lo, hi = g_lo + s_lo, g_lo + s_hi
+                ent = None
+                if hi > lo:
+                    key = (g_hi - g_lo, hi - lo, lo - g_lo, sub.tobytes())
+                    ent = self._native_steps.get(key)
+                    if ent is None:
+                        step = NativeStep(self, self._native_packs, hi - lo, self.generator.scene_index(sub, hi - lo, dev), g_hi - g_lo)
+                        ent = self._native_steps[key] = dict(step=step, graph=None, seen=0)
+                self._native_plan.append((g_lo, g_hi, lo, hi, ent))
+        for g_lo, g_hi, lo, hi, ent in self._native_plan:
             self._native_iteration = getattr(self, "_native_iteration", 0) + 1
             global_bs = g_hi - g_lo
-            lo, hi = g_lo, g_hi
             # train.py:471-473: two numpy scalars, then the noise of the GLOBAL mini-batch from torch's CPU generator
             t01 = (float(np.random.uniform(0, 0.1)), float(np.random.uniform(0.9, 1.0)))
             pin = None
@@ -398,19 +415,10 @@ class SocialWaysTrainer:
                 pin = pins[n_iter & 1]
                 pin["ev"].synchronize()                       # the upload that last read this pinned buffer has finished
                 torch.rand(global_bs, self.noise_len, out=pin["noise"])     # same stream as torch.rand(bs, noise_len)
-            if self.world_size > 1:       # this rank's contiguous block of scenes
-                s_lo, s_hi, sub = swdist.shard_scenes(sub, self.world_size, self.rank)
-                if s_hi <= s_lo:          # more ranks than scenes: contribute zero gradients to the three all-reduces
-                    self._native_empty_iteration()
-                    n_iter += 1
-                    continue
-                lo, hi = g_lo + s_lo, g_lo + s_hi
-            bs = hi - lo
-            key = (global_bs, bs, lo - g_lo, sub.tobytes())
-            ent = self._native_steps.get(key)
-            if ent is None:
-                step = NativeStep(self, self._native_packs, bs, self.generator.scene_index(sub, bs, dev), global_bs)
-                ent = self._native_steps[key] = dict(step=step, graph=None, seen=0)
+            if ent is None:               # more ranks than scenes: contribute zero gradients to the three all-reduces
+                self._native_empty_iteration()
+                n_iter += 1
+                continue
             step = ent["step"]
             step.obsv.copy_(self.dataset_obsv[lo:hi])
             step.pred.copy_(self.dataset_pred[lo:hi])

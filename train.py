@@ -15,6 +15,11 @@ Flags ADDED here (the reference hard-codes these as module constants / paths, tr
   --fused-adam      one kernel per optimiser step on flat buffers (fused_optim.FlatAdam); under torchrun it also carries
                     the gradient all-reduce of the sharded step over NVLink peer memory, which is what lets --cuda-graph
                     capture the multi-GPU iteration
+  --native          the iteration as ~30 launches of this library's own kernels replayed from one CUDA graph per mini-batch
+                    shape (no autograd / cuBLAS / ATen; implies --fused-adam): 0.4 ms per iteration at batch 256 on the toy set
+  --device-noise S  (with --native) draw the per-iteration latent noise on the GPU (Philox, seed S) instead of torch.rand
+                    on the CPU: same distribution, different stream -- the host generator otherwise bounds large batches
+--hidden-size: the sm_100a kernels are built for the default 64 (every BASELINE configuration); other values raise.
 Under `torchrun --nproc-per-node N train.py ...` the scenes of every mini-batch are sharded over the N GPUs.
 All arithmetic runs in the sm_100a kernels of socialways_b200 (no CPU fallback).
 """
@@ -41,7 +46,8 @@ parser.add_argument('--g-learning-rate', '--g-lr', type=float, default=1E-4, met
 parser.add_argument('--unrolling-steps', '--unroll', type=int, default=1, metavar='N',
                     help='number of steps to unroll gan (default: 1)')
 parser.add_argument('--hidden-size', '--h-size', type=int, default=64, metavar='N',
-                    help='size of network intermediate layer (default: 64)')
+                    help='size of network intermediate layer (default: 64; the sm_100a kernels are built for 64 only, '
+                         'other values raise SocialWaysCudaError)')
 parser.add_argument('--dataset', '--data', default='hotel', choices=['hotel'],
                     help='pick a specific dataset (default: "hotel")')
 parser.add_argument('--use-social', action='store_true')
@@ -54,6 +60,10 @@ parser.add_argument('--cuda-graph', action='store_true',
                     help='capture each mini-batch shape of train() into a CUDA graph and replay it')
 parser.add_argument('--fused-adam', action='store_true',
                     help='flat-buffer Adam in one kernel (with the gradient all-reduce fused in under torchrun)')
+parser.add_argument('--native', action='store_true',
+                    help='run the iteration on the library\'s own kernels only (native_step.py), one CUDA graph per batch shape')
+parser.add_argument('--device-noise', type=int, default=None, metavar='SEED',
+                    help='with --native: latent noise drawn on the GPU (Philox) instead of torch.rand on the CPU')
 
 
 def main():
@@ -70,7 +80,7 @@ def main():
         torch.cuda.set_device(local)
         device = f"cuda:{local}"
         dist.init_process_group("nccl", device_id=torch.device(device))
-        if args.cuda_graph and not args.fused_adam:
+        if args.cuda_graph and not (args.fused_adam or args.native):
             raise SystemExit("--cuda-graph under torchrun needs --fused-adam (NCCL calls are not captured)")
         # the sharded step relies on IDENTICAL numpy / torch CPU RNG streams on every rank (labels and noise are drawn for
         # the global mini-batch everywhere): without --seed rank 0 picks one and every rank adopts it
@@ -83,8 +93,8 @@ def main():
     data = np.load(args.input_file)
     tr = SocialWaysTrainer(data, batch_size=args.batch_size, hidden_size=args.hidden_size,
                            use_social=args.use_social, n_unrolling_steps=args.unrolling_steps,
-                           lr_g=args.g_learning_rate, lr_d=args.d_learning_rate, cuda_graph=args.cuda_graph,
-                           fused_adam=args.fused_adam, device=device)
+                           lr_g=args.g_learning_rate, lr_d=args.d_learning_rate, cuda_graph=args.cuda_graph and not args.native,
+                           fused_adam=args.fused_adam or args.native, device=device)
     if distributed:                                                  # replicas start from rank 0's parameters, whatever built them
         for p in list(tr.generator.parameters()) + list(tr.D.parameters()):
             dist.broadcast(p.data, src=0)
@@ -98,7 +108,10 @@ def main():
         start_epoch = 1
     for epoch in trange(start_epoch, args.epochs + 1):               # train.py:646-668
         tr.epoch = epoch
-        (tr.train_graphed if args.cuda_graph else tr.train)()
+        if args.native:
+            tr.train_native(device_noise_seed=args.device_noise)
+        else:
+            (tr.train_graphed if args.cuda_graph else tr.train)()
         if tr.rank == 0:                                            # replicas are bit-identical: rank 0 writes files
             if epoch % 50 == 0:
                 print('Saving model to file ...', model_file)
