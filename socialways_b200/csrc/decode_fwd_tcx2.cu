@@ -1,0 +1,474 @@
+// fp32-faithful tensor-core decode kernel, TWO 128-row tiles in flight per SM (CTA pairs, tcgen05 cta_group::2).
+//
+// Same computation and the same arithmetic as decode_fwd_tcx.cu (the loop of predict(), reference train.py:418-430, on fp16
+// hi/lo split operands, 3 MMAs per product, fp32 accumulation in TMEM) -- re-organised so that the tensor pipe and the CUDA
+// cores work on DIFFERENT tiles at the same time.  decode_fwd_tcx runs one tile per SM: one tile fills TMEM (480 of 512
+// columns) and shared memory (224 KB, 162 KB of it weights), so its ~3.9 K clk of MMA time and ~7.5 K clk of epilogue time per
+// step are serial (ncu: tensor pipe 35 %).  Here
+//   * two CTAs on the two SMs of a TPC form a pair and issue every MMA as ONE cta_group::2 instruction (UMMA M = 256): each
+//     CTA holds only HALF of every weight matrix (N/2 rows of B) -- 111 KB instead of 192 KB incl. the hoist weights, which
+//     are now resident too;
+//   * each CTA runs TWO tile slots (warps 0-7 / 8-15, thread = (TMEM lane = row, column half)); a slot owns 256 TMEM
+//     columns, its own h / x operand buffers and its own barriers, and is a strictly serial MMA -> epilogue chain; the two
+//     slots of an SM interleave by themselves (MMAs execute in issue order, whichever slot is in an epilogue leaves the
+//     tensor pipe to the other);
+//   * the step-invariant layer-1 term c1 (160 fp32 per row) no longer lives in TMEM: it is computed once per tile by MMAs,
+//     parked in a per-slot scratch buffer in global memory (80 KB per slot, L2 resident: 23.7 MB for the chip) and re-read
+//     by the thread that wrote it, coalesced, one K block ahead of its use.
+// TMEM columns of a slot: [0,160) layer-1 accumulator -> a1 hi|lo in place | [160,240) layer-2 accumulator | gates half 0 ->
+// [0,128) (queued behind the layer-2 MMAs, runs under the layer-2 epilogue), gates half 1 -> [128,256).  Tile prologue:
+// [160,256) holds the [S ; z] hi|lo A operand of the hoist, [0,160) its result.
+// Synchronisation: the threads of both CTAs signal "operands written" per warp on the LEADER CTA's `ready` mbarrier (remote
+// arrive, release at cluster scope); the leader's issuing warp waits for it, issues, and commits with a multicast arrive on
+// the `full` mbarriers of both CTAs.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include "sw_common.cuh"
+#include "sw_umma.cuh"
+
+namespace sw {
+
+constexpr int P_ROWS = 128;
+constexpr int P_THREADS = 512;
+constexpr int P_SLOT_THREADS = 256;
+constexpr int P_L2NL = 40;            // layer-2 B rows per CTA (N = 80)
+// per-rank fp16 weight image (elements); every matrix canonical [K/8][local rows][8]
+constexpr int PW_W1H_HI = 0, PW_W1H_LO = 5120,                                   // [8][80][8]
+              PW_W2_HI = 10240, PW_W2_LO = PW_W2_HI + 20 * P_L2NL * 8,           // [20][40][8]
+              PW_WHH = PW_W2_LO + 20 * P_L2NL * 8,                               // [half][hi|lo][8][64][8]
+              PW_WXK = PW_WHH + 16384,                                           // [half][2][64][8]  x-feedback K block
+              PW_WSZ_HI = PW_WXK + 2048, PW_WSZ_LO = PW_WSZ_HI + 7680,           // [12][80][8]  hoisted rows of W1 (S, z)
+              PW_TOTAL = PW_WSZ_LO + 7680;
+constexpr int PF_B1 = 0, PF_B2 = 160, PF_B34 = 240, PF_W34 = 256, PF_TOTAL = 256 + 160;
+constexpr uint32_t PC_R1 = 0, PC_R2 = 160, PC_AHI = 160, PC_ALO = 208;
+constexpr uint32_t PFMT = 0;          // fp16
+// c1 scratch: [cta][slot][10 K blocks][4][128 rows] float4
+constexpr int P_SCRATCH_F4_PER_SLOT = 10 * 4 * P_ROWS;
+
+struct Tcx2Smem {
+    float zst[2][P_ROWS * SW_Z];             // noise block of each slot's tile (TMA, 128-byte swizzle; 1024-byte aligned)
+    __half w[PW_TOTAL];                      // this rank's half of every weight matrix (113 664 B)
+    __half h[2][2][8 * P_ROWS * 8];          // [slot][hi|lo][8 chunks][128][8]
+    __half xk[2][2 * P_ROWS * 8];            // [slot] x-feedback A operand, one K block
+    float f32[PF_TOTAL];
+    float vpart[2][2 * P_ROWS];              // [slot][component][row]: partial velocity of column half 1
+    unsigned long long ready[2];             // operands written (16 warp arrivals: 8 warps x 2 CTAs; used in the leader CTA)
+    unsigned long long full[2][3];           // MMA completion: hoist / L1 / L2 | gates half 0 | gates half 1
+    unsigned long long bar_z[2];             // TMA: the slot's noise block
+    unsigned long long bar_w;                // TMA: weights
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void psplit2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h2 = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+}
+__device__ __forceinline__ void slot_sync(int slot) { asm volatile("bar.sync %0, %1;" :: "r"(slot + 1), "n"(P_SLOT_THREADS) : "memory"); }
+
+template <int NL, int KB>
+__device__ __forceinline__ void pmma3_ss(uint32_t d, const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo,
+                                         bool leader) {
+    pmma_ss<NL, KB>(d, a_hi, b_hi, PFMT, false, leader);
+    pmma_ss<NL, KB>(d, a_hi, b_lo, PFMT, true, leader);
+    pmma_ss<NL, KB>(d, a_lo, b_hi, PFMT, true, leader);
+}
+template <int NL, int KB, int A_STRIDE>
+__device__ __forceinline__ void pmma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const __half* b_hi, const __half* b_lo, bool leader) {
+    pmma_ts<NL, KB, A_STRIDE>(d, a_hi, b_hi, PFMT, false, leader);
+    pmma_ts<NL, KB, A_STRIDE>(d, a_hi, b_lo, PFMT, true, leader);
+    pmma_ts<NL, KB, A_STRIDE>(d, a_lo, b_hi, PFMT, true, leader);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][32] fp32, box 128 x 32, 128-byte swizzle */,
+                       const __half* __restrict__ w16 /* [2 ranks][PW_TOTAL] */, const float* __restrict__ wf32,
+                       const float* __restrict__ h0, const float* __restrict__ c0, const float* __restrict__ pooled,
+                       const float* __restrict__ x_last, float* __restrict__ out, float4* __restrict__ scratch,
+                       int* __restrict__ status, int n_agents, long long n_rows, int n_next, int n_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Tcx2Smem& s = *reinterpret_cast<Tcx2Smem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot = warp >> 3, w8 = warp & 7, st = tid & (P_SLOT_THREADS - 1);
+    const int lq = w8 & 3, hf = w8 >> 2;            // TMEM lane quarter (= warp % 4), column half
+    const int r = lq * 32 + lane;
+    const uint32_t cta = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const bool leader = lane == 0;
+    const bool issuer = cta == 0 && w8 == 0;        // warp that issues this slot's MMAs for BOTH CTAs
+    const int n_units = (n_tiles + 1) >> 1;         // work unit = two consecutive tiles, one per CTA of the pair
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(&s.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    auto prefetch_noise = [&](int sl, int tile) {
+        mbar_expect_tx(&s.bar_z[sl], P_ROWS * SW_Z * 4);
+        tma_load_2d(s.zst[sl], &noise_map, 0, tile * P_ROWS, &s.bar_z[sl]);
+    };
+    if (tid == 0) {
+        for (int sl = 0; sl < 2; ++sl) {
+            ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.ready[sl]), 16);
+            for (int j = 0; j < 3; ++j) ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.full[sl][j]), 1);
+            ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar_z[sl]), 1);
+        }
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar_w), 1);
+        ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
+        constexpr uint32_t W_BYTES = PW_TOTAL * 2, W_PIECE = W_BYTES / 4, F_BYTES = PF_TOTAL * 4;
+        static_assert(W_PIECE % 16 == 0 && F_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+        mbar_expect_tx(&s.bar_w, W_BYTES + F_BYTES);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(w16 + (size_t)cta * PW_TOTAL);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            tma_load_1d(reinterpret_cast<unsigned char*>(s.w) + q * W_PIECE, src + q * W_PIECE, W_PIECE, &s.bar_w);
+        tma_load_1d(s.f32, wf32, F_BYTES, &s.bar_w);
+        for (int sl = 0; sl < 2; ++sl) {
+            const int u = sl + 2 * pair, tile = 2 * u + (int)cta;
+            if (u < n_units && tile < n_tiles) prefetch_noise(sl, tile);
+        }
+    }
+    ptx::tcgen05_fence_before_thread_sync();
+    __syncthreads();
+    cluster_sync_all();                     // the peer's barriers exist before anything arrives on them
+    ptx::tcgen05_fence_after_thread_sync();
+    mbar_wait(&s.bar_w, 0u);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0);
+    const uint32_t ts = tmem + (uint32_t)(slot * 256);                 // this slot's columns, lane 0
+    const uint32_t tl = ts + ((uint32_t)(lq * 32) << 16);              // this thread's lane
+    uint32_t ph_ready = 0, ph_l = 0, ph_g = 0, ph_z = 0;
+    unsigned long long* const bar_ready = &s.ready[slot];
+    unsigned long long* const bar_l = &s.full[slot][0];
+    unsigned long long* const bar_g0 = &s.full[slot][1];
+    unsigned long long* const bar_g1 = &s.full[slot][2];
+    __half* const h_hi = s.h[slot][0];
+    __half* const h_lo = s.h[slot][1];
+    __half* const xk = s.xk[slot];
+    float4* const my_scratch = scratch + ((size_t)blockIdx.x * 2 + slot) * P_SCRATCH_F4_PER_SLOT + r;
+
+    // every warp: "my operand writes are done" -> one arrival on the leader's barrier
+    auto arrive_ready = [&]() {
+        ptx::tcgen05_fence_before_thread_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(bar_ready, 0);
+    };
+    // issuing warp: all 16 warps of the slot (both CTAs) have arrived
+    auto wait_ready = [&]() {
+        mbar_wait_cluster(bar_ready, ph_ready); ph_ready ^= 1;
+        ptx::tcgen05_fence_after_thread_sync();
+    };
+    auto wait_full = [&](unsigned long long* bar, uint32_t parity) {
+        mbar_wait_cluster(bar, parity);
+        ptx::tcgen05_fence_after_thread_sync();
+    };
+
+    for (int u = slot + 2 * pair; u < n_units; u += 2 * n_pairs) {
+        const int tile = 2 * u + (int)cta;
+        const bool has_tile = tile < n_tiles;                            // the odd last unit has one tile only
+        const long long row0 = (long long)tile * P_ROWS;
+        const bool valid = has_tile && row0 + r < n_rows;
+        const int abase = (int)(row0 % n_agents);
+        const int agent = valid ? (abase + r) % n_agents : 0;
+        // ---------------- tile prologue: every global load coalesced and issued up front ----------------
+        float4 sreg[8], hreg[4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                                     // S tile [128][16 pieces]: piece g = st + 256 i
+            const int g = st + i * P_SLOT_THREADS, row = g >> 4, piece = g & 15;
+            sreg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pooled && has_tile && row0 + row < n_rows)
+                sreg[i] = __ldg(reinterpret_cast<const float4*>(pooled + (size_t)((abase + row) % n_agents) * SW_H) + piece);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {                                 // h0 items: (row, 8-column chunk), 8 rows x 128 B per instruction
+                const int hrow = w8 * 8 + (lane & 7) + 64 * j, chunk = (lane >> 3) + 4 * i;
+                hreg[j * 2 + i][0] = hreg[j * 2 + i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (has_tile && row0 + hrow < n_rows) {
+                    const float4* src = reinterpret_cast<const float4*>(h0 + (size_t)((abase + hrow) % n_agents) * SW_H) + chunk * 2;
+                    hreg[j * 2 + i][0] = __ldg(src);
+                    hreg[j * 2 + i][1] = __ldg(src + 1);
+                }
+            }
+        float2 xl = make_float2(0.f, 0.f);
+        if (hf == 0 && valid) xl = __ldg(reinterpret_cast<const float2*>(x_last + (size_t)agent * 4));
+        {
+            float4* sS = reinterpret_cast<float4*>(h_hi);                 // [128 rows][16 pieces], piece' = piece ^ (row & 7); 32 KB = h hi|lo
+            const float4* sZ = reinterpret_cast<const float4*>(s.zst[slot]);   // [128 rows][8 pieces], TMA swizzle: piece' = piece ^ (row & 7)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int g = st + i * P_SLOT_THREADS, row = g >> 4, piece = g & 15;
+                sS[row * 16 + (piece ^ (row & 7))] = sreg[i];
+            }
+            if (has_tile) { mbar_wait(&s.bar_z[slot], ph_z); ph_z ^= 1; }
+            slot_sync(slot);
+            // [S ; z] (K = 96 = 24 pieces): this thread owns pieces 12 hf .. 12 hf + 11 of its row = K blocks 3 hf .. 3 hf + 2
+            uint32_t hi[24], lo[24];
+#pragma unroll
+            for (int e = 0; e < 12; ++e) {
+                const int piece = hf * 12 + e;
+                float4 v;
+                if (piece < 16) v = sS[r * 16 + (piece ^ (r & 7))];
+                else            v = has_tile ? sZ[r * 8 + ((piece - 16) ^ (r & 7))] : make_float4(0.f, 0.f, 0.f, 0.f);
+                psplit2(v.x, v.y, hi[2 * e], lo[2 * e]);
+                psplit2(v.z, v.w, hi[2 * e + 1], lo[2 * e + 1]);
+            }
+            tmem_st<24>(tl + PC_AHI + hf * 24, hi);
+            tmem_st<24>(tl + PC_ALO + hf * 24, lo);
+            ptx::tcgen05_wait_st();
+            slot_sync(slot);                                              // staging consumed: h region and noise buffer are free
+        }
+        {   // next tile's noise block: 12 steps ahead of its use
+            const int un = u + 2 * n_pairs, tn = 2 * un + (int)cta;
+            if (st == 0 && un < n_units && tn < n_tiles) prefetch_noise(slot, tn);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {                                     // h0 -> hi|lo operand chunks [chunk][row][8]
+            const int hrow = w8 * 8 + (lane & 7) + 64 * (q >> 1), chunk = (lane >> 3) + 4 * (q & 1);
+            uint32_t hi[4], lo[4];
+            psplit2(hreg[q][0].x, hreg[q][0].y, hi[0], lo[0]);
+            psplit2(hreg[q][0].z, hreg[q][0].w, hi[1], lo[1]);
+            psplit2(hreg[q][1].x, hreg[q][1].y, hi[2], lo[2]);
+            psplit2(hreg[q][1].z, hreg[q][1].w, hi[3], lo[3]);
+            const size_t off = ((size_t)chunk * P_ROWS + hrow) * 8;
+            *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        ptx::fence_proxy_async(ptx::space_shared);
+        arrive_ready();
+        if (issuer) {       // c1 = [S ; z] . W1[S,z rows]^T -> [0,160)
+            wait_ready();
+            pmma3_ts<80, 6, 8>(ts + PC_R1, ts + PC_AHI, ts + PC_ALO, s.w + PW_WSZ_HI, s.w + PW_WSZ_LO, leader);
+            umma_commit_pair(bar_l, leader);
+        }
+        // cell state of this thread's units: c[0..15] = units 16 hf .. (gates half 0), c[16..31] = units 32 + 16 hf .. (half 1)
+        float c[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 v = valid ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent * SW_H + (q >> 2) * 32 + hf * 16) + (q & 3))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+            c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+        }
+        float p0 = xl.x, p1 = xl.y;
+        bool out_of_range = false;
+        wait_full(bar_l, ph_l); ph_l ^= 1;
+#pragma unroll
+        for (int kb = 0; kb < 5; ++kb) {       // c1 + b1 -> scratch (this thread's 5 K blocks of 16 columns)
+            const int col0 = (hf * 5 + kb) * 16;
+            uint32_t v[16];
+            tmem_ld<16>(tl + PC_R1 + col0, v);
+            ptx::tcgen05_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                __stcg(my_scratch + ((hf * 5 + kb) * 4 + q) * P_ROWS,
+                       make_float4(__uint_as_float(v[4 * q]) + s.f32[PF_B1 + col0 + 4 * q], __uint_as_float(v[4 * q + 1]) + s.f32[PF_B1 + col0 + 4 * q + 1],
+                                   __uint_as_float(v[4 * q + 2]) + s.f32[PF_B1 + col0 + 4 * q + 2], __uint_as_float(v[4 * q + 3]) + s.f32[PF_B1 + col0 + 4 * q + 3]));
+        }
+        arrive_ready();
+        if (issuer) {       // layer 1 of step 0
+            wait_ready();
+            pmma3_ss<80, 4>(ts + PC_R1, h_hi, h_lo, s.w + PW_W1H_HI, s.w + PW_W1H_LO, leader);
+            umma_commit_pair(bar_l, leader);
+        }
+
+        for (int t = 0; t < n_next; ++t) {
+            const bool feed_back = t + 1 < n_next;
+            // ---------------- layer 1 epilogue: a1 = lrelu(acc + c1) -> hi|lo in place; c1 read one K block ahead ----------------
+            float4 cn[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cn[q] = __ldcg(my_scratch + ((hf * 5) * 4 + q) * P_ROWS);
+            wait_full(bar_l, ph_l); ph_l ^= 1;
+#pragma unroll
+            for (int kb = 0; kb < 5; ++kb) {
+                const float4 cc[4] = {cn[0], cn[1], cn[2], cn[3]};
+                if (kb < 4) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) cn[q] = __ldcg(my_scratch + ((hf * 5 + kb + 1) * 4 + q) * P_ROWS);
+                }
+                uint32_t acc[16], pc[16];
+                const uint32_t ta = tl + PC_R1 + (hf * 5 + kb) * 16;
+                tmem_ld<16>(ta, acc);
+                ptx::tcgen05_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float y0 = __uint_as_float(acc[4 * q]) + cc[q].x, y1 = __uint_as_float(acc[4 * q + 1]) + cc[q].y;
+                    const float y2 = __uint_as_float(acc[4 * q + 2]) + cc[q].z, y3 = __uint_as_float(acc[4 * q + 3]) + cc[q].w;
+                    psplit2(lrelu02(y0), lrelu02(y1), pc[2 * q], pc[8 + 2 * q]);
+                    psplit2(lrelu02(y2), lrelu02(y3), pc[2 * q + 1], pc[8 + 2 * q + 1]);
+                }
+                tmem_st<16>(ta, pc);
+            }
+            ptx::tcgen05_wait_st();
+            arrive_ready();
+            // ---------------- layer 2: a1 (K = 160, TMEM, K block kb at column 16 kb) -> 80 columns in [160,240); the h part of
+            //                  gates half 0 is queued right behind it (overwrites a1 once layer 2 has consumed it) ----------------
+            if (issuer) {
+                wait_ready();
+                pmma3_ts<P_L2NL, 10, 16>(ts + PC_R2, ts + PC_R1, ts + PC_R1 + 8, s.w + PW_W2_HI, s.w + PW_W2_LO, leader);
+                umma_commit_pair(bar_l, leader);
+                if (feed_back) pmma3_ss<64, 4>(ts, h_hi, h_lo, s.w + PW_WHH, s.w + PW_WHH + 4096, leader);
+            }
+            wait_full(bar_l, ph_l); ph_l ^= 1;
+            float v0 = 0.0f, v1 = 0.0f;
+            {   // layer-2 epilogue + folded layers 3+4 (80 -> 2): partial velocity over this thread's 40 columns
+                uint32_t acc[40];
+                tmem_ld<40>(tl + PC_R2 + hf * 40, acc);
+                ptx::tcgen05_wait_ld();
+                const float* b2 = s.f32 + PF_B2 + hf * 40;
+                const float2* w34 = reinterpret_cast<const float2*>(s.f32 + PF_W34) + hf * 40;
+#pragma unroll
+                for (int j = 0; j < 40; ++j) {
+                    const float y = lrelu02(__uint_as_float(acc[j]) + b2[j]);
+                    const float2 w = w34[j];
+                    v0 = fmaf(y, w.x, v0);
+                    v1 = fmaf(y, w.y, v1);
+                }
+            }
+            if (hf == 1) { s.vpart[slot][r] = v0; s.vpart[slot][P_ROWS + r] = v1; }
+            slot_sync(slot);
+            if (hf == 0) {      // column half 0 finishes the row: velocity, integration, emit; (p, v) -> hi|lo x block of the gate MMA
+                v0 += s.vpart[slot][r] + s.f32[PF_B34];
+                v1 += s.vpart[slot][P_ROWS + r] + s.f32[PF_B34 + 1];
+                p0 += v0; p1 += v1;
+                out_of_range |= !(fmaxf(fmaxf(fabsf(p0), fabsf(p1)), fmaxf(fabsf(v0), fabsf(v1))) <= 6.0e4f);   // fp16 range guard
+                if (feed_back) {
+                    uint32_t hp, lp, hv, lv;
+                    psplit2(p0, p1, hp, lp);
+                    psplit2(v0, v1, hv, lv);
+                    *reinterpret_cast<uint4*>(xk + (size_t)r * 8) = make_uint4(hp, hv, lp, lv);                      // k 0..7
+                    *reinterpret_cast<uint4*>(xk + (size_t)(P_ROWS + r) * 8) = make_uint4(hp, hv, 0x3C003C00u, 0u);  // k 8..15
+                }
+                if (valid)
+                    *reinterpret_cast<float4*>(out + ((size_t)(row0 + r) * n_next + t) * 4) = make_float4(p0, p1, v0, v1);
+            }
+            if (!feed_back) break;
+            ptx::fence_proxy_async(ptx::space_shared);
+            arrive_ready();
+            // ---------------- gates: x block of half 0 -> full[1]; half 1 (h part + x block) -> [128,256) -> full[2] ----------------
+            if (issuer) {
+                wait_ready();
+                pmma_ss<64, 1>(ts, xk, s.w + PW_WXK, PFMT, true, leader);
+                umma_commit_pair(bar_g0, leader);
+                pmma3_ss<64, 4>(ts + 128, h_hi, h_lo, s.w + PW_WHH + 8192, s.w + PW_WHH + 8192 + 4096, leader);
+                pmma_ss<64, 1>(ts + 128, xk, s.w + PW_WXK + 1024, PFMT, true, leader);
+                umma_commit_pair(bar_g1, leader);
+            }
+            // ---------------- LSTM cell: 16 units of half 0 (units 16 hf ..), then 16 units of half 1 (units 32 + 16 hf ..) ----------------
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (half == 0) wait_full(bar_g0, ph_g); else ptx::tcgen05_fence_after_thread_sync();
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    uint32_t a[32];
+                    tmem_ld<32>(tl + half * 128 + hf * 64 + ch * 32, a);
+                    ptx::tcgen05_wait_ld();
+                    float hv[8];
+#pragma unroll
+                    for (int uu = 0; uu < 8; uu += 2) {
+                        float g[2][4];
+#pragma unroll
+                        for (int w2 = 0; w2 < 2; ++w2)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) g[w2][q] = __uint_as_float(a[(uu + w2) * 4 + q]);
+                        lstm_cell_pair_prescaled(g[0], g[1], c[half * 16 + ch * 8 + uu], c[half * 16 + ch * 8 + uu + 1], hv[uu], hv[uu + 1]);
+                    }
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) psplit2(hv[2 * e], hv[2 * e + 1], hi[ch * 4 + e], lo[ch * 4 + e]);
+                }
+                // h is an operand of the half-1 gate MMAs: nothing may overwrite it before they have completed
+                if (half == 0) wait_full(bar_g1, ph_g);
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    const size_t off = ((size_t)(half * 4 + hf * 2 + ch) * P_ROWS + r) * 8;
+                    *reinterpret_cast<uint4*>(h_hi + off) = make_uint4(hi[ch * 4], hi[ch * 4 + 1], hi[ch * 4 + 2], hi[ch * 4 + 3]);
+                    *reinterpret_cast<uint4*>(h_lo + off) = make_uint4(lo[ch * 4], lo[ch * 4 + 1], lo[ch * 4 + 2], lo[ch * 4 + 3]);
+                }
+            }
+            ph_g ^= 1;
+            ptx::fence_proxy_async(ptx::space_shared);
+            arrive_ready();
+            if (issuer) {       // next step's layer 1
+                wait_ready();
+                pmma3_ss<80, 4>(ts + PC_R1, h_hi, h_lo, s.w + PW_W1H_HI, s.w + PW_W1H_LO, leader);
+                umma_commit_pair(bar_l, leader);
+            }
+        }
+        if (out_of_range && valid && status) atomicOr(status, 1);
+    }
+    ptx::tcgen05_fence_before_thread_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
+}  // namespace sw
+
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no link-time dependency on libcuda)
+static int encode_noise_map2(CUtensorMap* map, const float* noise, long long n_rows) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        SW_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !fn) return SW_ERR_UNSUPPORTED;
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t dims[2] = {(cuuint64_t)SW_Z, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)SW_Z * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)SW_Z, (cuuint32_t)sw::P_ROWS}, elem[2] = {1, 1};
+    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(noise), dims, strides, box, elem,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SW_OK : SW_ERR_ARG;
+}
+
+static int tcx2_grid(long long tiles, int sm_count) {
+    const long long units = (tiles + 1) / 2;            // two tiles (one per CTA of a pair) per unit, two unit slots per pair
+    long long pairs = (units + 1) / 2;
+    if (pairs > sm_count / 2) pairs = sm_count / 2;
+    if (pairs < 1) pairs = 1;
+    return (int)(2 * pairs);
+}
+
+extern "C" long long sw_decode_tcx2_scratch_bytes(int sm_count) {
+    if (sm_count < 2) return 0;
+    return (long long)(sm_count / 2) * 2 * 2 * sw::P_SCRATCH_F4_PER_SLOT * 16;
+}
+
+extern "C" int sw_decode_fwd_tcx2(const void* tcx2_w16, const float* tcx2_f32, const float* h0, const float* c0,
+                                  const float* pooled, const float* noise, const float* x_last, float* out, void* scratch,
+                                  long long scratch_bytes, int* status, int n_agents, int n_samples, int n_next, int sm_count,
+                                  void* stream) {
+    if (!tcx2_w16 || !tcx2_f32 || !h0 || !c0 || !noise || !x_last || !out || !scratch) return SW_ERR_ARG;
+    if (n_agents <= 0 || n_samples <= 0 || n_next <= 0 || sm_count < 2) return SW_ERR_ARG;
+    if (scratch_bytes < sw_decode_tcx2_scratch_bytes(sm_count) || ((uintptr_t)scratch & 15u) != 0) return SW_ERR_ARG;
+    const long long n_rows = (long long)n_agents * n_samples;
+    const long long tiles = (n_rows + sw::P_ROWS - 1) / sw::P_ROWS;
+    if (tiles > 0x3fffffffLL) return SW_ERR_UNSUPPORTED;
+    if (((uintptr_t)noise & 15u) != 0) return SW_ERR_ARG;
+    CUtensorMap noise_map;
+    const int rc = encode_noise_map2(&noise_map, noise, n_rows);
+    if (rc != SW_OK) return rc;
+    const int smem = (int)sizeof(sw::Tcx2Smem);
+    SW_SET_MAX_SMEM(sw::decode_fwd_tcx2_kernel, smem);
+    const int grid = tcx2_grid(tiles, sm_count);
+    sw::decode_fwd_tcx2_kernel<<<grid, sw::P_THREADS, smem, (cudaStream_t)stream>>>(
+        noise_map, (const __half*)tcx2_w16, tcx2_f32, h0, c0, pooled, x_last, out, (float4*)scratch, status, n_agents, n_rows, n_next,
+        (int)tiles);
+    SW_CUDA_TRY(cudaGetLastError());
+    return SW_OK;
+}
+
+extern "C" int sw_decode_tcx2_pack_sizes(int* n_w16, int* n_f32) {
+    if (!n_w16 || !n_f32) return SW_ERR_ARG;
+    *n_w16 = 2 * sw::PW_TOTAL;
+    *n_f32 = sw::PF_TOTAL;
+    return SW_OK;
+}

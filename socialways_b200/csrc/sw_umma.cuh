@@ -105,6 +105,73 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, const 
         umma_issue_ts(d_tmem, a_tmem + kb * A_STRIDE, bd + (uint64_t)(kb * 2 * B_ROWS), idesc, accumulate_first || kb > 0, leader);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair form (cta_group::2, a cluster of two CTAs on the two SMs of a TPC): ONE instruction, issued by a lane of the
+// leader CTA (cluster rank 0), computes D[256 x N] = A[256 x K] . B[N x K]^T where each CTA supplies ITS 128 rows of A
+// (same shared-memory offset / TMEM address in both CTAs), ITS N/2 rows of B (rank 0: rows [0, N/2), rank 1: [N/2, N)) and
+// receives ITS 128 rows of D (all N columns) in its own TMEM.  Every B matrix is therefore stored once per pair --
+// half per SM -- which is what lets two 128-row tiles per SM be in flight against one resident weight set.
+// (operand placement and instruction form pinned on hardware by tests/tc_probe/pair_mma_probe.cu)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ constexpr uint32_t umma_idesc_pair(int n, uint32_t ab_format) {       // M = 256
+    return (1u << 4) | (ab_format << 7) | (ab_format << 10) | ((uint32_t)(n >> 3) << 17) | (16u << 24);
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset as `bar` in CTA `cta` of the cluster.  Default semantics
+// (.release.cta), as CUTLASS's ClusterBarrier::arrive(cta_id): the cluster-scope form costs MEMBAR.ALL.GPU + ERRBAR per
+// arrival and CCTL.IVALL (an L1 invalidation) per wait -- 47 % of all stall samples of the first version of
+// decode_fwd_tcx2 (ncu).  What crosses the pair here is consumed by the tensor core's async proxy (shared-memory operands,
+// made visible by fence.proxy.async before the arrival) or lives in TMEM (tcgen05.wait::st + fence::before_thread_sync).
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned long long* bar, uint32_t cta) {
+    uint32_t ra;
+    const uint32_t la = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(ra) : "memory");
+}
+// wait on a barrier of this CTA whose arrivals come from the peer CTA (operand-ready) or from a multicast tcgen05.commit
+__device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, uint32_t parity) { mbar_wait(bar, parity); }
+// completion of every MMA issued so far by this thread -> one arrival on `bar` in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(unsigned long long* bar, bool leader) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %2;\n\t}"
+                 :: "r"(addr), "r"((uint32_t)leader), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_issue_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                   bool accumulate, bool leader) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate), "r"((uint32_t)leader)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_issue_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                                   bool accumulate, bool leader) {
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+                 "@q tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate), "r"((uint32_t)leader)
+                 : "memory");
+}
+// D[256 x N] (+)= A . B^T over KB K-blocks, A in shared memory ([K/8][128][8] per CTA), B [K/8][NL = N/2 local rows][8] per CTA
+template <int NL, int KB, typename T>
+__device__ __forceinline__ void pmma_ss(uint32_t d_tmem, const T* a, const T* b, uint32_t ab_format, bool accumulate_first, bool leader) {
+    const uint32_t idesc = umma_idesc_pair(2 * NL, ab_format);
+    const uint64_t ad = umma_desc_uniform(a, 128 * 16, 128), bd = umma_desc_uniform(b, NL * 16, 128);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+        umma_issue_ss_pair(d_tmem, ad + (uint64_t)(kb * 2 * 128), bd + (uint64_t)(kb * 2 * NL), idesc, accumulate_first || kb > 0, leader);
+}
+template <int NL, int KB, int A_STRIDE = 8, typename T>
+__device__ __forceinline__ void pmma_ts(uint32_t d_tmem, uint32_t a_tmem, const T* b, uint32_t ab_format, bool accumulate_first, bool leader) {
+    const uint32_t idesc = umma_idesc_pair(2 * NL, ab_format);
+    const uint64_t bd = umma_desc_uniform(b, NL * 16, 128);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+        umma_issue_ts_pair(d_tmem, a_tmem + kb * A_STRIDE, bd + (uint64_t)(kb * 2 * NL), idesc, accumulate_first || kb > 0, leader);
+}
+
 // TMEM load / store of NCOLS consecutive 32-bit columns of the calling thread's lane (32x32b shape),
 // decomposed into the power-of-two instruction widths.
 template <int NCOLS>

@@ -131,6 +131,50 @@ def pack_decoder_tcx(lstm_pack, dec_pack):
     return w16, wsz16, f32
 
 
+def pack_decoder_tcx2(lstm_pack, dec_pack):
+    """Operands of the CTA-pair decode kernel (csrc/decode_fwd_tcx2.cu, tcgen05 cta_group::2): the same hi/lo split matrices
+    as `pack_decoder_tcx`, but every B matrix [N][K] is cut into the two N halves the two CTAs of a pair supply (rank 0: rows
+    [0, N/2), rank 1: [N/2, N)), each canonical K-major.
+    w16  fp16 [2 ranks][56832]: W1h hi | lo [8][80][8]; W2 hi | lo [20][40][8] (not stacked: the pair kernel accumulates the
+         three products into ONE 80-column region); Whh per gate half g (n' in [128 g, 128 g + 128), the rank supplies 64 of
+         them) hi | lo [8][64][8]; the x-feedback K block per gate half [2][64][8] (k 0..3 Wx_hi, 4..7 Wx_hi, 8..11 Wx_lo,
+         12 b_hi, 13 b_lo, 14..15 zero); the hoisted rows of W1 (S: k 0..63, z: 64..95) hi | lo [12][80][8] -- resident in the
+         pair kernel.  Gate rows carry the ex2 prescale.
+    f32  [416]: b1 [160] | b2 [80] | b34 [2] | pad | W34 [80 k][2]  (as pack_decoder_tcx)"""
+    w1 = dec_pack[:25600].view(160, 160).t()                  # [n, k], k order {h, S, z}
+    b1 = dec_pack[25600:25760]
+    w2 = dec_pack[25760:38560].view(160, 80).t()
+    b2 = dec_pack[38560:38640]
+    b34 = dec_pack[38800:38802]
+    scale = _gate_prescale(lstm_pack.device, lstm_pack.dtype)
+    whh = lstm_pack[4:68].t() * scale[:, None]                # [256 n', 64]
+    wx = lstm_pack[0:4].t() * scale[:, None]                  # [256 n', 4]
+    bl = lstm_pack[68] * scale                                # [256]
+    w1h_hi, w1h_lo = _split_f16(w1[:, :64].contiguous())
+    w2_hi, w2_lo = _split_f16(w2.contiguous())
+    whh_hi, whh_lo = _split_f16(whh.contiguous())
+    wsz_hi, wsz_lo = _split_f16(w1[:, 64:].contiguous())
+    wx_hi, wx_lo = _split_f16(wx.contiguous())
+    bl_hi, bl_lo = _split_f16(bl.contiguous())
+    zero = torch.zeros(256, 2, device=wx.device, dtype=torch.float16)
+    xkb = torch.cat([wx_hi, wx_hi, wx_lo, bl_hi[:, None], bl_lo[:, None], zero], dim=1)      # [256, 16]
+    images = []
+    for rank in (0, 1):
+        parts = [_canonical_kmajor(m[80 * rank:80 * rank + 80]) for m in (w1h_hi, w1h_lo)]
+        parts += [_canonical_kmajor(m[40 * rank:40 * rank + 40]) for m in (w2_hi, w2_lo)]
+        for g in (0, 1):
+            r0 = 128 * g + 64 * rank
+            parts += [_canonical_kmajor(whh_hi[r0:r0 + 64]), _canonical_kmajor(whh_lo[r0:r0 + 64])]
+        for g in (0, 1):
+            r0 = 128 * g + 64 * rank
+            parts.append(_canonical_kmajor(xkb[r0:r0 + 64]))
+        parts += [_canonical_kmajor(m[80 * rank:80 * rank + 80]) for m in (wsz_hi, wsz_lo)]
+        images.append(torch.cat(parts))
+    w16 = torch.cat(images).contiguous()
+    f32 = torch.cat([b1, b2, b34, b34.new_zeros(14), dec_pack[38640:38800]]).contiguous()
+    return w16, f32
+
+
 def pack_pool_tcx(fc2_w):
     """Layer-2 operand of the tensor-core pooling kernel (csrc/pool_fwd_tcx.cu): EmbedSocialFeatures.fc.2.weight [64 n][32 k]
     as canonical hi block then canonical lo block ([4][64][8] each), fp16 [4096]."""
