@@ -168,6 +168,13 @@ int sw_decode_fwd_tcx2(const void* tcx2_w16, const float* tcx2_f32, const float*
 int sw_decode_tcx2_pack_sizes(int* n_w16, int* n_f32);
 long long sw_decode_tcx2_scratch_bytes(int sm_count);
 
+/* The CTA-pair decode in PING-PONG form (csrc/decode_fwd_tcx3.cu): same arguments, pack, scratch, outputs and arithmetic as
+ * sw_decode_fwd_tcx2, but all 16 epilogue warps of a CTA serve both tile slots alternately (while they work on one slot's
+ * epilogue the tensor pipe runs the other slot's MMAs) and a dedicated warp issues every MMA of the pair. */
+int sw_decode_fwd_tcx3(const void* tcx2_w16, const float* tcx2_f32, const float* h0, const float* c0, const float* pooled,
+                       const float* noise, const float* x_last, float* out, void* scratch, long long scratch_bytes,
+                       int* status, int n_agents, int n_samples, int n_next, int sm_count, void* stream);
+
 /* Discriminator FC heads (train.py:281-292, 300-309), one thread per trajectory, all 8 Linear layers fused.
  *   pack: sw_disc_heads_pack_floats(P, L) floats = Wo1[32][64] bo1 Wo2[32][32] bo2 Wp1[32][P] bp1 Wp2[32][32] bp2
  *         Wc1[32][64] bc1 Wc2[1][32] bc2 Wl1[32][64] bl1 Wl2[L][32] bl2 (torch [out][in] layouts), P = n_next*4, L = 2

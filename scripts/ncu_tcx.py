@@ -21,10 +21,10 @@ pooled = torch.randn(n, 64, device="cuda", generator=g) * 0.3
 noise = torch.rand(k, n, 32, device="cuda", generator=g)
 xl = torch.rand(n, 4, device="cuda", generator=g)
 out = torch.empty(k, n, T, 4, device="cuda")
-which = sys.argv[1] if len(sys.argv) > 1 else "tcx"       # "tcx" (one tile per SM) or "tcx2" (CTA pairs, two tiles per SM)
+which = sys.argv[1] if len(sys.argv) > 1 else "tcx"       # "tcx" (one tile per SM), "tcx2" / "tcx3" (CTA pairs, two tiles per SM)
 for _ in range(3):
-    if which == "tcx2":
-        ops.decode_tcx2(*pk["tcx2"], h, c, pooled, noise, xl, T, out=out)
+    if which in ("tcx2", "tcx3"):
+        ops.decode_tcx2(*pk["tcx2"], h, c, pooled, noise, xl, T, out=out, pingpong=which == "tcx3")
     else:
         ops.decode_tcx(*pk["tcx"], h, c, pooled, noise, xl, T, out=out)
 torch.cuda.synchronize()

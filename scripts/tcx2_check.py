@@ -14,6 +14,9 @@ from golden_data import synthetic_scenes
 from oracle import socialways_oracle as so
 
 
+PAIR_PRECISION = os.environ.get("SW_PAIR", "fp16x2q")       # "fp16x2p" = tcx2 (slot-private warps), "fp16x2q" = tcx3 (ping-pong)
+
+
 def small_cases():
     P = so.init_weights(seed=6)
     gen = sw.Generator(use_social=True)
@@ -28,7 +31,7 @@ def small_cases():
         noise = torch.rand(k, n, 32)
         for social in (True, False):
             gen.use_social = social
-            got = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision="fp16x2p")
+            got = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision=PAIR_PRECISION)
             old = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision="fp16x2")
             torch.cuda.synchronize()
             if k * n <= 2000:
@@ -57,7 +60,8 @@ def bench_case(scenes=16384, agents=8, k=20, reps=5):
     from socialways_b200 import ops
     outs = {}
     for name, fn in (("tcx", lambda o: ops.decode_tcx(*pk["tcx"], h, c, pooled, noise, x_last, 12, out=o)),
-                     ("tcx2", lambda o: ops.decode_tcx2(*pk["tcx2"], h, c, pooled, noise, x_last, 12, out=o))):
+                     ("tcx2", lambda o: ops.decode_tcx2(*pk["tcx2"], h, c, pooled, noise, x_last, 12, out=o)),
+                     ("tcx3", lambda o: ops.decode_tcx2(*pk["tcx2"], h, c, pooled, noise, x_last, 12, out=o, pingpong=True))):
         out = torch.empty(k, n, 12, 4, device="cuda")
         fn(out)
         torch.cuda.synchronize()
@@ -70,8 +74,9 @@ def bench_case(scenes=16384, agents=8, k=20, reps=5):
         ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
         outs[name] = out
         print(f"{name}: {min(ms):.3f} ms (median {sorted(ms)[len(ms) // 2]:.3f})  -> {k * n / min(ms) / 1e3:.1f} M traj/s", flush=True)
-    print("max |tcx2 - tcx| on the bench workload:", (outs["tcx2"] - outs["tcx"]).abs().max().item(),
-          " finite:", bool(torch.isfinite(outs["tcx2"]).all()))
+    for name in ("tcx2", "tcx3"):
+        print(f"max |{name} - tcx| on the bench workload:", (outs[name] - outs["tcx"]).abs().max().item(),
+              " finite:", bool(torch.isfinite(outs[name]).all()))
 
 
 if __name__ == "__main__":

@@ -21,30 +21,9 @@
 // Synchronisation: the threads of both CTAs signal "operands written" per warp on the LEADER CTA's `ready` mbarrier (remote
 // arrive, release at cluster scope); the leader's issuing warp waits for it, issues, and commits with a multicast arrive on
 // the `full` mbarriers of both CTAs.
-#include <cuda.h>
-#include <cuda_fp16.h>
-
-#include "sw_common.cuh"
-#include "sw_umma.cuh"
+#include "decode_pair.cuh"
 
 namespace sw {
-
-constexpr int P_ROWS = 128;
-constexpr int P_THREADS = 512;
-constexpr int P_SLOT_THREADS = 256;
-constexpr int P_L2NL = 40;            // layer-2 B rows per CTA (N = 80)
-// per-rank fp16 weight image (elements); every matrix canonical [K/8][local rows][8]
-constexpr int PW_W1H_HI = 0, PW_W1H_LO = 5120,                                   // [8][80][8]
-              PW_W2_HI = 10240, PW_W2_LO = PW_W2_HI + 20 * P_L2NL * 8,           // [20][40][8]
-              PW_WHH = PW_W2_LO + 20 * P_L2NL * 8,                               // [half][hi|lo][8][64][8]
-              PW_WXK = PW_WHH + 16384,                                           // [half][2][64][8]  x-feedback K block
-              PW_WSZ_HI = PW_WXK + 2048, PW_WSZ_LO = PW_WSZ_HI + 7680,           // [12][80][8]  hoisted rows of W1 (S, z)
-              PW_TOTAL = PW_WSZ_LO + 7680;
-constexpr int PF_B1 = 0, PF_B2 = 160, PF_B34 = 240, PF_W34 = 256, PF_TOTAL = 256 + 160;
-constexpr uint32_t PC_R1 = 0, PC_R2 = 160, PC_AHI = 160, PC_ALO = 208;
-constexpr uint32_t PFMT = 0;          // fp16
-// c1 scratch: [cta][slot][10 K blocks][4][128 rows] float4
-constexpr int P_SCRATCH_F4_PER_SLOT = 10 * 4 * P_ROWS;
 
 struct Tcx2Smem {
     float zst[2][P_ROWS * SW_Z];             // noise block of each slot's tile (TMA, 128-byte swizzle; 1024-byte aligned)
@@ -60,28 +39,7 @@ struct Tcx2Smem {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void psplit2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    const __half2 h2 = __floats2half2_rn(a, b);
-    const float2 back = __half22float2(h2);
-    const __half2 l2 = __floats2half2_rn(a - back.x, b - back.y);
-    hi = *reinterpret_cast<const uint32_t*>(&h2);
-    lo = *reinterpret_cast<const uint32_t*>(&l2);
-}
 __device__ __forceinline__ void slot_sync(int slot) { asm volatile("bar.sync %0, %1;" :: "r"(slot + 1), "n"(P_SLOT_THREADS) : "memory"); }
-
-template <int NL, int KB>
-__device__ __forceinline__ void pmma3_ss(uint32_t d, const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo,
-                                         bool leader) {
-    pmma_ss<NL, KB>(d, a_hi, b_hi, PFMT, false, leader);
-    pmma_ss<NL, KB>(d, a_hi, b_lo, PFMT, true, leader);
-    pmma_ss<NL, KB>(d, a_lo, b_hi, PFMT, true, leader);
-}
-template <int NL, int KB, int A_STRIDE>
-__device__ __forceinline__ void pmma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const __half* b_hi, const __half* b_lo, bool leader) {
-    pmma_ts<NL, KB, A_STRIDE>(d, a_hi, b_hi, PFMT, false, leader);
-    pmma_ts<NL, KB, A_STRIDE>(d, a_hi, b_lo, PFMT, true, leader);
-    pmma_ts<NL, KB, A_STRIDE>(d, a_lo, b_hi, PFMT, true, leader);
-}
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][32] fp32, box 128 x 32, 128-byte swizzle */,
@@ -406,28 +364,6 @@ decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
 }
 
 }  // namespace sw
-
-// cuTensorMapEncodeTiled through the runtime's driver-entry-point lookup (no link-time dependency on libcuda)
-static int encode_noise_map2(CUtensorMap* map, const float* noise, long long n_rows) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static EncodeFn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        SW_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-        if (q != cudaDriverEntryPointSuccess || !fn) return SW_ERR_UNSUPPORTED;
-        encode = (EncodeFn)fn;
-    }
-    const cuuint64_t dims[2] = {(cuuint64_t)SW_Z, (cuuint64_t)n_rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)SW_Z * 4};
-    const cuuint32_t box[2] = {(cuuint32_t)SW_Z, (cuuint32_t)sw::P_ROWS}, elem[2] = {1, 1};
-    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(noise), dims, strides, box, elem,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? SW_OK : SW_ERR_ARG;
-}
 
 static int tcx2_grid(long long tiles, int sm_count) {
     const long long units = (tiles + 1) / 2;            // two tiles (one per CTA of a pair) per unit, two unit slots per pair

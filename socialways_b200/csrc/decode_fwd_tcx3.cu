@@ -1,0 +1,502 @@
+// fp32-faithful tensor-core decode kernel, two 128-row tiles per SM in PING-PONG between the tensor pipe and the CUDA cores.
+//
+// Same computation, arithmetic, weight image, TMEM column map and c1 scratch as decode_fwd_tcx2.cu (the loop of predict(),
+// reference train.py:418-430, fp16 hi/lo split operands, 3 MMAs per product, fp32 accumulation in TMEM, CTA pairs issuing
+// cta_group::2 MMAs so that each SM holds half of every weight matrix and two tile slots of 256 TMEM columns).  What changes is
+// who works on what.  decode_fwd_tcx2 gives each slot its own 8 warps; ncu showed the two slots falling into step with each
+// other (both in the MUFU-bound cell update at the same time, both waiting for their MMAs at the same time): 32 % of all warp
+// samples sat on MMA-completion barriers and the tensor pipe was 36 % active, no better than one tile per SM.  Here
+//   * ALL 16 epilogue warps (thread = (TMEM lane = row, column quarter), as in decode_fwd_tcx.cu) serve BOTH slots, alternating
+//     slot 0 / slot 1 phase by phase: layer-1 epilogue (0), (1), layer-2 epilogue + velocity (0), (1), cell update (0), (1).
+//     While the warps are in slot 1's phase, the tensor pipe runs the MMAs slot 0's next phase waits for, and vice versa --
+//     every MMA group is shorter than the epilogue phase it hides under, so the warps (almost) never wait;
+//   * a 17th warp of the leader CTA does nothing but issue: it walks the same static schedule, waits for the "operands written"
+//     arrivals of a slot (16 warps x 2 CTAs), issues that slot's MMAs for both CTAs and commits to the slot's `full` barriers;
+//   * quarter -> work assignment is mirrored between the slots (layer-1 K blocks 3,3,2,2 in slot 0 and 2,2,3,3 in slot 1, the
+//     row finish on quarter 2 / quarter 1), so every warp carries the same load over a slot pair.
+#include <type_traits>
+
+#include "decode_pair.cuh"
+
+namespace sw {
+
+constexpr int Q_EPI = 512;            // epilogue threads (warps 0..15)
+constexpr int Q_THREADS = 640;        // + the issuing warp's warpgroup (register file = 4 x 16 K: a 17th warp alone would cap
+                                      //   every thread at 96 registers; setmaxnreg moves the idle group's registers over)
+
+struct Tcx3Smem {
+    float zst[2][P_ROWS * SW_Z];             // noise block of each slot's tile (TMA, 128-byte swizzle; 1024-byte aligned)
+    __half w[PW_TOTAL];                      // this rank's half of every weight matrix (113 664 B)
+    __half h[2][2][8 * P_ROWS * 8];          // [slot][hi|lo][8 chunks][128][8]
+    __half xk[2][2 * P_ROWS * 8];            // [slot] x-feedback A operand, one K block
+    float f32[PF_TOTAL];
+    float vpart[2][8 * P_ROWS];              // [slot][quarter * 2 + component][row]: partial velocities
+    unsigned long long ready[2];             // operands written: 32 warp arrivals (16 warps x 2 CTAs), used in the leader CTA
+    unsigned long long ready_x[2];           // x block written: 8 arrivals (the 4 finishing warps x 2 CTAs)
+    unsigned long long full[2][3];           // MMA completion: hoist / L1 / L2 | gates half 0 | gates half 1
+    unsigned long long bar_z[2];             // TMA: the slot's noise block
+    unsigned long long bar_w;                // TMA: weights
+    uint32_t tmem_base;
+};
+static_assert(sizeof(Tcx3Smem) <= 227 * 1024, "shared memory of one CTA");
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" :: "n"(Q_EPI) : "memory"); }
+__device__ __forceinline__ void wait_full3(unsigned long long* bar, uint32_t parity) {
+    mbar_wait(bar, parity);
+    ptx::tcgen05_fence_after_thread_sync();
+}
+
+// layer-1 epilogue of NKB K blocks: a1 = lrelu(acc + c1) -> hi|lo fp16 written in place (hi -> columns +0..7, lo -> +8..15 of
+// the 16 accumulator columns the thread has just read); c1 (+ b1) comes from this thread's scratch lines, one block ahead
+template <int NKB>
+__device__ __forceinline__ void l1_epilogue(uint32_t t_acc, const float4* sc, unsigned long long* bar, uint32_t parity) {
+    float4 cn[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) cn[q] = __ldcg(sc + q * P_ROWS);
+    wait_full3(bar, parity);
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb) {
+        const float4 cc[4] = {cn[0], cn[1], cn[2], cn[3]};
+        if (kb + 1 < NKB) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cn[q] = __ldcg(sc + ((kb + 1) * 4 + q) * P_ROWS);
+        }
+        uint32_t acc[16], pc[16];
+        tmem_ld<16>(t_acc + kb * 16, acc);
+        ptx::tcgen05_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float y0 = __uint_as_float(acc[4 * q]) + cc[q].x, y1 = __uint_as_float(acc[4 * q + 1]) + cc[q].y;
+            const float y2 = __uint_as_float(acc[4 * q + 2]) + cc[q].z, y3 = __uint_as_float(acc[4 * q + 3]) + cc[q].w;
+            psplit2(lrelu02(y0), lrelu02(y1), pc[2 * q], pc[8 + 2 * q]);
+            psplit2(lrelu02(y2), lrelu02(y3), pc[2 * q + 1], pc[8 + 2 * q + 1]);
+        }
+        tmem_st<16>(t_acc + kb * 16, pc);
+    }
+    ptx::tcgen05_wait_st();
+}
+
+// c1 + b1 of NKB K blocks: TMEM -> this thread's scratch lines (once per tile)
+template <int NKB>
+__device__ __forceinline__ void c1_to_scratch(uint32_t t_acc, float4* sc, const float* __restrict__ b1) {
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb) {
+        uint32_t v[16];
+        tmem_ld<16>(t_acc + kb * 16, v);
+        ptx::tcgen05_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 b = *reinterpret_cast<const float4*>(b1 + kb * 16 + 4 * q);
+            __stcg(sc + (kb * 4 + q) * P_ROWS, make_float4(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y,
+                                                          __uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w));
+        }
+    }
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1)
+decode_fwd_tcx3_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][32] fp32, box 128 x 32, 128-byte swizzle */,
+                       const __half* __restrict__ w16 /* [2 ranks][PW_TOTAL] */, const float* __restrict__ wf32,
+                       const float* __restrict__ h0, const float* __restrict__ c0, const float* __restrict__ pooled,
+                       const float* __restrict__ x_last, float* __restrict__ out, float4* __restrict__ scratch,
+                       int* __restrict__ status, int n_agents, long long n_rows, int n_next, int n_tiles) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    Tcx3Smem& s = *reinterpret_cast<Tcx3Smem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lq = warp & 3, cq = (warp >> 2) & 3;  // TMEM lane quarter (= warp % 4), column quarter
+    const int r = lq * 32 + lane;
+    const uint32_t cta = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const bool leader = lane == 0;
+    const int n_units = (n_tiles + 1) >> 1;         // work unit = two consecutive tiles, one per CTA of the pair
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(&s.tmem_base)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    auto prefetch_noise = [&](int sl, int tile) {
+        mbar_expect_tx(&s.bar_z[sl], P_ROWS * SW_Z * 4);
+        tma_load_2d(s.zst[sl], &noise_map, 0, tile * P_ROWS, &s.bar_z[sl]);
+    };
+    if (tid == 0) {
+        for (int sl = 0; sl < 2; ++sl) {
+            ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.ready[sl]), 32);
+            ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.ready_x[sl]), 8);
+            for (int j = 0; j < 3; ++j) ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.full[sl][j]), 1);
+            ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar_z[sl]), 1);
+        }
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar_w), 1);
+        ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
+        constexpr uint32_t W_BYTES = PW_TOTAL * 2, W_PIECE = W_BYTES / 4, F_BYTES = PF_TOTAL * 4;
+        static_assert(W_PIECE % 16 == 0 && F_BYTES % 16 == 0, "bulk copies move multiples of 16 bytes");
+        mbar_expect_tx(&s.bar_w, W_BYTES + F_BYTES);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(w16 + (size_t)cta * PW_TOTAL);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            tma_load_1d(reinterpret_cast<unsigned char*>(s.w) + q * W_PIECE, src + q * W_PIECE, W_PIECE, &s.bar_w);
+        tma_load_1d(s.f32, wf32, F_BYTES, &s.bar_w);
+        for (int sl = 0; sl < 2; ++sl) {
+            const int u = 2 * pair + sl, tile = 2 * u + (int)cta;
+            if (u < n_units && tile < n_tiles) prefetch_noise(sl, tile);
+        }
+    }
+    ptx::tcgen05_fence_before_thread_sync();
+    __syncthreads();
+    cluster_sync_all();                     // the peer's barriers exist before anything arrives on them
+    ptx::tcgen05_fence_after_thread_sync();
+    mbar_wait(&s.bar_w, 0u);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0);
+
+    if (warp >= 16) {
+        // =========================== the issuing warp (leader CTA only): the static MMA schedule ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (cta == 0 && warp == 16) {
+            uint32_t ph_r = 0, ph_x = 0;            // bit sl = parity of the slot's ready / ready_x barrier
+            auto wait_ready = [&](int sl) {
+                mbar_wait(&s.ready[sl], (ph_r >> sl) & 1u); ph_r ^= 1u << sl;
+                ptx::tcgen05_fence_after_thread_sync();
+            };
+            // Every group: the whole warp waits for the arrivals, ONE elected lane issues the MMAs and the commit back to back
+            // (sw_umma.cuh: the lane-predicated forms cost ~15 instructions per MMA, which made this warp the bottleneck).
+            auto issue_hoist = [&](int sl) {
+                const uint32_t ts = tmem + (uint32_t)(sl * 256);
+                wait_ready(sl);         // c1 = [S ; z] . W1[S,z rows]^T -> [0,160)
+                if (elect_one()) {
+                    pmma3_ts1<80, 6, 8>(ts + PC_R1, ts + PC_AHI, ts + PC_ALO, s.w + PW_WSZ_HI, s.w + PW_WSZ_LO);
+                    umma1_commit_pair(&s.full[sl][0]);
+                }
+                __syncwarp();
+            };
+            auto issue_l1 = [&](int sl) {
+                const uint32_t ts = tmem + (uint32_t)(sl * 256);
+                wait_ready(sl);         // layer 1: h (K = 64, smem) -> [0,160)
+                if (elect_one()) {
+                    pmma3_ss1<80, 4>(ts + PC_R1, s.h[sl][0], s.h[sl][1], s.w + PW_W1H_HI, s.w + PW_W1H_LO);
+                    umma1_commit_pair(&s.full[sl][0]);
+                }
+                __syncwarp();
+            };
+            auto issue_l2 = [&](int sl, bool feed_back) {
+                const uint32_t ts = tmem + (uint32_t)(sl * 256);
+                wait_ready(sl);         // layer 2: a1 (K = 160, TMEM) -> [160,240); the h part of gates half 0 queued behind it
+                if (elect_one()) {
+                    pmma3_ts1<P_L2NL, 10, 16>(ts + PC_R2, ts + PC_R1, ts + PC_R1 + 8, s.w + PW_W2_HI, s.w + PW_W2_LO);
+                    umma1_commit_pair(&s.full[sl][0]);
+                    if (feed_back) pmma3_ss1<64, 4>(ts, s.h[sl][0], s.h[sl][1], s.w + PW_WHH, s.w + PW_WHH + 4096);
+                }
+                __syncwarp();
+            };
+            auto issue_x = [&](int sl) {
+                const uint32_t ts = tmem + (uint32_t)(sl * 256);
+                mbar_wait(&s.ready_x[sl], (ph_x >> sl) & 1u); ph_x ^= 1u << sl;
+                ptx::tcgen05_fence_after_thread_sync();
+                if (elect_one()) {
+                    pmma1_ss<64, 1>(ts, s.xk[sl], s.w + PW_WXK, PFMT, true);
+                    umma1_commit_pair(&s.full[sl][1]);
+                    pmma3_ss1<64, 4>(ts + 128, s.h[sl][0], s.h[sl][1], s.w + PW_WHH + 8192, s.w + PW_WHH + 8192 + 4096);
+                    pmma1_ss<64, 1>(ts + 128, s.xk[sl], s.w + PW_WXK + 1024, PFMT, true);
+                    umma1_commit_pair(&s.full[sl][2]);
+                }
+                __syncwarp();
+            };
+            for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
+                const int n_act = ub + 1 < n_units ? 2 : 1;
+#pragma unroll 1
+                for (int sl = 0; sl < n_act; ++sl) issue_hoist(sl);
+#pragma unroll 1
+                for (int sl = 0; sl < n_act; ++sl) issue_l1(sl);       // layer 1 of step 0
+                // Step loop.  The slots run HALF A STEP apart (slot 1 behind): the epilogue warps visit
+                //   L1(0,t)  cell(1,t-1)  L2(0,t)  L1(1,t)  cell(0,t)  L2(1,t)
+                // so that the long MMA group (layer 2 + the h part of gates half 0: ~2.5 K clk) of one slot runs under the long
+                // epilogue phase (the cell update, ~5 K clk) of the other.  This warp issues in the order the arrivals come:
+                // one rolled loop over the six groups of a step, slot = e & 1, group = e % 3.
+#pragma unroll 1
+                for (int t = 0; t < n_next; ++t) {
+                    const bool feed_back = t + 1 < n_next;
+#pragma unroll 1
+                    for (int e = 0; e < 6; ++e) {
+                        const int sl = e & 1, kind = e % 3;
+                        if (sl >= n_act) continue;
+                        if (kind == 0) issue_l2(sl, feed_back);
+                        else if (kind == 1) { if (sl == 1 ? t > 0 : feed_back) issue_l1(sl); }
+                        else if (feed_back) issue_x(sl);
+                    }
+                }
+            }
+        }
+    } else {
+        // =========================== the 16 epilogue warps ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);           // this thread's lane, slot 0, column 0
+        uint32_t ph_l[2] = {0, 0}, ph_g[2] = {0, 0}, ph_z[2] = {0, 0};
+        // every warp: "my operand writes are done" -> one arrival on the leader CTA's barrier
+        auto arrive = [&](unsigned long long* bar) {
+            ptx::tcgen05_fence_before_thread_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar, 0);
+        };
+        // quarter -> layer-1 K blocks: slot 0: quarters 0,1 own 3 blocks, 2,3 own 2; slot 1 mirrored
+        int kb0[2], fin[2];
+        {
+            const int q0 = cq, q1 = 3 - cq;
+            kb0[0] = q0 < 2 ? 3 * q0 : 6 + 2 * (q0 - 2);
+            kb0[1] = q1 < 2 ? 3 * q1 : 6 + 2 * (q1 - 2);
+            fin[0] = cq == 2;               // the quarter that finishes the rows of the slot (velocity, integration, emit)
+            fin[1] = cq == 1;
+        }
+        const bool three[2] = {cq < 2, cq >= 2};
+
+        for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
+            const int n_act = ub + 1 < n_units ? 2 : 1;
+            bool has_tile[2], valid[2];
+            long long row0[2];
+            int abase[2], agent[2];
+            float4 sreg[2][4], hreg[2][2][2];
+            float2 xl = make_float2(0.f, 0.f);
+            // ---------------- tile prologue, both slots: every global load coalesced and issued up front ----------------
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                const int tile = 2 * (ub + sl) + (int)cta;
+                has_tile[sl] = sl < n_act && tile < n_tiles;              // the odd last unit has one tile only
+                row0[sl] = (long long)tile * P_ROWS;
+                valid[sl] = has_tile[sl] && row0[sl] + r < n_rows;
+                abase[sl] = has_tile[sl] ? (int)(row0[sl] % n_agents) : 0;
+                agent[sl] = valid[sl] ? (abase[sl] + r) % n_agents : 0;
+                if (sl >= n_act) continue;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {                             // S tile [128][16 pieces]: piece g = tid + 512 i
+                    const int g = tid + i * Q_EPI, row = g >> 4, piece = g & 15;
+                    sreg[sl][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (pooled && has_tile[sl] && row0[sl] + row < n_rows)
+                        sreg[sl][i] = __ldg(reinterpret_cast<const float4*>(pooled + (size_t)((abase[sl] + row) % n_agents) * SW_H) + piece);
+                }
+                const int hrow = warp * 8 + (lane & 7);                   // h0 items: (row, chunk = (lane >> 3) + 4 i)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    hreg[sl][i][0] = hreg[sl][i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_tile[sl] && row0[sl] + hrow < n_rows) {
+                        const float4* src = reinterpret_cast<const float4*>(h0 + (size_t)((abase[sl] + hrow) % n_agents) * SW_H) + ((lane >> 3) + 4 * i) * 2;
+                        hreg[sl][i][0] = __ldg(src);
+                        hreg[sl][i][1] = __ldg(src + 1);
+                    }
+                }
+                if (fin[sl] && valid[sl]) xl = __ldg(reinterpret_cast<const float2*>(x_last + (size_t)agent[sl] * 4));
+            }
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                if (sl >= n_act) continue;
+                float4* sS = reinterpret_cast<float4*>(s.h[sl][0]);       // [128 rows][16 pieces], piece' = piece ^ (row & 7); 32 KB = h hi|lo
+                const float4* sZ = reinterpret_cast<const float4*>(s.zst[sl]);   // [128 rows][8 pieces], TMA swizzle: piece' = piece ^ (row & 7)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int g = tid + i * Q_EPI, row = g >> 4, piece = g & 15;
+                    sS[row * 16 + (piece ^ (row & 7))] = sreg[sl][i];
+                }
+                if (has_tile[sl]) { mbar_wait(&s.bar_z[sl], ph_z[sl]); ph_z[sl] ^= 1; }
+                epi_sync();
+                // [S ; z] (K = 96 = 24 pieces): this thread owns pieces 6 cq .. 6 cq + 5 of its row -> hi|lo TMEM A operand
+                uint32_t hi[12], lo[12];
+#pragma unroll
+                for (int e = 0; e < 6; ++e) {
+                    const int piece = cq * 6 + e;
+                    float4 v;
+                    if (piece < 16) v = sS[r * 16 + (piece ^ (r & 7))];
+                    else            v = has_tile[sl] ? sZ[r * 8 + ((piece - 16) ^ (r & 7))] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    psplit2(v.x, v.y, hi[2 * e], lo[2 * e]);
+                    psplit2(v.z, v.w, hi[2 * e + 1], lo[2 * e + 1]);
+                }
+                const uint32_t tls = tl + (uint32_t)(sl * 256);
+                tmem_st<12>(tls + PC_AHI + cq * 12, hi);
+                tmem_st<12>(tls + PC_ALO + cq * 12, lo);
+                ptx::tcgen05_wait_st();
+                epi_sync();                                               // staging consumed: h region and noise buffer are free
+                {   // next tile's noise block: 12 steps ahead of its use
+                    const int un = ub + sl + 2 * n_pairs, tn = 2 * un + (int)cta;
+                    if (tid == 0 && un < n_units && tn < n_tiles) prefetch_noise(sl, tn);
+                }
+                const int hrow = warp * 8 + (lane & 7);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {                             // h0 -> hi|lo operand chunks [chunk][row][8]
+                    uint32_t hh[4], ll[4];
+                    psplit2(hreg[sl][i][0].x, hreg[sl][i][0].y, hh[0], ll[0]);
+                    psplit2(hreg[sl][i][0].z, hreg[sl][i][0].w, hh[1], ll[1]);
+                    psplit2(hreg[sl][i][1].x, hreg[sl][i][1].y, hh[2], ll[2]);
+                    psplit2(hreg[sl][i][1].z, hreg[sl][i][1].w, hh[3], ll[3]);
+                    const size_t off = ((size_t)((lane >> 3) + 4 * i) * P_ROWS + hrow) * 8;
+                    *reinterpret_cast<uint4*>(s.h[sl][0] + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                    *reinterpret_cast<uint4*>(s.h[sl][1] + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                }
+                ptx::fence_proxy_async(ptx::space_shared);
+                arrive(&s.ready[sl]);                                     // -> hoist MMAs of the slot
+            }
+            // cell state of this thread's units: c[sl][0..7] = units 8 cq .. (gates half 0), c[sl][8..15] = units 32 + 8 cq .. (half 1)
+            float c[2][16];
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = valid[sl] ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent[sl] * SW_H + (q >> 1) * 32 + cq * 8) + (q & 1))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                    c[sl][4 * q] = v.x; c[sl][4 * q + 1] = v.y; c[sl][4 * q + 2] = v.z; c[sl][4 * q + 3] = v.w;
+                }
+            float p0 = xl.x, p1 = xl.y;                                   // state of the rows this thread finishes (one slot at most)
+            bool out_of_range = false;
+            float4* sc[2];
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                sc[sl] = scratch + ((size_t)blockIdx.x * 2 + sl) * P_SCRATCH_F4_PER_SLOT + (size_t)kb0[sl] * 4 * P_ROWS + r;
+                if (sl >= n_act) continue;
+                const uint32_t ta = tl + (uint32_t)(sl * 256) + PC_R1 + kb0[sl] * 16;
+                wait_full3(&s.full[sl][0], ph_l[sl]); ph_l[sl] ^= 1;      // c1 + b1 -> scratch (the K blocks this thread re-reads)
+                if (three[sl]) c1_to_scratch<3>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
+                else           c1_to_scratch<2>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
+                arrive(&s.ready[sl]);                                     // -> layer 1 of step 0
+            }
+
+            // ---------------- layer 1 epilogue: a1 = lrelu(acc + c1) -> hi|lo in place ----------------
+            auto phase_l1 = [&](auto slc) {
+                constexpr int sl = decltype(slc)::value;
+                const uint32_t ta = tl + (uint32_t)(sl * 256) + PC_R1 + kb0[sl] * 16;
+                if (three[sl]) l1_epilogue<3>(ta, sc[sl], &s.full[sl][0], ph_l[sl]);
+                else           l1_epilogue<2>(ta, sc[sl], &s.full[sl][0], ph_l[sl]);
+                ph_l[sl] ^= 1;
+                arrive(&s.ready[sl]);                                     // -> layer 2 (+ h part of gates half 0)
+            };
+            // ---------------- layer-2 epilogue + folded layers 3+4 (80 -> 2), row finish ----------------
+            auto phase_l2 = [&](auto slc, int t, bool feed_back) {
+                constexpr int sl = decltype(slc)::value;
+                wait_full3(&s.full[sl][0], ph_l[sl]); ph_l[sl] ^= 1;
+                float v0 = 0.0f, v1 = 0.0f;
+                {
+                    uint32_t acc[20];
+                    tmem_ld<20>(tl + (uint32_t)(sl * 256) + PC_R2 + cq * 20, acc);
+                    ptx::tcgen05_wait_ld();
+                    const float4* b2 = reinterpret_cast<const float4*>(s.f32 + PF_B2 + cq * 20);
+                    const float4* w34 = reinterpret_cast<const float4*>(s.f32 + PF_W34 + cq * 40);
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const float4 b = b2[j], wa = w34[2 * j], wb = w34[2 * j + 1];
+                        const float y0 = lrelu02(__uint_as_float(acc[4 * j]) + b.x), y1 = lrelu02(__uint_as_float(acc[4 * j + 1]) + b.y);
+                        const float y2 = lrelu02(__uint_as_float(acc[4 * j + 2]) + b.z), y3 = lrelu02(__uint_as_float(acc[4 * j + 3]) + b.w);
+                        v0 = fmaf(y0, wa.x, v0); v1 = fmaf(y0, wa.y, v1);
+                        v0 = fmaf(y1, wa.z, v0); v1 = fmaf(y1, wa.w, v1);
+                        v0 = fmaf(y2, wb.x, v0); v1 = fmaf(y2, wb.y, v1);
+                        v0 = fmaf(y3, wb.z, v0); v1 = fmaf(y3, wb.w, v1);
+                    }
+                }
+                if (!fin[sl]) { s.vpart[sl][(cq * 2) * P_ROWS + r] = v0; s.vpart[sl][(cq * 2 + 1) * P_ROWS + r] = v1; }
+                ptx::tcgen05_fence_before_thread_sync();
+                epi_sync();
+                if (fin[sl]) {      // velocity, integration, emit; (p, v) -> hi|lo x block of the gate MMA
+                    const float* vp = s.vpart[sl];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (q != (sl == 0 ? 2 : 1)) { v0 += vp[(q * 2) * P_ROWS + r]; v1 += vp[(q * 2 + 1) * P_ROWS + r]; }
+                    v0 += s.f32[PF_B34]; v1 += s.f32[PF_B34 + 1];
+                    p0 += v0; p1 += v1;
+                    out_of_range |= !(fmaxf(fmaxf(fabsf(p0), fabsf(p1)), fmaxf(fabsf(v0), fabsf(v1))) <= 6.0e4f);   // fp16 range guard
+                    if (feed_back) {
+                        uint32_t hp, lp, hv, lv;
+                        psplit2(p0, p1, hp, lp);
+                        psplit2(v0, v1, hv, lv);
+                        *reinterpret_cast<uint4*>(s.xk[sl] + (size_t)r * 8) = make_uint4(hp, hv, lp, lv);                      // k 0..7
+                        *reinterpret_cast<uint4*>(s.xk[sl] + (size_t)(P_ROWS + r) * 8) = make_uint4(hp, hv, 0x3C003C00u, 0u);  // k 8..15
+                        ptx::fence_proxy_async(ptx::space_shared);
+                        arrive(&s.ready_x[sl]);                           // -> x blocks of the gates, h part of half 1
+                    }
+                    if (valid[sl])
+                        *reinterpret_cast<float4*>(out + ((size_t)(row0[sl] + r) * n_next + t) * 4) = make_float4(p0, p1, v0, v1);
+                }
+            };
+            // ---------------- LSTM cell: 8 units of gates half 0 (units 8 cq ..), then 8 units of half 1 (units 32 + 8 cq ..) ----------------
+            auto phase_cell = [&](auto slc) {
+                constexpr int sl = decltype(slc)::value;
+                const uint32_t tls = tl + (uint32_t)(sl * 256);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if (half == 0) wait_full3(&s.full[sl][1], ph_g[sl]);
+                    uint32_t a[32];
+                    tmem_ld<32>(tls + half * 128 + cq * 32, a);
+                    ptx::tcgen05_wait_ld();
+                    float hv[8];
+#pragma unroll
+                    for (int uu = 0; uu < 8; uu += 2) {
+                        float g[2][4];
+#pragma unroll
+                        for (int w2 = 0; w2 < 2; ++w2)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) g[w2][q] = __uint_as_float(a[(uu + w2) * 4 + q]);
+                        lstm_cell_pair_prescaled(g[0], g[1], c[sl][half * 8 + uu], c[sl][half * 8 + uu + 1], hv[uu], hv[uu + 1]);
+                    }
+                    uint32_t hh[4], ll[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) psplit2(hv[2 * e], hv[2 * e + 1], hh[e], ll[e]);
+                    // h is an operand of the half-1 gate MMAs: nothing may overwrite it before they have completed
+                    if (half == 0) wait_full3(&s.full[sl][2], ph_g[sl]);
+                    const size_t off = ((size_t)(half * 4 + cq) * P_ROWS + r) * 8;
+                    *reinterpret_cast<uint4*>(s.h[sl][0] + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+                    *reinterpret_cast<uint4*>(s.h[sl][1] + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+                }
+                ph_g[sl] ^= 1;
+                ptx::fence_proxy_async(ptx::space_shared);
+                arrive(&s.ready[sl]);                                     // -> next step's layer 1
+            };
+            using S0 = std::integral_constant<int, 0>;
+            using S1 = std::integral_constant<int, 1>;
+            // The slots run half a step apart (slot 1 behind): the long MMA group of one slot (layer 2 + the h part of gates half
+            // 0, ~2.5 K clk) runs under the long epilogue phase of the other (the cell update, ~5 K clk); see the issuing warp.
+            for (int t = 0; t < n_next; ++t) {
+                const bool feed_back = t + 1 < n_next;
+                phase_l1(S0{});
+                if (n_act > 1 && t > 0) phase_cell(S1{});
+                phase_l2(S0{}, t, feed_back);
+                if (n_act > 1) phase_l1(S1{});
+                if (feed_back) phase_cell(S0{});
+                if (n_act > 1) phase_l2(S1{}, t, feed_back);
+            }
+            if (out_of_range && status) {
+                if ((fin[0] && valid[0]) || (fin[1] && valid[1])) atomicOr(status, 1);
+            }
+        }
+    }
+    ptx::tcgen05_fence_before_thread_sync();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(512u) : "memory");
+}
+
+}  // namespace sw
+
+static int tcx3_grid(long long tiles, int sm_count) {
+    const long long units = (tiles + 1) / 2;            // two tiles (one per CTA of a pair) per unit, two unit slots per pair
+    long long pairs = (units + 1) / 2;
+    if (pairs > sm_count / 2) pairs = sm_count / 2;
+    if (pairs < 1) pairs = 1;
+    return (int)(2 * pairs);
+}
+
+extern "C" long long sw_decode_tcx2_scratch_bytes(int sm_count);
+
+extern "C" int sw_decode_fwd_tcx3(const void* tcx2_w16, const float* tcx2_f32, const float* h0, const float* c0,
+                                  const float* pooled, const float* noise, const float* x_last, float* out, void* scratch,
+                                  long long scratch_bytes, int* status, int n_agents, int n_samples, int n_next, int sm_count,
+                                  void* stream) {
+    if (!tcx2_w16 || !tcx2_f32 || !h0 || !c0 || !noise || !x_last || !out || !scratch) return SW_ERR_ARG;
+    if (n_agents <= 0 || n_samples <= 0 || n_next <= 0 || sm_count < 2) return SW_ERR_ARG;
+    if (scratch_bytes < sw_decode_tcx2_scratch_bytes(sm_count) || ((uintptr_t)scratch & 15u) != 0) return SW_ERR_ARG;
+    const long long n_rows = (long long)n_agents * n_samples;
+    const long long tiles = (n_rows + sw::P_ROWS - 1) / sw::P_ROWS;
+    if (tiles > 0x3fffffffLL) return SW_ERR_UNSUPPORTED;
+    if (((uintptr_t)noise & 15u) != 0) return SW_ERR_ARG;
+    CUtensorMap noise_map;
+    const int rc = encode_noise_map2(&noise_map, noise, n_rows);
+    if (rc != SW_OK) return rc;
+    const int smem = (int)sizeof(sw::Tcx3Smem);
+    SW_SET_MAX_SMEM(sw::decode_fwd_tcx3_kernel, smem);
+    const int grid = tcx3_grid(tiles, sm_count);
+    sw::decode_fwd_tcx3_kernel<<<grid, sw::Q_THREADS, smem, (cudaStream_t)stream>>>(
+        noise_map, (const __half*)tcx2_w16, tcx2_f32, h0, c0, pooled, x_last, out, (float4*)scratch, status, n_agents, n_rows, n_next,
+        (int)tiles);
+    SW_CUDA_TRY(cudaGetLastError());
+    return SW_OK;
+}

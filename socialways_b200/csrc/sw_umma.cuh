@@ -172,6 +172,49 @@ __device__ __forceinline__ void pmma_ts(uint32_t d_tmem, uint32_t a_tmem, const 
         umma_issue_ts_pair(d_tmem, a_tmem + kb * A_STRIDE, bd + (uint64_t)(kb * 2 * NL), idesc, accumulate_first || kb > 0, leader);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Single-thread issue forms: called INSIDE `if (elect_one()) { ... }` by the one elected lane -- no per-instruction
+// predicate, so ptxas emits the MMAs back to back from uniform registers (the lane-predicated forms above compile to an
+// ELECT / BRA.U.ANY loop around every UTCHMMA, ~15 instructions per MMA: enough to make ONE issuing warp the bottleneck of
+// a kernel whose MMAs take 57-128 clk each).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void umma1_commit_pair(unsigned long long* bar) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(addr), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma1_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma1_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int NL, int KB, typename T>
+__device__ __forceinline__ void pmma1_ss(uint32_t d_tmem, const T* a, const T* b, uint32_t ab_format, bool accumulate_first) {
+    const uint32_t idesc = umma_idesc_pair(2 * NL, ab_format);
+    const uint64_t ad = umma_desc(a, 128 * 16, 128), bd = umma_desc(b, NL * 16, 128);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+        umma1_ss_pair(d_tmem, ad + (uint64_t)(kb * 2 * 128), bd + (uint64_t)(kb * 2 * NL), idesc, (accumulate_first || kb > 0) ? 1u : 0u);
+}
+template <int NL, int KB, int A_STRIDE = 8, typename T>
+__device__ __forceinline__ void pmma1_ts(uint32_t d_tmem, uint32_t a_tmem, const T* b, uint32_t ab_format, bool accumulate_first) {
+    const uint32_t idesc = umma_idesc_pair(2 * NL, ab_format);
+    const uint64_t bd = umma_desc(b, NL * 16, 128);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+        umma1_ts_pair(d_tmem, a_tmem + kb * A_STRIDE, bd + (uint64_t)(kb * 2 * NL), idesc, (accumulate_first || kb > 0) ? 1u : 0u);
+}
+
 // TMEM load / store of NCOLS consecutive 32-bit columns of the calling thread's lane (32x32b shape),
 // decomposed into the power-of-two instruction widths.
 template <int NCOLS>

@@ -307,9 +307,11 @@ def decode_tcx2_scratch(device):
     return _TCX2_SCRATCH[key]
 
 
-def decode_tcx2(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, status=None, scratch=None):
-    """sw_decode_fwd_tcx2: the fp16 hi/lo split tcgen05 decode kernel with two tiles in flight per SM (CTA pairs,
-    cta_group::2); same inputs, outputs and arithmetic as decode_tcx.  Packs from packing.pack_decoder_tcx2."""
+def decode_tcx2(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, status=None, scratch=None, pingpong=False):
+    """sw_decode_fwd_tcx2 / sw_decode_fwd_tcx3 (pingpong=True): the fp16 hi/lo split tcgen05 decode kernel with two tiles in
+    flight per SM (CTA pairs, cta_group::2); same inputs, outputs and arithmetic as decode_tcx.  Packs from
+    packing.pack_decoder_tcx2.  tcx2: each tile slot has its own 8 warps; tcx3: all 16 warps alternate between the slots and
+    a dedicated warp issues the MMAs."""
     noise = _f32(noise)
     k, n, z = noise.shape
     if z != Z or h0.shape != (n, H):
@@ -322,12 +324,13 @@ def decode_tcx2(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, statu
         out = torch.empty(k, n, n_next, 4, device=noise.device)
     if scratch is None:
         scratch = decode_tcx2_scratch(noise.device)
-    code = _lib.lib().sw_decode_fwd_tcx2(w16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(_f32(h0)), _lib.ptr(_f32(c0)),
-                                         _lib.ptr(None if pooled is None else _f32(pooled)), _lib.ptr(noise),
-                                         _lib.ptr(_f32(x_last)), _lib.ptr(out), scratch.data_ptr(), scratch.numel(),
-                                         None if status is None else status.data_ptr(), n, k, n_next,
-                                         sm_count(noise.device), _stream())
-    _lib.check(code, "sw_decode_fwd_tcx2")
+    name = "sw_decode_fwd_tcx3" if pingpong else "sw_decode_fwd_tcx2"
+    code = getattr(_lib.lib(), name)(w16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(_f32(h0)), _lib.ptr(_f32(c0)),
+                                     _lib.ptr(None if pooled is None else _f32(pooled)), _lib.ptr(noise),
+                                     _lib.ptr(_f32(x_last)), _lib.ptr(out), scratch.data_ptr(), scratch.numel(),
+                                     None if status is None else status.data_ptr(), n, k, n_next,
+                                     sm_count(noise.device), _stream())
+    _lib.check(code, name)
     return out
 
 

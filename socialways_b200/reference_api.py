@@ -341,7 +341,8 @@ class Generator(nn.Module):
                 raise ValueError("predict_k: give `noise`, or `seed` and `k` for device-side noise")
             sd, off = (seed if isinstance(seed, tuple) else (seed, 0))
             noise = ops.noise_uniform((k, n, self.noise_len), obsv_p.device, sd, off, out=noise_buf)
-        pair = precision == "fp16x2p"       # decode with two tiles in flight per SM (CTA pairs); otherwise = "fp16x2"
+        # "fp16x2p" / "fp16x2q": decode with two tiles in flight per SM (CTA pairs; q = ping-pong form); otherwise = "fp16x2"
+        pair, pingpong = precision in ("fp16x2p", "fp16x2q"), precision == "fp16x2q"
         if pair:
             precision = "fp16x2"
         if precision == "fp16x2":           # both recurrent kernels on the tensor cores (fp16 hi/lo split operands)
@@ -360,7 +361,7 @@ class Generator(nn.Module):
             return ops.decode_tc(pk["tc_w16"], pk["tc_f32"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
         if pair:
             return ops.decode_tcx2(*pk["tcx2"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out,
-                                   status=self._status_word(obsv_p.device))
+                                   status=self._status_word(obsv_p.device), pingpong=pingpong)
         if precision == "fp16x2":
             return ops.decode_tcx(*pk["tcx"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out,
                                   status=self._status_word(obsv_p.device))
