@@ -41,6 +41,10 @@ struct Tcx3Smem {
 static_assert(sizeof(Tcx3Smem) <= 227 * 1024, "shared memory of one CTA");
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" :: "n"(Q_EPI) : "memory"); }
+// partial-velocity exchange of a slot (named barrier 2 + slot): the 12 contributing warps only ARRIVE (they never block), the 4
+// finishing warps wait for all 16
+__device__ __forceinline__ void vel_arrive(int sl) { asm volatile("bar.arrive %0, %1;" :: "r"(2 + sl), "n"(Q_EPI) : "memory"); }
+__device__ __forceinline__ void vel_sync(int sl) { asm volatile("bar.sync %0, %1;" :: "r"(2 + sl), "n"(Q_EPI) : "memory"); }
 __device__ __forceinline__ void wait_full3(unsigned long long* bar, uint32_t parity) {
     mbar_wait(bar, parity);
     ptx::tcgen05_fence_after_thread_sync();
@@ -101,9 +105,13 @@ decode_fwd_tcx3_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                        int* __restrict__ status, int n_agents, long long n_rows, int n_next, int n_tiles) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Tcx3Smem& s = *reinterpret_cast<Tcx3Smem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int lq = warp & 3, cq = (warp >> 2) & 3;  // TMEM lane quarter (= warp % 4), column quarter
-    const int r = lq * 32 + lane;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int lq = warp & 3;                        // TMEM lane quarter (= warp % 4)
+    int lane = tid & 31, cq = (warp >> 2) & 3;      // column quarter
+    int r = lq * 32 + lane;
+    // opaque: kept in registers (ptxas otherwise re-derives them from S2R tid -- a ~25 clk special-register read -- at every use
+    // inside the step loop: 13 % of the layer-1 epilogue's stall samples)
+    asm volatile("" : "+r"(cq), "+r"(lane), "+r"(r));
     const uint32_t cta = cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const bool leader = lane == 0;
@@ -230,10 +238,15 @@ decode_fwd_tcx3_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
         const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);           // this thread's lane, slot 0, column 0
         uint32_t ph_l[2] = {0, 0}, ph_g[2] = {0, 0}, ph_z[2] = {0, 0};
         // every warp: "my operand writes are done" -> one arrival on the leader CTA's barrier
+        // (address of ready[0] in the LEADER CTA's shared memory, computed once: ready[1], ready_x[0], ready_x[1] follow at +8 ...)
+        uint32_t ready0_leader;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ready0_leader) : "r"((uint32_t)__cvta_generic_to_shared(&s.ready[0])), "r"(0));
         auto arrive = [&](unsigned long long* bar) {
             ptx::tcgen05_fence_before_thread_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(bar, 0);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];"
+                             :: "r"(ready0_leader + (uint32_t)((const char*)bar - (const char*)&s.ready[0])) : "memory");
         };
         // quarter -> layer-1 K blocks: slot 0: quarters 0,1 own 3 blocks, 2,3 own 2; slot 1 mirrored
         int kb0[2], fin[2];
@@ -384,10 +397,12 @@ decode_fwd_tcx3_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                         v0 = fmaf(y3, wb.z, v0); v1 = fmaf(y3, wb.w, v1);
                     }
                 }
-                if (!fin[sl]) { s.vpart[sl][(cq * 2) * P_ROWS + r] = v0; s.vpart[sl][(cq * 2 + 1) * P_ROWS + r] = v1; }
                 ptx::tcgen05_fence_before_thread_sync();
-                epi_sync();
-                if (fin[sl]) {      // velocity, integration, emit; (p, v) -> hi|lo x block of the gate MMA
+                if (!fin[sl]) {
+                    s.vpart[sl][(cq * 2) * P_ROWS + r] = v0; s.vpart[sl][(cq * 2 + 1) * P_ROWS + r] = v1;
+                    vel_arrive(sl);     // (bar.arrive orders the shared-memory writes above before the finishing warps' reads)
+                } else {            // velocity, integration, emit; (p, v) -> hi|lo x block of the gate MMA
+                    vel_sync(sl);
                     const float* vp = s.vpart[sl];
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
