@@ -19,8 +19,12 @@
 // [0,128) (queued behind the layer-2 MMAs, runs under the layer-2 epilogue), gates half 1 -> [128,256).  Tile prologue:
 // [160,256) holds the [S ; z] hi|lo A operand of the hoist, [0,160) its result.
 // Synchronisation: the threads of both CTAs signal "operands written" per warp on the LEADER CTA's `ready` mbarrier (remote
-// arrive, release at cluster scope); the leader's issuing warp waits for it, issues, and commits with a multicast arrive on
-// the `full` mbarriers of both CTAs.
+// arrive); the slot's ISSUING WARP -- warps 16 / 17 of the leader CTA, one per slot, which do nothing else -- waits for it,
+// one elected lane issues the slot's MMAs back to back and commits with a multicast arrive on the `full` mbarriers of both CTAs.
+// (First version: warp 0 of each slot issued, between its own epilogue work, through lane-predicated tcgen05.mma -- ptxas
+// wraps each of those in an ELECT / BRA.U.ANY loop, ~15 instructions per MMA, ~1.5 K instructions per step on ONE warp while
+// the slot's other 7 warps waited: 28 % of all warp samples sat on the MMA barriers.)  The issuing warps' warpgroup gives
+// its registers to the epilogue warps (setmaxnreg: 32 / 112).
 #include "decode_pair.cuh"
 
 namespace sw {
@@ -33,15 +37,20 @@ struct Tcx2Smem {
     float f32[PF_TOTAL];
     float vpart[2][2 * P_ROWS];              // [slot][component][row]: partial velocity of column half 1
     unsigned long long ready[2];             // operands written (16 warp arrivals: 8 warps x 2 CTAs; used in the leader CTA)
+    unsigned long long ready_x[2];           // x block written (8 arrivals: the 4 row-finishing warps x 2 CTAs)
     unsigned long long full[2][3];           // MMA completion: hoist / L1 / L2 | gates half 0 | gates half 1
     unsigned long long bar_z[2];             // TMA: the slot's noise block
     unsigned long long bar_w;                // TMA: weights
     uint32_t tmem_base;
 };
 
+constexpr int P_THREADS_ALL = P_THREADS + 128;   // + the issuing warps' warpgroup
 __device__ __forceinline__ void slot_sync(int slot) { asm volatile("bar.sync %0, %1;" :: "r"(slot + 1), "n"(P_SLOT_THREADS) : "memory"); }
+// partial-velocity exchange (named barrier 3 + slot): column half 1 only arrives, column half 0 (which finishes the rows) waits
+__device__ __forceinline__ void vel_arrive2(int slot) { asm volatile("bar.arrive %0, %1;" :: "r"(slot + 3), "n"(P_SLOT_THREADS) : "memory"); }
+__device__ __forceinline__ void vel_sync2(int slot) { asm volatile("bar.sync %0, %1;" :: "r"(slot + 3), "n"(P_SLOT_THREADS) : "memory"); }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS_ALL, 1)
 decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][32] fp32, box 128 x 32, 128-byte swizzle */,
                        const __half* __restrict__ w16 /* [2 ranks][PW_TOTAL] */, const float* __restrict__ wf32,
                        const float* __restrict__ h0, const float* __restrict__ c0, const float* __restrict__ pooled,
@@ -49,14 +58,15 @@ decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                        int* __restrict__ status, int n_agents, long long n_rows, int n_next, int n_tiles) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     Tcx2Smem& s = *reinterpret_cast<Tcx2Smem*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int slot = warp >> 3, w8 = warp & 7, st = tid & (P_SLOT_THREADS - 1);
-    const int lq = w8 & 3, hf = w8 >> 2;            // TMEM lane quarter (= warp % 4), column half
-    const int r = lq * 32 + lane;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int w8 = warp & 7, st = tid & (P_SLOT_THREADS - 1);
+    const int lq = w8 & 3;                          // TMEM lane quarter (= warp % 4)
+    int lane = tid & 31, slot = (warp >> 3) & 1, hf = w8 >> 2;      // tile slot, column half
+    int r = lq * 32 + lane;
+    // opaque: kept in registers (ptxas otherwise re-derives them from S2R tid, a ~25 clk special-register read, at every use)
+    asm volatile("" : "+r"(lane), "+r"(slot), "+r"(hf), "+r"(r));
     const uint32_t cta = cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const bool leader = lane == 0;
-    const bool issuer = cta == 0 && w8 == 0;        // warp that issues this slot's MMAs for BOTH CTAs
     const int n_units = (n_tiles + 1) >> 1;         // work unit = two consecutive tiles, one per CTA of the pair
 
     if (warp == 0) {
@@ -71,6 +81,7 @@ decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
     if (tid == 0) {
         for (int sl = 0; sl < 2; ++sl) {
             ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.ready[sl]), 16);
+            ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.ready_x[sl]), 8);
             for (int j = 0; j < 3; ++j) ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.full[sl][j]), 1);
             ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar_z[sl]), 1);
         }
@@ -95,10 +106,69 @@ decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
     ptx::tcgen05_fence_after_thread_sync();
     mbar_wait(&s.bar_w, 0u);
     const uint32_t tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0);
+    if (warp >= 16) {
+        // =========================== the issuing warps (leader CTA: warp 16 -> slot 0, warp 17 -> slot 1) ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+        if (cta == 0 && warp < 18) {
+            const int sl = warp - 16;
+            const uint32_t ts = tmem + (uint32_t)(sl * 256);
+            uint32_t ph_r = 0, ph_x = 0;
+            auto wait_ready = [&]() {
+                mbar_wait(&s.ready[sl], ph_r); ph_r ^= 1;
+                ptx::tcgen05_fence_after_thread_sync();
+            };
+            const __half* const h_hi = s.h[sl][0];
+            const __half* const h_lo = s.h[sl][1];
+            const __half* const xk = s.xk[sl];
+            for (int u = sl + 2 * pair; u < n_units; u += 2 * n_pairs) {
+                wait_ready();           // c1 = [S ; z] . W1[S,z rows]^T -> [0,160)
+                if (elect_one()) {
+                    pmma3_ts1<80, 6, 8>(ts + PC_R1, ts + PC_AHI, ts + PC_ALO, s.w + PW_WSZ_HI, s.w + PW_WSZ_LO);
+                    umma1_commit_pair(&s.full[sl][0]);
+                }
+                __syncwarp();
+                wait_ready();           // layer 1 of step 0
+                if (elect_one()) {
+                    pmma3_ss1<80, 4>(ts + PC_R1, h_hi, h_lo, s.w + PW_W1H_HI, s.w + PW_W1H_LO);
+                    umma1_commit_pair(&s.full[sl][0]);
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int t = 0; t < n_next; ++t) {
+                    const bool feed_back = t + 1 < n_next;
+                    wait_ready();       // layer 2: a1 (K = 160, TMEM) -> [160,240); the h part of gates half 0 queued behind it
+                    if (elect_one()) {
+                        pmma3_ts1<P_L2NL, 10, 16>(ts + PC_R2, ts + PC_R1, ts + PC_R1 + 8, s.w + PW_W2_HI, s.w + PW_W2_LO);
+                        umma1_commit_pair(&s.full[sl][0]);
+                        if (feed_back) pmma3_ss1<64, 4>(ts, h_hi, h_lo, s.w + PW_WHH, s.w + PW_WHH + 4096);
+                    }
+                    __syncwarp();
+                    if (!feed_back) break;
+                    mbar_wait(&s.ready_x[sl], ph_x); ph_x ^= 1;
+                    ptx::tcgen05_fence_after_thread_sync();
+                    if (elect_one()) {  // gates: x block of half 0 -> full[1]; half 1 (h part + x block) -> [128,256) -> full[2]
+                        pmma1_ss<64, 1>(ts, xk, s.w + PW_WXK, PFMT, true);
+                        umma1_commit_pair(&s.full[sl][1]);
+                        pmma3_ss1<64, 4>(ts + 128, h_hi, h_lo, s.w + PW_WHH + 8192, s.w + PW_WHH + 8192 + 4096);
+                        pmma1_ss<64, 1>(ts + 128, xk, s.w + PW_WXK + 1024, PFMT, true);
+                        umma1_commit_pair(&s.full[sl][2]);
+                    }
+                    __syncwarp();
+                    wait_ready();       // next step's layer 1
+                    if (elect_one()) {
+                        pmma3_ss1<80, 4>(ts + PC_R1, h_hi, h_lo, s.w + PW_W1H_HI, s.w + PW_W1H_LO);
+                        umma1_commit_pair(&s.full[sl][0]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+    // =========================== the epilogue warps: 8 per slot ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const uint32_t ts = tmem + (uint32_t)(slot * 256);                 // this slot's columns, lane 0
     const uint32_t tl = ts + ((uint32_t)(lq * 32) << 16);              // this thread's lane
-    uint32_t ph_ready = 0, ph_l = 0, ph_g = 0, ph_z = 0;
-    unsigned long long* const bar_ready = &s.ready[slot];
+    uint32_t ph_l = 0, ph_g = 0, ph_z = 0;
     unsigned long long* const bar_l = &s.full[slot][0];
     unsigned long long* const bar_g0 = &s.full[slot][1];
     unsigned long long* const bar_g1 = &s.full[slot][2];
@@ -106,17 +176,15 @@ decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
     __half* const h_lo = s.h[slot][1];
     __half* const xk = s.xk[slot];
     float4* const my_scratch = scratch + ((size_t)blockIdx.x * 2 + slot) * P_SCRATCH_F4_PER_SLOT + r;
+    // address of this slot's `ready` barrier in the LEADER CTA's shared memory (ready_x[slot] follows 16 bytes later)
+    uint32_t ready_leader;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ready_leader) : "r"((uint32_t)__cvta_generic_to_shared(&s.ready[slot])), "r"(0));
 
     // every warp: "my operand writes are done" -> one arrival on the leader's barrier
     auto arrive_ready = [&]() {
         ptx::tcgen05_fence_before_thread_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(bar_ready, 0);
-    };
-    // issuing warp: all 16 warps of the slot (both CTAs) have arrived
-    auto wait_ready = [&]() {
-        mbar_wait_cluster(bar_ready, ph_ready); ph_ready ^= 1;
-        ptx::tcgen05_fence_after_thread_sync();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(ready_leader) : "memory");
     };
     auto wait_full = [&](unsigned long long* bar, uint32_t parity) {
         mbar_wait_cluster(bar, parity);
@@ -197,11 +265,6 @@ decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
         }
         ptx::fence_proxy_async(ptx::space_shared);
         arrive_ready();
-        if (issuer) {       // c1 = [S ; z] . W1[S,z rows]^T -> [0,160)
-            wait_ready();
-            pmma3_ts<80, 6, 8>(ts + PC_R1, ts + PC_AHI, ts + PC_ALO, s.w + PW_WSZ_HI, s.w + PW_WSZ_LO, leader);
-            umma_commit_pair(bar_l, leader);
-        }
         // cell state of this thread's units: c[0..15] = units 16 hf .. (gates half 0), c[16..31] = units 32 + 16 hf .. (half 1)
         float c[32];
 #pragma unroll
@@ -226,11 +289,6 @@ decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                                    __uint_as_float(v[4 * q + 2]) + s.f32[PF_B1 + col0 + 4 * q + 2], __uint_as_float(v[4 * q + 3]) + s.f32[PF_B1 + col0 + 4 * q + 3]));
         }
         arrive_ready();
-        if (issuer) {       // layer 1 of step 0
-            wait_ready();
-            pmma3_ss<80, 4>(ts + PC_R1, h_hi, h_lo, s.w + PW_W1H_HI, s.w + PW_W1H_LO, leader);
-            umma_commit_pair(bar_l, leader);
-        }
 
         for (int t = 0; t < n_next; ++t) {
             const bool feed_back = t + 1 < n_next;
@@ -263,12 +321,6 @@ decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             arrive_ready();
             // ---------------- layer 2: a1 (K = 160, TMEM, K block kb at column 16 kb) -> 80 columns in [160,240); the h part of
             //                  gates half 0 is queued right behind it (overwrites a1 once layer 2 has consumed it) ----------------
-            if (issuer) {
-                wait_ready();
-                pmma3_ts<P_L2NL, 10, 16>(ts + PC_R2, ts + PC_R1, ts + PC_R1 + 8, s.w + PW_W2_HI, s.w + PW_W2_LO, leader);
-                umma_commit_pair(bar_l, leader);
-                if (feed_back) pmma3_ss<64, 4>(ts, h_hi, h_lo, s.w + PW_WHH, s.w + PW_WHH + 4096, leader);
-            }
             wait_full(bar_l, ph_l); ph_l ^= 1;
             float v0 = 0.0f, v1 = 0.0f;
             {   // layer-2 epilogue + folded layers 3+4 (80 -> 2): partial velocity over this thread's 40 columns
@@ -285,9 +337,10 @@ decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                     v1 = fmaf(y, w.y, v1);
                 }
             }
-            if (hf == 1) { s.vpart[slot][r] = v0; s.vpart[slot][P_ROWS + r] = v1; }
-            slot_sync(slot);
-            if (hf == 0) {      // column half 0 finishes the row: velocity, integration, emit; (p, v) -> hi|lo x block of the gate MMA
+            ptx::tcgen05_fence_before_thread_sync();
+            if (hf == 1) { s.vpart[slot][r] = v0; s.vpart[slot][P_ROWS + r] = v1; vel_arrive2(slot); }
+            else {              // column half 0 finishes the row: velocity, integration, emit; (p, v) -> hi|lo x block of the gate MMA
+                vel_sync2(slot);
                 v0 += s.vpart[slot][r] + s.f32[PF_B34];
                 v1 += s.vpart[slot][P_ROWS + r] + s.f32[PF_B34 + 1];
                 p0 += v0; p1 += v1;
@@ -298,22 +351,15 @@ decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                     psplit2(v0, v1, hv, lv);
                     *reinterpret_cast<uint4*>(xk + (size_t)r * 8) = make_uint4(hp, hv, lp, lv);                      // k 0..7
                     *reinterpret_cast<uint4*>(xk + (size_t)(P_ROWS + r) * 8) = make_uint4(hp, hv, 0x3C003C00u, 0u);  // k 8..15
+                    ptx::fence_proxy_async(ptx::space_shared);
+                    ptx::tcgen05_fence_before_thread_sync();
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(ready_leader + 16u) : "memory");
                 }
                 if (valid)
                     *reinterpret_cast<float4*>(out + ((size_t)(row0 + r) * n_next + t) * 4) = make_float4(p0, p1, v0, v1);
             }
             if (!feed_back) break;
-            ptx::fence_proxy_async(ptx::space_shared);
-            arrive_ready();
-            // ---------------- gates: x block of half 0 -> full[1]; half 1 (h part + x block) -> [128,256) -> full[2] ----------------
-            if (issuer) {
-                wait_ready();
-                pmma_ss<64, 1>(ts, xk, s.w + PW_WXK, PFMT, true, leader);
-                umma_commit_pair(bar_g0, leader);
-                pmma3_ss<64, 4>(ts + 128, h_hi, h_lo, s.w + PW_WHH + 8192, s.w + PW_WHH + 8192 + 4096, leader);
-                pmma_ss<64, 1>(ts + 128, xk, s.w + PW_WXK + 1024, PFMT, true, leader);
-                umma_commit_pair(bar_g1, leader);
-            }
             // ---------------- LSTM cell: 16 units of half 0 (units 16 hf ..), then 16 units of half 1 (units 32 + 16 hf ..) ----------------
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
@@ -349,14 +395,10 @@ decode_fwd_tcx2_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             ph_g ^= 1;
             ptx::fence_proxy_async(ptx::space_shared);
             arrive_ready();
-            if (issuer) {       // next step's layer 1
-                wait_ready();
-                pmma3_ss<80, 4>(ts + PC_R1, h_hi, h_lo, s.w + PW_W1H_HI, s.w + PW_W1H_LO, leader);
-                umma_commit_pair(bar_l, leader);
-            }
         }
         if (out_of_range && valid && status) atomicOr(status, 1);
     }
+    }   // epilogue warps
     ptx::tcgen05_fence_before_thread_sync();
     __syncthreads();
     cluster_sync_all();
@@ -395,7 +437,7 @@ extern "C" int sw_decode_fwd_tcx2(const void* tcx2_w16, const float* tcx2_f32, c
     const int smem = (int)sizeof(sw::Tcx2Smem);
     SW_SET_MAX_SMEM(sw::decode_fwd_tcx2_kernel, smem);
     const int grid = tcx2_grid(tiles, sm_count);
-    sw::decode_fwd_tcx2_kernel<<<grid, sw::P_THREADS, smem, (cudaStream_t)stream>>>(
+    sw::decode_fwd_tcx2_kernel<<<grid, sw::P_THREADS_ALL, smem, (cudaStream_t)stream>>>(
         noise_map, (const __half*)tcx2_w16, tcx2_f32, h0, c0, pooled, x_last, out, (float4*)scratch, status, n_agents, n_rows, n_next,
         (int)tiles);
     SW_CUDA_TRY(cudaGetLastError());

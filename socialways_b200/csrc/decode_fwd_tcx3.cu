@@ -21,6 +21,10 @@
 namespace sw {
 
 constexpr int Q_EPI = 512;            // epilogue threads (warps 0..15)
+#ifndef Q_BIG
+#define Q_BIG 3
+#endif
+constexpr int Q_NB = Q_BIG, Q_NS = 5 - Q_BIG;   // layer-1 K blocks of a "big" / "small" quarter (2 big + 2 small = 10 blocks)
 constexpr int Q_THREADS = 640;        // + the issuing warp's warpgroup (register file = 4 x 16 K: a 17th warp alone would cap
                                       //   every thread at 96 registers; setmaxnreg moves the idle group's registers over)
 
@@ -53,10 +57,9 @@ __device__ __forceinline__ void wait_full3(unsigned long long* bar, uint32_t par
 // layer-1 epilogue of NKB K blocks: a1 = lrelu(acc + c1) -> hi|lo fp16 written in place (hi -> columns +0..7, lo -> +8..15 of
 // the 16 accumulator columns the thread has just read); c1 (+ b1) comes from this thread's scratch lines, one block ahead
 template <int NKB>
-__device__ __forceinline__ void l1_epilogue(uint32_t t_acc, const float4* sc, unsigned long long* bar, uint32_t parity) {
-    float4 cn[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) cn[q] = __ldcg(sc + q * P_ROWS);
+__device__ __forceinline__ void l1_epilogue(uint32_t t_acc, const float4* sc, unsigned long long* bar, uint32_t parity, float4 (&cn)[4]) {
+    // cn = c1 of the first block, loaded a whole phase earlier (c1_prefetch): the scratch lives in L2 (~700 clk away; the L1 is
+    // all shared memory here), and a load issued just before the barrier wait was exposed at every phase start
     wait_full3(bar, parity);
 #pragma unroll
     for (int kb = 0; kb < NKB; ++kb) {
@@ -114,7 +117,6 @@ decode_fwd_tcx3_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
     asm volatile("" : "+r"(cq), "+r"(lane), "+r"(r));
     const uint32_t cta = cluster_ctarank();
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
-    const bool leader = lane == 0;
     const int n_units = (n_tiles + 1) >> 1;         // work unit = two consecutive tiles, one per CTA of the pair
 
     if (warp == 0) {
@@ -252,8 +254,8 @@ decode_fwd_tcx3_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
         int kb0[2], fin[2];
         {
             const int q0 = cq, q1 = 3 - cq;
-            kb0[0] = q0 < 2 ? 3 * q0 : 6 + 2 * (q0 - 2);
-            kb0[1] = q1 < 2 ? 3 * q1 : 6 + 2 * (q1 - 2);
+            kb0[0] = q0 < 2 ? Q_NB * q0 : 2 * Q_NB + Q_NS * (q0 - 2);
+            kb0[1] = q1 < 2 ? Q_NB * q1 : 2 * Q_NB + Q_NS * (q1 - 2);
             fin[0] = cq == 2;               // the quarter that finishes the rows of the slot (velocity, integration, emit)
             fin[1] = cq == 1;
         }
@@ -361,34 +363,49 @@ decode_fwd_tcx3_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 if (sl >= n_act) continue;
                 const uint32_t ta = tl + (uint32_t)(sl * 256) + PC_R1 + kb0[sl] * 16;
                 wait_full3(&s.full[sl][0], ph_l[sl]); ph_l[sl] ^= 1;      // c1 + b1 -> scratch (the K blocks this thread re-reads)
-                if (three[sl]) c1_to_scratch<3>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
-                else           c1_to_scratch<2>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
+                if (three[sl]) c1_to_scratch<Q_NB>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
+                else           c1_to_scratch<Q_NS>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
                 arrive(&s.ready[sl]);                                     // -> layer 1 of step 0
             }
 
             // ---------------- layer 1 epilogue: a1 = lrelu(acc + c1) -> hi|lo in place ----------------
+            float4 cpre[4];             // c1 of the first layer-1 block of the NEXT layer-1 phase (one pending at a time)
+            auto c1_prefetch = [&](auto slc) {
+                constexpr int sl = decltype(slc)::value;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cpre[q] = __ldcg(sc[sl] + q * P_ROWS);
+            };
             auto phase_l1 = [&](auto slc) {
                 constexpr int sl = decltype(slc)::value;
                 const uint32_t ta = tl + (uint32_t)(sl * 256) + PC_R1 + kb0[sl] * 16;
-                if (three[sl]) l1_epilogue<3>(ta, sc[sl], &s.full[sl][0], ph_l[sl]);
-                else           l1_epilogue<2>(ta, sc[sl], &s.full[sl][0], ph_l[sl]);
+                if (three[sl]) l1_epilogue<Q_NB>(ta, sc[sl], &s.full[sl][0], ph_l[sl], cpre);
+                else           l1_epilogue<Q_NS>(ta, sc[sl], &s.full[sl][0], ph_l[sl], cpre);
                 ph_l[sl] ^= 1;
                 arrive(&s.ready[sl]);                                     // -> layer 2 (+ h part of gates half 0)
             };
             // ---------------- layer-2 epilogue + folded layers 3+4 (80 -> 2), row finish ----------------
             auto phase_l2 = [&](auto slc, int t, bool feed_back) {
                 constexpr int sl = decltype(slc)::value;
+                const float4* b2 = reinterpret_cast<const float4*>(s.f32 + PF_B2 + cq * 20);
+                const float4* w34 = reinterpret_cast<const float4*>(s.f32 + PF_W34 + cq * 40);
+#ifdef Q_P2_PRELOAD
+                float4 bb[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) bb[j] = b2[j];
+#endif
                 wait_full3(&s.full[sl][0], ph_l[sl]); ph_l[sl] ^= 1;
                 float v0 = 0.0f, v1 = 0.0f;
                 {
                     uint32_t acc[20];
                     tmem_ld<20>(tl + (uint32_t)(sl * 256) + PC_R2 + cq * 20, acc);
                     ptx::tcgen05_wait_ld();
-                    const float4* b2 = reinterpret_cast<const float4*>(s.f32 + PF_B2 + cq * 20);
-                    const float4* w34 = reinterpret_cast<const float4*>(s.f32 + PF_W34 + cq * 40);
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
+#ifdef Q_P2_PRELOAD
+                        const float4 b = bb[j], wa = w34[2 * j], wb = w34[2 * j + 1];
+#else
                         const float4 b = b2[j], wa = w34[2 * j], wb = w34[2 * j + 1];
+#endif
                         const float y0 = lrelu02(__uint_as_float(acc[4 * j]) + b.x), y1 = lrelu02(__uint_as_float(acc[4 * j + 1]) + b.y);
                         const float y2 = lrelu02(__uint_as_float(acc[4 * j + 2]) + b.z), y3 = lrelu02(__uint_as_float(acc[4 * j + 3]) + b.w);
                         v0 = fmaf(y0, wa.x, v0); v1 = fmaf(y0, wa.y, v1);
@@ -441,7 +458,11 @@ decode_fwd_tcx3_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                         for (int w2 = 0; w2 < 2; ++w2)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) g[w2][q] = __uint_as_float(a[(uu + w2) * 4 + q]);
+#ifdef Q_CELL2
+                        lstm_cell_pair_prescaled_x2(g[0], g[1], c[sl][half * 8 + uu], c[sl][half * 8 + uu + 1], hv[uu], hv[uu + 1]);
+#else
                         lstm_cell_pair_prescaled(g[0], g[1], c[sl][half * 8 + uu], c[sl][half * 8 + uu + 1], hv[uu], hv[uu + 1]);
+#endif
                     }
                     uint32_t hh[4], ll[4];
 #pragma unroll
@@ -460,13 +481,16 @@ decode_fwd_tcx3_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             using S1 = std::integral_constant<int, 1>;
             // The slots run half a step apart (slot 1 behind): the long MMA group of one slot (layer 2 + the h part of gates half
             // 0, ~2.5 K clk) runs under the long epilogue phase of the other (the cell update, ~5 K clk); see the issuing warp.
+            c1_prefetch(S0{});
             for (int t = 0; t < n_next; ++t) {
                 const bool feed_back = t + 1 < n_next;
                 phase_l1(S0{});
                 if (n_act > 1 && t > 0) phase_cell(S1{});
+                if (n_act > 1) c1_prefetch(S1{});
                 phase_l2(S0{}, t, feed_back);
                 if (n_act > 1) phase_l1(S1{});
                 if (feed_back) phase_cell(S0{});
+                if (feed_back) c1_prefetch(S0{});
                 if (n_act > 1) phase_l2(S1{}, t, feed_back);
             }
             if (out_of_range && status) {
