@@ -156,24 +156,19 @@ int sw_decode_fwd_tcx(const void* tcx_w16, const void* tcx_wsz16, const float* t
                       int* status, int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 int sw_decode_tcx_pack_sizes(int* n_w16, int* n_wsz16, int* n_f32);
 
-/* The same fp16 hi/lo split decode with TWO 128-row tiles in flight per SM: clusters of two CTAs issue every MMA as one
- * tcgen05 cta_group::2 instruction (each CTA holds half of every weight matrix), each CTA interleaves two tile slots, and the
- * hoisted layer-1 term lives in `scratch` (device memory, sw_decode_tcx2_scratch_bytes(sm_count) bytes, 16-byte aligned;
- * written and re-read inside the launch, contents meaningless afterwards; one buffer per concurrently running launch).
- * Same inputs / outputs / status word / arithmetic as sw_decode_fwd_tcx; pack from packing.pack_decoder_tcx2
- * (sizes via sw_decode_tcx2_pack_sizes).  Replaces the loop of predict(), reference train.py:418-430, x K samples. */
-int sw_decode_fwd_tcx2(const void* tcx2_w16, const float* tcx2_f32, const float* h0, const float* c0, const float* pooled,
+/* The same fp16 hi/lo split decode with TWO 128-row tiles in flight per SM (csrc/decode_fwd_pair.cu; the default decode of the
+ * inference path): clusters of two CTAs issue every MMA as one tcgen05 cta_group::2 instruction (each CTA holds half of every
+ * weight matrix), all 16 epilogue warps of a CTA serve two tile slots alternately (while they work on one slot's epilogue the
+ * tensor pipe runs the other slot's MMAs), a dedicated warp issues every MMA of the pair, and the hoisted layer-1 term lives
+ * in `scratch` (device memory, sw_decode_pair_scratch_bytes(sm_count) bytes, 16-byte aligned; written and re-read inside the
+ * launch, contents meaningless afterwards; one buffer per concurrently running launch).
+ * Same inputs / outputs / status word / arithmetic as sw_decode_fwd_tcx; pack from packing.pack_decoder_pair
+ * (sizes via sw_decode_pair_pack_sizes).  Replaces the loop of predict(), reference train.py:418-430, x K samples. */
+int sw_decode_fwd_pair(const void* pair_w16, const float* pair_f32, const float* h0, const float* c0, const float* pooled,
                        const float* noise, const float* x_last, float* out, void* scratch, long long scratch_bytes,
                        int* status, int n_agents, int n_samples, int n_next, int sm_count, void* stream);
-int sw_decode_tcx2_pack_sizes(int* n_w16, int* n_f32);
-long long sw_decode_tcx2_scratch_bytes(int sm_count);
-
-/* The CTA-pair decode in PING-PONG form (csrc/decode_fwd_tcx3.cu): same arguments, pack, scratch, outputs and arithmetic as
- * sw_decode_fwd_tcx2, but all 16 epilogue warps of a CTA serve both tile slots alternately (while they work on one slot's
- * epilogue the tensor pipe runs the other slot's MMAs) and a dedicated warp issues every MMA of the pair. */
-int sw_decode_fwd_tcx3(const void* tcx2_w16, const float* tcx2_f32, const float* h0, const float* c0, const float* pooled,
-                       const float* noise, const float* x_last, float* out, void* scratch, long long scratch_bytes,
-                       int* status, int n_agents, int n_samples, int n_next, int sm_count, void* stream);
+int sw_decode_pair_pack_sizes(int* n_w16, int* n_f32);
+long long sw_decode_pair_scratch_bytes(int sm_count);
 
 /* Discriminator FC heads (train.py:281-292, 300-309), one thread per trajectory, all 8 Linear layers fused.
  *   pack: sw_disc_heads_pack_floats(P, L) floats = Wo1[32][64] bo1 Wo2[32][32] bo2 Wp1[32][P] bp1 Wp2[32][32] bp2

@@ -1,5 +1,5 @@
 """One launch of the tcx decode kernel on the profile workload (655 360 trajectories, 12 steps) -- the target of
-`ncu --set full --import-source on -k regex:decode_fwd_tcx --launch-skip 1 -c 1`."""
+`ncu --set full --import-source on -k regex:decode_fwd_ --launch-skip 1 -c 1`."""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -21,10 +21,10 @@ pooled = torch.randn(n, 64, device="cuda", generator=g) * 0.3
 noise = torch.rand(k, n, 32, device="cuda", generator=g)
 xl = torch.rand(n, 4, device="cuda", generator=g)
 out = torch.empty(k, n, T, 4, device="cuda")
-which = sys.argv[1] if len(sys.argv) > 1 else "tcx"       # "tcx" (one tile per SM), "tcx2" / "tcx3" (CTA pairs, two tiles per SM)
+which = sys.argv[1] if len(sys.argv) > 1 else "tcx"       # "tcx" (one tile per SM) or "pair" (CTA pairs, two tiles per SM)
 for _ in range(3):
-    if which in ("tcx2", "tcx3"):
-        ops.decode_tcx2(*pk["tcx2"], h, c, pooled, noise, xl, T, out=out, pingpong=which == "tcx3")
+    if which == "pair":
+        ops.decode_pair(*pk["pair"], h, c, pooled, noise, xl, T, out=out)
     else:
         ops.decode_tcx(*pk["tcx"], h, c, pooled, noise, xl, T, out=out)
 torch.cuda.synchronize()

@@ -1,4 +1,4 @@
-"""Bring-up check of the CTA-pair decode kernel (sw_decode_fwd_tcx2) on a GPU box: parity vs the fp32 oracle on small ragged
+"""Bring-up check of the CTA-pair decode kernel (sw_decode_fwd_pair) on a GPU box: parity vs the fp32 oracle on small ragged
 cases, agreement with the one-tile-per-SM kernel on the bench workload, and the CUDA-event time of both."""
 import os
 import sys
@@ -12,9 +12,6 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import socialways_b200 as sw
 from golden_data import synthetic_scenes
 from oracle import socialways_oracle as so
-
-
-PAIR_PRECISION = os.environ.get("SW_PAIR", "fp16x2q")       # "fp16x2p" = tcx2 (slot-private warps), "fp16x2q" = tcx3 (ping-pong)
 
 
 def small_cases():
@@ -31,8 +28,8 @@ def small_cases():
         noise = torch.rand(k, n, 32)
         for social in (True, False):
             gen.use_social = social
-            got = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision=PAIR_PRECISION)
-            old = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision="fp16x2")
+            got = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision="fp16x2")
+            old = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision="fp16x2s")
             torch.cuda.synchronize()
             if k * n <= 2000:
                 want = torch.stack([so.predict(P, obsv, noise[i], 12, data["batches"], social, "closed") for i in range(k)])
@@ -60,8 +57,7 @@ def bench_case(scenes=16384, agents=8, k=20, reps=5):
     from socialways_b200 import ops
     outs = {}
     for name, fn in (("tcx", lambda o: ops.decode_tcx(*pk["tcx"], h, c, pooled, noise, x_last, 12, out=o)),
-                     ("tcx2", lambda o: ops.decode_tcx2(*pk["tcx2"], h, c, pooled, noise, x_last, 12, out=o)),
-                     ("tcx3", lambda o: ops.decode_tcx2(*pk["tcx2"], h, c, pooled, noise, x_last, 12, out=o, pingpong=True))):
+                     ("pair", lambda o: ops.decode_pair(*pk["pair"], h, c, pooled, noise, x_last, 12, out=o))):
         out = torch.empty(k, n, 12, 4, device="cuda")
         fn(out)
         torch.cuda.synchronize()
@@ -74,9 +70,8 @@ def bench_case(scenes=16384, agents=8, k=20, reps=5):
         ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
         outs[name] = out
         print(f"{name}: {min(ms):.3f} ms (median {sorted(ms)[len(ms) // 2]:.3f})  -> {k * n / min(ms) / 1e3:.1f} M traj/s", flush=True)
-    for name in ("tcx2", "tcx3"):
-        print(f"max |{name} - tcx| on the bench workload:", (outs[name] - outs["tcx"]).abs().max().item(),
-              " finite:", bool(torch.isfinite(outs[name]).all()))
+    print("max |pair - tcx| on the bench workload:", (outs["pair"] - outs["tcx"]).abs().max().item(),
+          " finite:", bool(torch.isfinite(outs["pair"]).all()))
 
 
 if __name__ == "__main__":

@@ -1,19 +1,34 @@
-// fp32-faithful tensor-core decode kernel, two 128-row tiles per SM in PING-PONG between the tensor pipe and the CUDA cores.
+// fp32-faithful tensor-core decode kernel, TWO 128-row tiles in flight per SM: CTA pairs (tcgen05 cta_group::2), the tensor
+// pipe and the CUDA cores in PING-PONG over two tile slots.  The default decode kernel of the inference path.
 //
-// Same computation, arithmetic, weight image, TMEM column map and c1 scratch as decode_fwd_tcx2.cu (the loop of predict(),
-// reference train.py:418-430, fp16 hi/lo split operands, 3 MMAs per product, fp32 accumulation in TMEM, CTA pairs issuing
-// cta_group::2 MMAs so that each SM holds half of every weight matrix and two tile slots of 256 TMEM columns).  What changes is
-// who works on what.  decode_fwd_tcx2 gives each slot its own 8 warps; ncu showed the two slots falling into step with each
-// other (both in the MUFU-bound cell update at the same time, both waiting for their MMAs at the same time): 32 % of all warp
-// samples sat on MMA-completion barriers and the tensor pipe was 36 % active, no better than one tile per SM.  Here
-//   * ALL 16 epilogue warps (thread = (TMEM lane = row, column quarter), as in decode_fwd_tcx.cu) serve BOTH slots, alternating
-//     slot 0 / slot 1 phase by phase: layer-1 epilogue (0), (1), layer-2 epilogue + velocity (0), (1), cell update (0), (1).
-//     While the warps are in slot 1's phase, the tensor pipe runs the MMAs slot 0's next phase waits for, and vice versa --
-//     every MMA group is shorter than the epilogue phase it hides under, so the warps (almost) never wait;
+// Same computation and arithmetic as decode_fwd_tcx.cu (the loop of predict(), reference train.py:418-430, on fp16 hi/lo split
+// operands, 3 MMAs per product, fp32 accumulation in TMEM).  decode_fwd_tcx runs one tile per SM: one tile fills TMEM (480 of
+// 512 columns) and shared memory (224 KB, 162 KB of it weights), so its MMA time and its epilogue time per step are serial.  Here
+//   * two CTAs on the two SMs of a TPC form a pair and issue every MMA as ONE cta_group::2 instruction (UMMA M = 256): each CTA
+//     holds only HALF of every weight matrix (N/2 rows of B) -- 111 KB, hoist weights included -- which leaves room for TWO
+//     tile slots per CTA (a slot = 256 TMEM columns, its own h / x operand buffers and barriers);
+//   * the step-invariant layer-1 term c1 (160 fp32 per row) does not live in TMEM: it is computed once per tile by MMAs, parked in a
+//     per-slot scratch buffer in global memory (80 KB per slot, L2 resident: 23.7 MB for the chip) and re-read by the thread that
+//     wrote it, coalesced, ahead of its use;
+//   * ALL 16 epilogue warps (thread = (TMEM lane = row, column quarter)) serve BOTH slots, half a step apart:
+//         L1 epilogue (0,t) | cell update (1,t-1) | L2 epilogue + row finish (0,t) | L1 epilogue (1,t) | cell (0,t) | L2 (1,t)
+//     so that each MMA group of one slot runs under an epilogue phase of the other that is longer than it (layer 2 + the h part
+//     of gates half 0, ~2.5 K clk, under the ~4.5 K clk cell update; layer 1 and the gate x blocks under the L2 / L1 epilogues);
 //   * a 17th warp of the leader CTA does nothing but issue: it walks the same static schedule, waits for the "operands written"
-//     arrivals of a slot (16 warps x 2 CTAs), issues that slot's MMAs for both CTAs and commits to the slot's `full` barriers;
+//     arrivals of a slot (16 warps x 2 CTAs, remote mbarrier arrives), ONE elected lane issues the group's MMAs back to back and
+//     commits with a multicast arrive on the slot's `full` barriers in both CTAs.  Its warpgroup gives its registers to the
+//     epilogue warps (setmaxnreg 32 / 112: a 17th warp alone would cap every thread at 96);
 //   * quarter -> work assignment is mirrored between the slots (layer-1 K blocks 3,3,2,2 in slot 0 and 2,2,3,3 in slot 1, the
 //     row finish on quarter 2 / quarter 1), so every warp carries the same load over a slot pair.
+// TMEM columns of a slot: [0,160) layer-1 accumulator -> a1 hi|lo in place | [160,240) layer-2 accumulator | gates half 0 ->
+// [0,128) (queued behind the layer-2 MMAs), gates half 1 -> [128,256).  Tile prologue: [160,256) holds the [S ; z] hi|lo A
+// operand of the hoist, [0,160) its result.
+// Measured history (B200, 2.62 M trajectories x 12 steps; decode_fwd_tcx = 10.03 ms): slot-private warps with lane-predicated
+// issue from an epilogue warp 9.64 ms (ncu: 28 % of warp samples on MMA barriers -- ptxas wraps a lane-predicated tcgen05.mma in
+// an ELECT / BRA.U.ANY loop, ~15 instructions per MMA, ~1.5 K instructions per step on ONE warp); the same with dedicated issuing
+// warps 9.15 ms; ping-pong in lockstep order 9.78 ms (layer 2 of one slot does not fit under the 1.1 K clk L1 epilogue of the
+// other); half-step order with the lane-predicated issue 10.37 ms (the issuing warp never caught up: 175 clk per MMA);
+// single-lane issue 8.71 ms; non-blocking velocity exchange + indices kept in registers 8.24 ms.
 #include <type_traits>
 
 #include "decode_pair.cuh"
@@ -28,7 +43,7 @@ constexpr int Q_NB = Q_BIG, Q_NS = 5 - Q_BIG;   // layer-1 K blocks of a "big" /
 constexpr int Q_THREADS = 640;        // + the issuing warp's warpgroup (register file = 4 x 16 K: a 17th warp alone would cap
                                       //   every thread at 96 registers; setmaxnreg moves the idle group's registers over)
 
-struct Tcx3Smem {
+struct PairSmem {
     float zst[2][P_ROWS * SW_Z];             // noise block of each slot's tile (TMA, 128-byte swizzle; 1024-byte aligned)
     __half w[PW_TOTAL];                      // this rank's half of every weight matrix (113 664 B)
     __half h[2][2][8 * P_ROWS * 8];          // [slot][hi|lo][8 chunks][128][8]
@@ -42,7 +57,7 @@ struct Tcx3Smem {
     unsigned long long bar_w;                // TMA: weights
     uint32_t tmem_base;
 };
-static_assert(sizeof(Tcx3Smem) <= 227 * 1024, "shared memory of one CTA");
+static_assert(sizeof(PairSmem) <= 227 * 1024, "shared memory of one CTA");
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" :: "n"(Q_EPI) : "memory"); }
 // partial-velocity exchange of a slot (named barrier 2 + slot): the 12 contributing warps only ARRIVE (they never block), the 4
@@ -101,13 +116,13 @@ __device__ __forceinline__ void c1_to_scratch(uint32_t t_acc, float4* sc, const 
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1)
-decode_fwd_tcx3_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][32] fp32, box 128 x 32, 128-byte swizzle */,
+decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][32] fp32, box 128 x 32, 128-byte swizzle */,
                        const __half* __restrict__ w16 /* [2 ranks][PW_TOTAL] */, const float* __restrict__ wf32,
                        const float* __restrict__ h0, const float* __restrict__ c0, const float* __restrict__ pooled,
                        const float* __restrict__ x_last, float* __restrict__ out, float4* __restrict__ scratch,
                        int* __restrict__ status, int n_agents, long long n_rows, int n_next, int n_tiles) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    Tcx3Smem& s = *reinterpret_cast<Tcx3Smem*>(smem_raw);
+    PairSmem& s = *reinterpret_cast<PairSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5;
     const int lq = warp & 3;                        // TMEM lane quarter (= warp % 4)
     int lane = tid & 31, cq = (warp >> 2) & 3;      // column quarter
@@ -506,7 +521,7 @@ decode_fwd_tcx3_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
 
 }  // namespace sw
 
-static int tcx3_grid(long long tiles, int sm_count) {
+static int pair_grid(long long tiles, int sm_count) {
     const long long units = (tiles + 1) / 2;            // two tiles (one per CTA of a pair) per unit, two unit slots per pair
     long long pairs = (units + 1) / 2;
     if (pairs > sm_count / 2) pairs = sm_count / 2;
@@ -514,15 +529,25 @@ static int tcx3_grid(long long tiles, int sm_count) {
     return (int)(2 * pairs);
 }
 
-extern "C" long long sw_decode_tcx2_scratch_bytes(int sm_count);
+extern "C" long long sw_decode_pair_scratch_bytes(int sm_count) {
+    if (sm_count < 2) return 0;
+    return (long long)(sm_count / 2) * 2 * 2 * sw::P_SCRATCH_F4_PER_SLOT * 16;
+}
 
-extern "C" int sw_decode_fwd_tcx3(const void* tcx2_w16, const float* tcx2_f32, const float* h0, const float* c0,
+extern "C" int sw_decode_pair_pack_sizes(int* n_w16, int* n_f32) {
+    if (!n_w16 || !n_f32) return SW_ERR_ARG;
+    *n_w16 = 2 * sw::PW_TOTAL;
+    *n_f32 = sw::PF_TOTAL;
+    return SW_OK;
+}
+
+extern "C" int sw_decode_fwd_pair(const void* pair_w16, const float* pair_f32, const float* h0, const float* c0,
                                   const float* pooled, const float* noise, const float* x_last, float* out, void* scratch,
                                   long long scratch_bytes, int* status, int n_agents, int n_samples, int n_next, int sm_count,
                                   void* stream) {
-    if (!tcx2_w16 || !tcx2_f32 || !h0 || !c0 || !noise || !x_last || !out || !scratch) return SW_ERR_ARG;
+    if (!pair_w16 || !pair_f32 || !h0 || !c0 || !noise || !x_last || !out || !scratch) return SW_ERR_ARG;
     if (n_agents <= 0 || n_samples <= 0 || n_next <= 0 || sm_count < 2) return SW_ERR_ARG;
-    if (scratch_bytes < sw_decode_tcx2_scratch_bytes(sm_count) || ((uintptr_t)scratch & 15u) != 0) return SW_ERR_ARG;
+    if (scratch_bytes < sw_decode_pair_scratch_bytes(sm_count) || ((uintptr_t)scratch & 15u) != 0) return SW_ERR_ARG;
     const long long n_rows = (long long)n_agents * n_samples;
     const long long tiles = (n_rows + sw::P_ROWS - 1) / sw::P_ROWS;
     if (tiles > 0x3fffffffLL) return SW_ERR_UNSUPPORTED;
@@ -530,11 +555,11 @@ extern "C" int sw_decode_fwd_tcx3(const void* tcx2_w16, const float* tcx2_f32, c
     CUtensorMap noise_map;
     const int rc = encode_noise_map2(&noise_map, noise, n_rows);
     if (rc != SW_OK) return rc;
-    const int smem = (int)sizeof(sw::Tcx3Smem);
-    SW_SET_MAX_SMEM(sw::decode_fwd_tcx3_kernel, smem);
-    const int grid = tcx3_grid(tiles, sm_count);
-    sw::decode_fwd_tcx3_kernel<<<grid, sw::Q_THREADS, smem, (cudaStream_t)stream>>>(
-        noise_map, (const __half*)tcx2_w16, tcx2_f32, h0, c0, pooled, x_last, out, (float4*)scratch, status, n_agents, n_rows, n_next,
+    const int smem = (int)sizeof(sw::PairSmem);
+    SW_SET_MAX_SMEM(sw::decode_fwd_pair_kernel, smem);
+    const int grid = pair_grid(tiles, sm_count);
+    sw::decode_fwd_pair_kernel<<<grid, sw::Q_THREADS, smem, (cudaStream_t)stream>>>(
+        noise_map, (const __half*)pair_w16, pair_f32, h0, c0, pooled, x_last, out, (float4*)scratch, status, n_agents, n_rows, n_next,
         (int)tiles);
     SW_CUDA_TRY(cudaGetLastError());
     return SW_OK;

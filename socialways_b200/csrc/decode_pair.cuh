@@ -1,5 +1,5 @@
-// Shared by the CTA-pair (tcgen05 cta_group::2) decode kernels decode_fwd_tcx2.cu / decode_fwd_tcx3.cu: the per-rank weight
-// image (packing.pack_decoder_tcx2), TMEM column map of a tile slot, the c1 scratch layout, the hi/lo split and the three-pass
+// Shared by the CTA-pair (tcgen05 cta_group::2) decode kernel decode_fwd_pair.cu: the per-rank weight
+// image (packing.pack_decoder_pair), TMEM column map of a tile slot, the c1 scratch layout, the hi/lo split and the three-pass
 // pair MMAs, and the host-side tensor map of the noise tensor.
 #pragma once
 #include <cuda.h>
@@ -11,8 +11,6 @@
 namespace sw {
 
 constexpr int P_ROWS = 128;
-constexpr int P_THREADS = 512;
-constexpr int P_SLOT_THREADS = 256;
 constexpr int P_L2NL = 40;            // layer-2 B rows per CTA (N = 80)
 // per-rank fp16 weight image (elements); every matrix canonical [K/8][local rows][8]
 constexpr int PW_W1H_HI = 0, PW_W1H_LO = 5120,                                   // [8][80][8]

@@ -123,7 +123,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 // arrive on the mbarrier at the same shared-memory offset as `bar` in CTA `cta` of the cluster.  Default semantics
 // (.release.cta), as CUTLASS's ClusterBarrier::arrive(cta_id): the cluster-scope form costs MEMBAR.ALL.GPU + ERRBAR per
 // arrival and CCTL.IVALL (an L1 invalidation) per wait -- 47 % of all stall samples of the first version of
-// decode_fwd_tcx2 (ncu).  What crosses the pair here is consumed by the tensor core's async proxy (shared-memory operands,
+// the pair decode kernel (ncu).  What crosses the pair here is consumed by the tensor core's async proxy (shared-memory operands,
 // made visible by fence.proxy.async before the arrival) or lives in TMEM (tcgen05.wait::st + fence::before_thread_sync).
 __device__ __forceinline__ void mbar_arrive_cluster(unsigned long long* bar, uint32_t cta) {
     uint32_t ra;

@@ -283,54 +283,52 @@ def decode_tcx(w16, wsz16, f32, h0, c0, pooled, noise, x_last, n_next, out=None,
     return out
 
 
-_TCX2_SIZES = None
-_TCX2_SCRATCH = {}
+_PAIR_SIZES = None
+_PAIR_SCRATCH = {}
 
 
-def _tcx2_pack_sizes():
-    global _TCX2_SIZES
-    if _TCX2_SIZES is None:
+def _pair_pack_sizes():
+    global _PAIR_SIZES
+    if _PAIR_SIZES is None:
         import ctypes
         a, b = ctypes.c_int(), ctypes.c_int()
-        _lib.check(_lib.lib().sw_decode_tcx2_pack_sizes(ctypes.byref(a), ctypes.byref(b)), "sw_decode_tcx2_pack_sizes")
-        _TCX2_SIZES = (a.value, b.value)
-    return _TCX2_SIZES
+        _lib.check(_lib.lib().sw_decode_pair_pack_sizes(ctypes.byref(a), ctypes.byref(b)), "sw_decode_pair_pack_sizes")
+        _PAIR_SIZES = (a.value, b.value)
+    return _PAIR_SIZES
 
 
-def decode_tcx2_scratch(device):
-    """Per-device scratch of sw_decode_fwd_tcx2 (the hoisted layer-1 term of the tiles in flight: 160 KB per CTA, 23.7 MB for
+def decode_pair_scratch(device):
+    """Per-device scratch of sw_decode_fwd_pair (the hoisted layer-1 term of the tiles in flight: 160 KB per CTA, 23.7 MB for
     148 SMs; written and re-read inside one launch, so it stays in L2).  One buffer per (device, stream)."""
     key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(device).cuda_stream)
-    if key not in _TCX2_SCRATCH:
-        n = int(_lib.lib().sw_decode_tcx2_scratch_bytes(sm_count(device)))
-        _TCX2_SCRATCH[key] = torch.empty(n, dtype=torch.uint8, device=device)
-    return _TCX2_SCRATCH[key]
+    if key not in _PAIR_SCRATCH:
+        n = int(_lib.lib().sw_decode_pair_scratch_bytes(sm_count(device)))
+        _PAIR_SCRATCH[key] = torch.empty(n, dtype=torch.uint8, device=device)
+    return _PAIR_SCRATCH[key]
 
 
-def decode_tcx2(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, status=None, scratch=None, pingpong=False):
-    """sw_decode_fwd_tcx2 / sw_decode_fwd_tcx3 (pingpong=True): the fp16 hi/lo split tcgen05 decode kernel with two tiles in
-    flight per SM (CTA pairs, cta_group::2); same inputs, outputs and arithmetic as decode_tcx.  Packs from
-    packing.pack_decoder_tcx2.  tcx2: each tile slot has its own 8 warps; tcx3: all 16 warps alternate between the slots and
-    a dedicated warp issues the MMAs."""
+def decode_pair(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, status=None, scratch=None):
+    """sw_decode_fwd_pair: the fp16 hi/lo split tcgen05 decode kernel with two tiles in flight per SM (CTA pairs, cta_group::2,
+    epilogue warps in ping-pong over two tile slots, dedicated issuing warp); same inputs, outputs and arithmetic as decode_tcx.
+    Packs from packing.pack_decoder_pair."""
     noise = _f32(noise)
     k, n, z = noise.shape
     if z != Z or h0.shape != (n, H):
-        raise ValueError("decode_tcx2: noise must be [K, N, 32] and h0 [N, 64]")
+        raise ValueError("decode_pair: noise must be [K, N, 32] and h0 [N, 64]")
     if w16.dtype != torch.float16 or not w16.is_contiguous():
-        raise ValueError("decode_tcx2: fp16 contiguous operand pack expected (packing.pack_decoder_tcx2)")
-    if (w16.numel(), f32.numel()) != _tcx2_pack_sizes():
-        raise ValueError(f"decode_tcx2: pack sizes {(w16.numel(), f32.numel())} do not match the kernel's {_tcx2_pack_sizes()}")
+        raise ValueError("decode_pair: fp16 contiguous operand pack expected (packing.pack_decoder_pair)")
+    if (w16.numel(), f32.numel()) != _pair_pack_sizes():
+        raise ValueError(f"decode_pair: pack sizes {(w16.numel(), f32.numel())} do not match the kernel's {_pair_pack_sizes()}")
     if out is None:
         out = torch.empty(k, n, n_next, 4, device=noise.device)
     if scratch is None:
-        scratch = decode_tcx2_scratch(noise.device)
-    name = "sw_decode_fwd_tcx3" if pingpong else "sw_decode_fwd_tcx2"
-    code = getattr(_lib.lib(), name)(w16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(_f32(h0)), _lib.ptr(_f32(c0)),
-                                     _lib.ptr(None if pooled is None else _f32(pooled)), _lib.ptr(noise),
-                                     _lib.ptr(_f32(x_last)), _lib.ptr(out), scratch.data_ptr(), scratch.numel(),
-                                     None if status is None else status.data_ptr(), n, k, n_next,
-                                     sm_count(noise.device), _stream())
-    _lib.check(code, name)
+        scratch = decode_pair_scratch(noise.device)
+    code = _lib.lib().sw_decode_fwd_pair(w16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(_f32(h0)), _lib.ptr(_f32(c0)),
+                                         _lib.ptr(None if pooled is None else _f32(pooled)), _lib.ptr(noise),
+                                         _lib.ptr(_f32(x_last)), _lib.ptr(out), scratch.data_ptr(), scratch.numel(),
+                                         None if status is None else status.data_ptr(), n, k, n_next,
+                                         sm_count(noise.device), _stream())
+    _lib.check(code, "sw_decode_fwd_pair")
     return out
 
 

@@ -131,8 +131,8 @@ def pack_decoder_tcx(lstm_pack, dec_pack):
     return w16, wsz16, f32
 
 
-def pack_decoder_tcx2(lstm_pack, dec_pack):
-    """Operands of the CTA-pair decode kernel (csrc/decode_fwd_tcx2.cu, tcgen05 cta_group::2): the same hi/lo split matrices
+def pack_decoder_pair(lstm_pack, dec_pack):
+    """Operands of the CTA-pair decode kernel (csrc/decode_fwd_pair.cu, tcgen05 cta_group::2): the same hi/lo split matrices
     as `pack_decoder_tcx`, but every B matrix [N][K] is cut into the two N halves the two CTAs of a pair supply (rank 0: rows
     [0, N/2), rank 1: [N/2, N)), each canonical K-major.
     w16  fp16 [2 ranks][56832]: W1h hi | lo [8][80][8]; W2 hi | lo [20][40][8] (not stacked: the pair kernel accumulates the

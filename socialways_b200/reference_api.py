@@ -279,7 +279,7 @@ class Generator(nn.Module):
                              pool_m=m.contiguous(), pool_m0=m0.contiguous())
                 packs["tc_w16"], packs["tc_f32"] = packing.pack_decoder_tc(packs["enc"], packs["dec"])
                 packs["tcx"] = packing.pack_decoder_tcx(packs["enc"], packs["dec"])
-                packs["tcx2"] = packing.pack_decoder_tcx2(packs["enc"], packs["dec"])
+                packs["pair"] = packing.pack_decoder_pair(packs["enc"], packs["dec"])
                 packs["enc_tcx"] = packing.pack_encoder_tcx(packs["enc"])
                 packs["pool_tcx"] = packing.pack_pool_tcx(fe[2].weight)
                 # weights beyond fp16's range (|w| > 65 504 -> inf in the hi part) poison the split: raise the status word now
@@ -341,9 +341,10 @@ class Generator(nn.Module):
                 raise ValueError("predict_k: give `noise`, or `seed` and `k` for device-side noise")
             sd, off = (seed if isinstance(seed, tuple) else (seed, 0))
             noise = ops.noise_uniform((k, n, self.noise_len), obsv_p.device, sd, off, out=noise_buf)
-        # "fp16x2p" / "fp16x2q": decode with two tiles in flight per SM (CTA pairs; q = ping-pong form); otherwise = "fp16x2"
-        pair, pingpong = precision in ("fp16x2p", "fp16x2q"), precision == "fp16x2q"
-        if pair:
+        # "fp16x2" decodes with two tiles in flight per SM (CTA pairs, csrc/decode_fwd_pair.cu); "fp16x2s" = the same arithmetic
+        # on the one-tile-per-SM kernel (csrc/decode_fwd_tcx.cu)
+        single = precision == "fp16x2s"
+        if single:
             precision = "fp16x2"
         if precision == "fp16x2":           # both recurrent kernels on the tensor cores (fp16 hi/lo split operands)
             enc = ops.lstm_seq_tcx(*pk["enc_tcx"], obsv_p)
@@ -359,14 +360,14 @@ class Generator(nn.Module):
                 pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
         if precision == "bf16":
             return ops.decode_tc(pk["tc_w16"], pk["tc_f32"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
-        if pair:
-            return ops.decode_tcx2(*pk["tcx2"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out,
-                                   status=self._status_word(obsv_p.device), pingpong=pingpong)
-        if precision == "fp16x2":
+        if single:
             return ops.decode_tcx(*pk["tcx"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out,
                                   status=self._status_word(obsv_p.device))
+        if precision == "fp16x2":
+            return ops.decode_pair(*pk["pair"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out,
+                                   status=self._status_word(obsv_p.device))
         if precision != "fp32":
-            raise ValueError("precision must be 'fp32', 'fp16x2' or 'bf16'")
+            raise ValueError("precision must be 'fp32', 'fp16x2', 'fp16x2s' or 'bf16'")
         return ops.decode(pk["enc"], pk["dec"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
 
     def predict(self, obsv_p, noise, n_next, sub_batches=()):

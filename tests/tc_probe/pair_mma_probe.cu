@@ -1,6 +1,6 @@
 // Probe (bring-up aid, not product code): tcgen05.mma with cta_group::2 (a CTA pair, UMMA M = 256).
 //  part A  correctness: D = A.B^T for small-integer fp16 operands, A from shared memory (SS) and from TMEM (TS), operand-ready
-//          signalling through remote mbarrier arrives on the leader CTA -- the protocol decode_fwd_tcx2 uses
+//          signalling through remote mbarrier arrives on the leader CTA -- the protocol decode_fwd_pair uses
 //  part B  cost: cycles per MMA of a back-to-back sequence, cta_group::1 and ::2, SS and TS, N = 64 .. 256
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o pair_mma_probe.bin pair_mma_probe.cu
 #include <cuda_fp16.h>

@@ -14,10 +14,11 @@ from golden_data import synthetic_scenes
 pytestmark = pytest.mark.gpu
 
 ATOL = 2e-5
-PRECISION = "fp32"      # set per test by the `precision` fixture: every test runs on both fp32-faithful decode kernels
+PRECISION = "fp32"      # set per test by the `precision` fixture: every test runs on all three fp32-faithful decode kernels
+                        # (FFMA, CTA-pair tcgen05 = the default, one-tile-per-SM tcgen05)
 
 
-@pytest.fixture(autouse=True, params=["fp32", "fp16x2"])
+@pytest.fixture(autouse=True, params=["fp32", "fp16x2", "fp16x2s"])
 def precision(request):
     global PRECISION
     PRECISION = request.param

@@ -78,9 +78,13 @@ def test_tc_decode_vs_bf16_emulation_and_oracle(sizes, k):
     assert ((got[..., :2] - prev) - got[..., 2:]).abs().max().item() < 1e-6
 
 
+SPLIT_KERNELS = ["fp16x2", "fp16x2s"]     # CTA-pair kernel (decode_fwd_pair.cu, the default) and one-tile-per-SM kernel (decode_fwd_tcx.cu)
+
+
+@pytest.mark.parametrize("prec", SPLIT_KERNELS)
 @pytest.mark.parametrize("sizes,k", [([8] * 16, 1), ([5, 1, 32, 2, 9], 3), ([8] * 40, 7), ([6] * 36, 2)])
-def test_tcx_fp16_split_decode_is_fp32_faithful(sizes, k):
-    """tcgen05 kernel on fp16 hi/lo split operands vs the fp32 oracle: operator tolerance 2e-5 (normalised),
+def test_tcx_fp16_split_decode_is_fp32_faithful(sizes, k, prec):
+    """tcgen05 kernels on fp16 hi/lo split operands vs the fp32 oracle: operator tolerance 2e-5 (normalised),
     best-of-K ADE/FDE within the 1e-4 bar of north_star."""
     import socialways_b200 as sw
     from socialways_b200 import ops
@@ -98,10 +102,10 @@ def test_tcx_fp16_split_decode_is_fp32_faithful(sizes, k):
     gen = gen.cuda().requires_grad_(False)
     for social in (True, False):
         gen.use_social = social
-        got = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision="fp16x2")
+        got = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision=prec)
         want = torch.stack([so.predict(P, obsv, noise[i], 12, data["batches"], social, "closed") for i in range(k)])
         err = (got.cpu() - want).abs().max().item()
-        print(f"fp16x2 tensor-core decode (use_social={social}): max |gpu - fp32 oracle| = {err:.2e}")
+        print(f"{prec} tensor-core decode (use_social={social}): max |gpu - fp32 oracle| = {err:.2e}")
         assert err < 2e-5, err
         m = ops.bestofk_metrics(got, pred.cuda(), sc.sx).cpu()
         e = (((want[..., :2] - pred) / sc.sx) ** 2).sum(-1).sqrt()
@@ -179,8 +183,35 @@ def test_pool_tcx_rejects_scenes_beyond_its_limit():
 # ---------------------------------------------------------------------------------------------------------------------
 # fp16 hi/lo split hardening: trained checkpoints, inputs far from the normalised range, the overflow guard
 # ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,k,n_next", [(1, 1, 12), (128, 1, 1), (129, 2, 2), (257, 3, 12), (640, 1, 5), (3 * 128 * 148 + 77, 1, 3),
+                                           (4099, 20, 12)])
+def test_pair_decode_tile_and_unit_edge_cases(rows, k, n_next):
+    """The CTA-pair kernel's work split (unit = two tiles, two unit slots per pair, 74 pairs): one row, exactly one tile, an odd
+    last unit, fewer units than slots, more units than one wave, short horizons -- against the FFMA kernel on the same inputs
+    (which the other tests pin to the oracle), bit-for-bit agreement with the one-tile-per-SM tensor-core kernel's tolerance."""
+    import socialways_b200 as sw
+    from socialways_b200 import ops
+    torch.manual_seed(rows)
+    gen = sw.Generator(use_social=True).cuda().requires_grad_(False)
+    pk = gen.packs()
+    g = torch.Generator(device="cuda").manual_seed(rows + 1)
+    h = torch.randn(rows, 64, device="cuda", generator=g) * 0.3
+    c = torch.randn(rows, 64, device="cuda", generator=g) * 0.3
+    pooled = torch.randn(rows, 64, device="cuda", generator=g) * 0.3
+    x_last = torch.randn(rows, 4, device="cuda", generator=g) * 0.1
+    noise = torch.rand(k, rows, 32, device="cuda", generator=g)
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for pl in (pooled, None):
+        want = ops.decode(pk["enc"], pk["dec"], h, c, pl, noise, x_last, n_next)
+        got = ops.decode_pair(*pk["pair"], h, c, pl, noise, x_last, n_next, status=status)
+        assert got.shape == want.shape and torch.isfinite(got).all()
+        assert (got - want).abs().max().item() < 2e-5
+    assert int(status.item()) == 0
+
+
+@pytest.mark.parametrize("prec", SPLIT_KERNELS)
 @pytest.mark.parametrize("case", ["train_toy_216.npz", "train_ragged.npz"])
-def test_fp16x2_on_trained_weights(case):
+def test_fp16x2_on_trained_weights(case, prec):
     """Trained weights, not random init: for the toy case the post-training weights the unmodified reference produced
     (tests/golden/train_toy_216.npz `w1.*`); for the obs 8 / pred 12 case the weights after the golden number of epochs of
     this package's trainer from the golden start (test_gpu_training pins those to the reference's norms).  Tensor-core
@@ -210,7 +241,7 @@ def test_fp16x2_on_trained_weights(case):
     gen = gen.cuda()
     torch.manual_seed(3)
     noise = torch.rand(5, obsv.shape[0], 32)
-    a = gen.predict_k(obsv.cuda(), noise.cuda(), n_next, data["batches"], precision="fp16x2")
+    a = gen.predict_k(obsv.cuda(), noise.cuda(), n_next, data["batches"], precision=prec)
     b = gen.predict_k(obsv.cuda(), noise.cuda(), n_next, data["batches"], precision="fp32")
     assert not gen.fp16_overflowed()
     assert (a - b).abs().max().item() < 2e-5
@@ -218,8 +249,9 @@ def test_fp16x2_on_trained_weights(case):
     assert (a.cpu() - ref).abs().max().item() < 2e-5
 
 
+@pytest.mark.parametrize("prec", SPLIT_KERNELS)
 @pytest.mark.parametrize("scale", [1e3, 1e-4])
-def test_fp16x2_on_inputs_far_from_the_normalised_range(scale):
+def test_fp16x2_on_inputs_far_from_the_normalised_range(scale, prec):
     """Coordinates 1 000 x larger (metres instead of Scale-normalised) or 10 000 x smaller: positions are integrated in
     fp32 and enter the split as one K block, so the tensor-core path must track the FFMA path relative to the magnitude."""
     import socialways_b200 as sw
@@ -229,14 +261,15 @@ def test_fp16x2_on_inputs_far_from_the_normalised_range(scale):
     d = synthetic_scenes([8, 3, 1, 6, 8, 8, 2, 7], seed=4)
     obsv = (torch.from_numpy(d["obsvs"]) * 0.05 * scale).cuda()
     noise = torch.rand(4, obsv.shape[0], 32).cuda()
-    a = gen.predict_k(obsv, noise, 12, d["batches"], precision="fp16x2")
+    a = gen.predict_k(obsv, noise, 12, d["batches"], precision=prec)
     b = gen.predict_k(obsv, noise, 12, d["batches"], precision="fp32")
     assert not gen.fp16_overflowed()
     tol = 2e-5 * max(1.0, b.abs().max().item())
     assert torch.isfinite(a).all() and (a - b).abs().max().item() < tol
 
 
-def test_fp16_overflow_is_flagged_and_test_falls_back_to_fp32(capsys):
+@pytest.mark.parametrize("prec", SPLIT_KERNELS)
+def test_fp16_overflow_is_flagged_and_test_falls_back_to_fp32(capsys, prec):
     """An operand beyond fp16's range (here: a layer-1 bias that pushes a1 past 65 504) must never pass silently: the
     status word is raised, and SocialWaysTrainer.test() reruns on the fp32 kernels and reports the fp32 numbers."""
     import socialways_b200 as sw
@@ -248,7 +281,7 @@ def test_fp16_overflow_is_flagged_and_test_falls_back_to_fp32(capsys):
     tr = SocialWaysTrainer(so.toy_samples(216, 6), batch_size=64, use_social=True, weights=W)
     torch.manual_seed(0)
     state = torch.get_rng_state()
-    tr.generator.inference_precision = "fp16x2"
+    tr.generator.inference_precision = prec
     m_tc = tr.test(5, verbose=False)
     assert "falls back to the fp32 kernels" in capsys.readouterr().out
     torch.set_rng_state(state)
