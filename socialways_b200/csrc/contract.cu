@@ -202,12 +202,11 @@ struct TcSmem {
     int last;
 };
 
-__device__ __forceinline__ void umma_issue_ss_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                   bool accumulate, bool leader) {
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-                 "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate), "r"((uint32_t)leader)
-                 : "memory");
+// issued by ONE elected lane (inside `if (elect_one())`, sw_umma.cuh)
+__device__ __forceinline__ void umma1_issue_ss_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
 
 // x -> (hi, lo): hi = x with the 13 low mantissa bits cleared (exactly a tf32 number), lo = (x - hi) rounded to tf32
@@ -330,19 +329,21 @@ contract_tc_kernel(const __grid_constant__ ContractParams P, float* __restrict__
         __syncthreads();
         if (warp == 0) {
             ptx::tcgen05_fence_after_thread_sync();
-            const bool leader = lane == 0;
             // canonical K-major, no swizzle: core matrix = 8 rows x 16 B; SBO (8-row group stride) = 128 B,
             // LBO (K-chunk stride) = the padded chunk size; one tf32 MMA (K = 8) spans two chunks
             const uint64_t ah = umma_desc_uniform(s.a_hi, TC_CHUNK * 4, 128), al = umma_desc_uniform(s.a_lo, TC_CHUNK * 4, 128);
             const uint64_t bh = umma_desc_uniform(s.b_hi, TC_CHUNK * 4, 128), bl = umma_desc_uniform(s.b_lo, TC_CHUNK * 4, 128);
+            if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint64_t off = (uint64_t)(ks * 2 * TC_CHUNK * 4 / 16);
-                umma_issue_ss_tf32(tmem, ah + off, bh + off, idesc, img > img0 || ks > 0, leader);
-                umma_issue_ss_tf32(tmem, ah + off, bl + off, idesc, true, leader);
-                umma_issue_ss_tf32(tmem, al + off, bh + off, idesc, true, leader);
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint64_t off = (uint64_t)(ks * 2 * TC_CHUNK * 4 / 16);
+                    umma1_issue_ss_tf32(tmem, ah + off, bh + off, idesc, img > img0 || ks > 0);
+                    umma1_issue_ss_tf32(tmem, ah + off, bl + off, idesc, true);
+                    umma1_issue_ss_tf32(tmem, al + off, bh + off, idesc, true);
+                }
+                umma1_commit(&s.bar);
             }
-            umma_commit(&s.bar, leader);
+            __syncwarp();
         }
         if (img + 1 < img1) {                                         // next image's loads: in flight during the MMAs + the wait
             fetch_operand(ra, J.a, J.a_stride, J.a_k0, mt * TC_M, mrows, J.K, a_ones, img + 1, J.a_kind, J.n_rows);

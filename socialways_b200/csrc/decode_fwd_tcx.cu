@@ -71,21 +71,22 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
 }
 
 // three-pass product with both operands in shared memory (called by the whole issuing warp)
+// (all MMA forms below are the single-thread ones of sw_umma.cuh: called by ONE elected lane of warp 0, back to back)
 template <int B_ROWS, int N, int KB>
 __device__ __forceinline__ void mma3_ss(uint32_t d, const __half* a_hi, const __half* a_lo, const __half* b_hi,
-                                        const __half* b_lo, bool leader, bool accumulate_first = false) {
-    umma_ss<B_ROWS, N, KB>(d, a_hi, b_hi, FMT_F16, accumulate_first, leader);
-    umma_ss<B_ROWS, N, KB>(d, a_hi, b_lo, FMT_F16, true, leader);
-    umma_ss<B_ROWS, N, KB>(d, a_lo, b_hi, FMT_F16, true, leader);
+                                        const __half* b_lo, bool accumulate_first = false) {
+    umma1_ss<B_ROWS, N, KB>(d, a_hi, b_hi, FMT_F16, accumulate_first);
+    umma1_ss<B_ROWS, N, KB>(d, a_hi, b_lo, FMT_F16, true);
+    umma1_ss<B_ROWS, N, KB>(d, a_lo, b_hi, FMT_F16, true);
 }
 
 // three-pass product with the A operand (hi / lo column blocks) in TMEM
 template <int B_ROWS, int N, int KB, int A_STRIDE = 8>
 __device__ __forceinline__ void mma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const __half* b_hi, const __half* b_lo,
-                                        bool accumulate_first, bool leader) {
-    umma_ts<B_ROWS, N, KB, A_STRIDE>(d, a_hi, b_hi, FMT_F16, accumulate_first, leader);
-    umma_ts<B_ROWS, N, KB, A_STRIDE>(d, a_hi, b_lo, FMT_F16, true, leader);
-    umma_ts<B_ROWS, N, KB, A_STRIDE>(d, a_lo, b_hi, FMT_F16, true, leader);
+                                        bool accumulate_first) {
+    umma1_ts<B_ROWS, N, KB, A_STRIDE>(d, a_hi, b_hi, FMT_F16, accumulate_first);
+    umma1_ts<B_ROWS, N, KB, A_STRIDE>(d, a_hi, b_lo, FMT_F16, true);
+    umma1_ts<B_ROWS, N, KB, A_STRIDE>(d, a_lo, b_hi, FMT_F16, true);
 }
 
 // Epilogue of layer 1, NKB K-blocks (16 output features each) of this thread: y = lrelu(acc + c1) (c1 carries the bias),
@@ -154,7 +155,6 @@ decode_fwd_tcx_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lq = warp & 3, cq = warp >> 2;
     const int r = lq * 32 + lane;
-    const bool leader = lane == 0;          // lane of warp 0 that issues the MMAs
 
     if (warp == 0) {
         ptx::tcgen05_alloc(ptx::cta_group_1, &s.tmem_base, 512u);
@@ -292,9 +292,12 @@ decode_fwd_tcx_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][
             }
             if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
-                mma3_ts<160, 160, 2>(tmem + XC_C1, tmem + XC_R1 + ch * 16, tmem + XC_R1 + 48 + ch * 16, s.stage,
-                                     s.stage + XW_SZ_CHUNK / 2, ch > 0, leader);
-                umma_commit(&s.bar[0], leader);
+                if (elect_one()) {
+                    mma3_ts<160, 160, 2>(tmem + XC_C1, tmem + XC_R1 + ch * 16, tmem + XC_R1 + 48 + ch * 16, s.stage,
+                                         s.stage + XW_SZ_CHUNK / 2, ch > 0);
+                    umma1_commit(&s.bar[0]);
+                }
+                __syncwarp();
             }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;       // staging buffer is free again / c1 complete
             ptx::tcgen05_fence_after_thread_sync();
@@ -310,8 +313,11 @@ decode_fwd_tcx_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][
         __syncthreads();
         if (warp == 0) {    // layer 1 of step 0 (the later steps' layer-1 MMAs are issued from inside the previous gate epilogue)
             ptx::tcgen05_fence_after_thread_sync();
-            mma3_ss<160, 160, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_W1H_HI, s.w + XW_W1H_LO, leader);
-            umma_commit(&s.bar[0], leader);
+            if (elect_one()) {
+                mma3_ss<160, 160, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_W1H_HI, s.w + XW_W1H_LO);
+                umma1_commit(&s.bar[0]);
+            }
+            __syncwarp();
         }
 
         for (int t = 0; t < n_next; ++t) {
@@ -334,12 +340,15 @@ decode_fwd_tcx_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][
                 // W2 hi and lo rows are stacked along N ([20 chunks][hi 80 | lo 80 rows][8]): one N = 160 pass yields a1_hi.W2_hi
                 // in columns [0,80) and a1_hi.W2_lo in [80,160); a1_lo.W2_hi accumulates into [0,80).  20 MMAs instead of 30
                 // (every tcgen05.mma carries a fixed cost); the epilogue adds the two column halves.
-                umma_ts<160, 160, 10, 16>(tmem + XC_RG, tmem + XC_R1, s.w + XW_W2_CAT, FMT_F16, false, leader);
-                umma_ts<160, 80, 10, 16>(tmem + XC_RG, tmem + XC_R1 + 8, s.w + XW_W2_CAT, FMT_F16, true, leader);
-                umma_commit(&s.bar[0], leader);
-                if (feed_back)     // gates, N half 1, h part -> [160,288): runs under the L2 / L34 epilogues (its x block and
-                                   // commit follow once the velocity exists)
-                    mma3_ss<256, 128, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_WHH_HI + 128 * 8, s.w + XW_WHH_LO + 128 * 8, leader);
+                if (elect_one()) {
+                    umma1_ts<160, 160, 10, 16>(tmem + XC_RG, tmem + XC_R1, s.w + XW_W2_CAT, FMT_F16, false);
+                    umma1_ts<160, 80, 10, 16>(tmem + XC_RG, tmem + XC_R1 + 8, s.w + XW_W2_CAT, FMT_F16, true);
+                    umma1_commit(&s.bar[0]);
+                    if (feed_back)     // gates, N half 1, h part -> [160,288): runs under the L2 / L34 epilogues (its x block and
+                                       // commit follow once the velocity exists)
+                        mma3_ss<256, 128, 4>(tmem + XC_R1, s.h[0], s.h[1], s.w + XW_WHH_HI + 128 * 8, s.w + XW_WHH_LO + 128 * 8);
+                }
+                __syncwarp();
             }
             mbar_wait(&s.bar[0], ph0); ph0 ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
@@ -381,11 +390,14 @@ decode_fwd_tcx_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][
             //                  while the tensor pipe works on half 0. ----------------
             if (warp == 0) {
                 ptx::tcgen05_fence_after_thread_sync();
-                umma_ss<256, 128, 1>(tmem + XC_R1, s.xk, s.w + XW_WXK + 128 * 8, FMT_F16, true, leader);
-                umma_commit(&s.bar[2], leader);
-                mma3_ss<256, 128, 4>(tmem + XC_RG, s.h[0], s.h[1], s.w + XW_WHH_HI, s.w + XW_WHH_LO, leader);
-                umma_ss<256, 128, 1>(tmem + XC_RG, s.xk, s.w + XW_WXK, FMT_F16, true, leader);
-                umma_commit(&s.bar[1], leader);
+                if (elect_one()) {
+                    umma1_ss<256, 128, 1>(tmem + XC_R1, s.xk, s.w + XW_WXK + 128 * 8, FMT_F16, true);
+                    umma1_commit(&s.bar[2]);
+                    mma3_ss<256, 128, 4>(tmem + XC_RG, s.h[0], s.h[1], s.w + XW_WHH_HI, s.w + XW_WHH_LO);
+                    umma1_ss<256, 128, 1>(tmem + XC_RG, s.xk, s.w + XW_WXK, FMT_F16, true);
+                    umma1_commit(&s.bar[1]);
+                }
+                __syncwarp();
             }
             // ---------------- LSTM cell.  EVERY quarter first updates 8 units of gate half 1 (units 32 + 8cq .., ready early:
             //                  its h part ran under the epilogues) while the tensor pipe works on half 0, then 8 units of half 0
@@ -423,9 +435,12 @@ decode_fwd_tcx_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][
                 if (warp == 0) {   // next step's layer 1, the two K blocks whose h chunks are complete
                     ptx::tcgen05_fence_after_thread_sync();
                     const int kb0 = round == 0 ? 2 : 0;
-                    mma3_ss<160, 160, 2>(tmem + XC_R1, s.h[0] + kb0 * 2 * X_ROWS * 8, s.h[1] + kb0 * 2 * X_ROWS * 8,
-                                         s.w + XW_W1H_HI + kb0 * 2 * 160 * 8, s.w + XW_W1H_LO + kb0 * 2 * 160 * 8, leader, round == 1);
-                    if (round == 1) umma_commit(&s.bar[0], leader);
+                    if (elect_one()) {
+                        mma3_ss<160, 160, 2>(tmem + XC_R1, s.h[0] + kb0 * 2 * X_ROWS * 8, s.h[1] + kb0 * 2 * X_ROWS * 8,
+                                             s.w + XW_W1H_HI + kb0 * 2 * 160 * 8, s.w + XW_W1H_LO + kb0 * 2 * 160 * 8, round == 1);
+                        if (round == 1) umma1_commit(&s.bar[0]);
+                    }
+                    __syncwarp();
                 }
             }
             ph1 ^= 1;

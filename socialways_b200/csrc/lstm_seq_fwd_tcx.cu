@@ -41,7 +41,6 @@ lstm_seq_fwd_tcx_kernel(const __half* __restrict__ w16, const float* __restrict_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lq = warp & 3, cq = warp >> 2;                 // TMEM lane quarter, column half (units 32 cq .. 32 cq + 31)
     const int r = lq * 32 + lane;
-    const bool leader = lane == 0;
 
     for (int i = tid * 8; i < EW_TOTAL; i += E_THREADS * 8)
         *reinterpret_cast<uint4*>(s.w + i) = __ldg(reinterpret_cast<const uint4*>(w16 + i));
@@ -78,12 +77,15 @@ lstm_seq_fwd_tcx_kernel(const __half* __restrict__ w16, const float* __restrict_
         __syncthreads();
 
         for (int t = 0; t < T; ++t) {
-            if (warp == 0) {
+            if (warp == 0) {    // one elected lane issues the 12 MMAs back to back (sw_umma.cuh: single-thread issue forms)
                 ptx::tcgen05_fence_after_thread_sync();
-                umma_ss<256, 256, 4>(tmem, s.h[0], s.w + EW_HI, 0u, false, leader);
-                umma_ss<256, 256, 4>(tmem, s.h[0], s.w + EW_LO, 0u, true, leader);
-                umma_ss<256, 256, 4>(tmem, s.h[1], s.w + EW_HI, 0u, true, leader);
-                umma_commit(&s.bar, leader);
+                if (elect_one()) {
+                    umma1_ss<256, 256, 4>(tmem, s.h[0], s.w + EW_HI, 0u, false);
+                    umma1_ss<256, 256, 4>(tmem, s.h[0], s.w + EW_LO, 0u, true);
+                    umma1_ss<256, 256, 4>(tmem, s.h[1], s.w + EW_HI, 0u, true);
+                    umma1_commit(&s.bar);
+                }
+                __syncwarp();
             }
             // the 4-d state (p_t, p_t - p_{t-1}), v_0 := v_1 (train.py:131-133), formed while the MMAs run
             float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;

@@ -65,7 +65,6 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(sstart + PT_ROWS + 1);   // 8 B aligned (even int count)
     uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bar + 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool leader = lane == 0;
 
     const int row0 = units ? units[2 * blockIdx.x] : blockIdx.x * PT_ROWS;
     const int row1 = units ? row0 + units[2 * blockIdx.x + 1] : min(row0 + PT_ROWS, n_agents);
@@ -167,10 +166,13 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
         __syncthreads();
         if (warp == 0) {                                // a2 = a1 . W2^T : [128 pairs] x [64] x K = 32, three passes
             ptx::tcgen05_fence_after_thread_sync();
-            umma_ss<64, 64, 2>(tmem, a1s, w2, 0u, false, leader);
-            umma_ss<64, 64, 2>(tmem, a1s, w2 + 2048, 0u, true, leader);
-            umma_ss<64, 64, 2>(tmem, a1s + 4096, w2, 0u, true, leader);
-            umma_commit(bar, leader);
+            if (elect_one()) {                          // single-lane issue (sw_umma.cuh)
+                umma1_ss<64, 64, 2>(tmem, a1s, w2, 0u, false);
+                umma1_ss<64, 64, 2>(tmem, a1s, w2 + 2048, 0u, true);
+                umma1_ss<64, 64, 2>(tmem, a1s + 4096, w2, 0u, true);
+                umma1_commit(bar);
+            }
+            __syncwarp();
         }
         mbar_wait(bar, ph); ph ^= 1;
         ptx::tcgen05_fence_after_thread_sync();

@@ -183,6 +183,38 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+// cta_group::1 forms
+__device__ __forceinline__ void umma1_commit(unsigned long long* bar) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(addr) : "memory");
+}
+__device__ __forceinline__ void umma1_issue_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma1_issue_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 :: "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+template <int B_ROWS, int N, int KB, typename T>
+__device__ __forceinline__ void umma1_ss(uint32_t d_tmem, const T* a, const T* b, uint32_t ab_format, bool accumulate_first) {
+    const uint32_t idesc = umma_idesc(N, ab_format);
+    const uint64_t ad = umma_desc(a, 128 * 16, 128), bd = umma_desc(b, B_ROWS * 16, 128);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+        umma1_issue_ss(d_tmem, ad + (uint64_t)(kb * 2 * 128), bd + (uint64_t)(kb * 2 * B_ROWS), idesc, (accumulate_first || kb > 0) ? 1u : 0u);
+}
+template <int B_ROWS, int N, int KB, int A_STRIDE = 8, typename T>
+__device__ __forceinline__ void umma1_ts(uint32_t d_tmem, uint32_t a_tmem, const T* b, uint32_t ab_format, bool accumulate_first) {
+    const uint32_t idesc = umma_idesc(N, ab_format);
+    const uint64_t bd = umma_desc(b, B_ROWS * 16, 128);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+        umma1_issue_ts(d_tmem, a_tmem + kb * A_STRIDE, bd + (uint64_t)(kb * 2 * B_ROWS), idesc, (accumulate_first || kb > 0) ? 1u : 0u);
+}
+// cta_group::2 forms
 __device__ __forceinline__ void umma1_commit_pair(unsigned long long* bar) {
     const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
