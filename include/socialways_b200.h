@@ -169,11 +169,6 @@ int sw_decode_fwd_pair(const void* pair_w16, const float* pair_f32, const float*
                        int* status, int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 int sw_decode_pair_pack_sizes(int* n_w16, int* n_f32);
 long long sw_decode_pair_scratch_bytes(int sm_count);
-/* Same arguments / results as sw_decode_fwd_pair; warps specialised by pipe (csrc/decode_fwd_pair2.cu): 8 warps run the
- * layer-1 / layer-2 epilogues of both tile slots, 8 warps the LSTM cell update of both slots, one issuing warp per slot. */
-int sw_decode_fwd_pair2(const void* pair_w16, const float* pair_f32, const float* h0, const float* c0, const float* pooled,
-                        const float* noise, const float* x_last, float* out, void* scratch, long long scratch_bytes,
-                        int* status, int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 
 /* Discriminator FC heads (train.py:281-292, 300-309), one thread per trajectory, all 8 Linear layers fused.
  *   pack: sw_disc_heads_pack_floats(P, L) floats = Wo1[32][64] bo1 Wo2[32][32] bo2 Wp1[32][P] bp1 Wp2[32][32] bp2

@@ -23,8 +23,8 @@ xl = torch.rand(n, 4, device="cuda", generator=g)
 out = torch.empty(k, n, T, 4, device="cuda")
 which = sys.argv[1] if len(sys.argv) > 1 else "tcx"       # "tcx" (one tile per SM) or "pair" (CTA pairs, two tiles per SM)
 for _ in range(3):
-    if which in ("pair", "pair2"):
-        ops.decode_pair(*pk["pair"], h, c, pooled, noise, xl, T, out=out, variant=2 if which == "pair2" else 1)
+    if which == "pair":
+        ops.decode_pair(*pk["pair"], h, c, pooled, noise, xl, T, out=out)
     else:
         ops.decode_tcx(*pk["tcx"], h, c, pooled, noise, xl, T, out=out)
 torch.cuda.synchronize()

@@ -14,11 +14,7 @@ from golden_data import synthetic_scenes
 from oracle import socialways_oracle as so
 
 
-VARIANT2 = True      # small cases: also run the pipe-specialised kernel (variant 2) and print |pair2 - pair| instead of |pair - tcx|
-
-
 def small_cases():
-    from socialways_b200 import ops
     P = so.init_weights(seed=6)
     gen = sw.Generator(use_social=True)
     gen.load_state_dict({key: v for key, v in P.items() if not key.startswith("D.")})
@@ -41,18 +37,6 @@ def small_cases():
             else:
                 err = float("nan")
             d = (got - old).abs().max().item()
-            if VARIANT2:
-                pk = gen.packs()
-                enc = ops.lstm_seq_tcx(*pk["enc_tcx"], obsv.cuda())
-                pooled = None
-                if social:
-                    scenes = gen.scene_index(data["batches"], n, obsv.cuda().device)
-                    ub = ops.rows_linear(enc["h"], pk["pool_m"], pk["pool_m0"])
-                    pooled = ops.pool(pk["pool"], enc["x_last"], enc["h"], ub, scenes)
-                g2 = ops.decode_pair(*pk["pair"], enc["h"], enc["c"], pooled, noise.cuda(), enc["x_last"], 12, variant=2)
-                g1 = ops.decode_pair(*pk["pair"], enc["h"], enc["c"], pooled, noise.cuda(), enc["x_last"], 12)
-                torch.cuda.synchronize()
-                d = (g2 - g1).abs().max().item()
             print(f"rows {k * n:6d} social={social}: |pair - oracle| = {err:.2e}  |pair - tcx| = {d:.2e}  overflow={gen.fp16_overflowed()}",
                   flush=True)
 
@@ -73,8 +57,7 @@ def bench_case(scenes=16384, agents=8, k=20, reps=5):
     from socialways_b200 import ops
     outs = {}
     for name, fn in (("tcx", lambda o: ops.decode_tcx(*pk["tcx"], h, c, pooled, noise, x_last, 12, out=o)),
-                     ("pair", lambda o: ops.decode_pair(*pk["pair"], h, c, pooled, noise, x_last, 12, out=o)),
-                     ("pair2", lambda o: ops.decode_pair(*pk["pair"], h, c, pooled, noise, x_last, 12, out=o, variant=2))):
+                     ("pair", lambda o: ops.decode_pair(*pk["pair"], h, c, pooled, noise, x_last, 12, out=o))):
         out = torch.empty(k, n, 12, 4, device="cuda")
         fn(out)
         torch.cuda.synchronize()
@@ -87,9 +70,8 @@ def bench_case(scenes=16384, agents=8, k=20, reps=5):
         ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)]
         outs[name] = out
         print(f"{name}: {min(ms):.3f} ms (median {sorted(ms)[len(ms) // 2]:.3f})  -> {k * n / min(ms) / 1e3:.1f} M traj/s", flush=True)
-    for name in ("pair", "pair2"):
-        print(f"max |{name} - tcx| on the bench workload:", (outs[name] - outs["tcx"]).abs().max().item(),
-              " finite:", bool(torch.isfinite(outs[name]).all()))
+    print("max |pair - tcx| on the bench workload:", (outs["pair"] - outs["tcx"]).abs().max().item(),
+          " finite:", bool(torch.isfinite(outs["pair"]).all()))
 
 
 if __name__ == "__main__":

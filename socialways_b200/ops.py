@@ -307,7 +307,7 @@ def decode_pair_scratch(device):
     return _PAIR_SCRATCH[key]
 
 
-def decode_pair(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, status=None, scratch=None, variant=1):
+def decode_pair(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, status=None, scratch=None):
     """sw_decode_fwd_pair: the fp16 hi/lo split tcgen05 decode kernel with two tiles in flight per SM (CTA pairs, cta_group::2,
     epilogue warps in ping-pong over two tile slots, dedicated issuing warp); same inputs, outputs and arithmetic as decode_tcx.
     Packs from packing.pack_decoder_pair."""
@@ -323,13 +323,12 @@ def decode_pair(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, statu
         out = torch.empty(k, n, n_next, 4, device=noise.device)
     if scratch is None:
         scratch = decode_pair_scratch(noise.device)
-    name = "sw_decode_fwd_pair2" if variant == 2 else "sw_decode_fwd_pair"
-    code = getattr(_lib.lib(), name)(w16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(_f32(h0)), _lib.ptr(_f32(c0)),
+    code = _lib.lib().sw_decode_fwd_pair(w16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(_f32(h0)), _lib.ptr(_f32(c0)),
                                          _lib.ptr(None if pooled is None else _f32(pooled)), _lib.ptr(noise),
                                          _lib.ptr(_f32(x_last)), _lib.ptr(out), scratch.data_ptr(), scratch.numel(),
                                          None if status is None else status.data_ptr(), n, k, n_next,
                                          sm_count(noise.device), _stream())
-    _lib.check(code, name)
+    _lib.check(code, "sw_decode_fwd_pair")
     return out
 
 
