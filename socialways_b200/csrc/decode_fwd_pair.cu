@@ -64,6 +64,12 @@ __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" :: "
 // finishing warps wait for all 16
 __device__ __forceinline__ void vel_arrive(int sl) { asm volatile("bar.arrive %0, %1;" :: "r"(2 + sl), "n"(Q_EPI) : "memory"); }
 __device__ __forceinline__ void vel_sync(int sl) { asm volatile("bar.sync %0, %1;" :: "r"(2 + sl), "n"(Q_EPI) : "memory"); }
+// ... and the way back (named barrier 4 + slot): the finishing warps announce "partials consumed", the contributing warps pass
+// it before they overwrite the buffer a step later.  The arrival is a whole step old by then (the next write sits behind this
+// slot's cell update, layer-1 MMAs and layer-1 epilogue, all of which wait for the finishing warps), so nobody ever blocks
+// here; it makes the write-after-read order explicit instead of implied by the mbarrier / MMA chain (and visible to racecheck).
+__device__ __forceinline__ void vel_free_arrive(int sl) { asm volatile("bar.arrive %0, %1;" :: "r"(4 + sl), "n"(Q_EPI) : "memory"); }
+__device__ __forceinline__ void vel_free_sync(int sl) { asm volatile("bar.sync %0, %1;" :: "r"(4 + sl), "n"(Q_EPI) : "memory"); }
 __device__ __forceinline__ void wait_full3(unsigned long long* bar, uint32_t parity) {
     mbar_wait(bar, parity);
     ptx::tcgen05_fence_after_thread_sync();
@@ -275,6 +281,8 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             fin[1] = cq == 1;
         }
         const bool three[2] = {cq < 2, cq >= 2};
+        if (fin[0]) vel_free_arrive(0);     // prime the "partials consumed" barriers: the first step of the first tile finds them passed
+        if (fin[1]) vel_free_arrive(1);
 
         for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
             const int n_act = ub + 1 < n_units ? 2 : 1;
@@ -431,6 +439,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 }
                 ptx::tcgen05_fence_before_thread_sync();
                 if (!fin[sl]) {
+                    vel_free_sync(sl);
                     s.vpart[sl][(cq * 2) * P_ROWS + r] = v0; s.vpart[sl][(cq * 2 + 1) * P_ROWS + r] = v1;
                     vel_arrive(sl);     // (bar.arrive orders the shared-memory writes above before the finishing warps' reads)
                 } else {            // velocity, integration, emit; (p, v) -> hi|lo x block of the gate MMA
@@ -439,6 +448,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         if (q != (sl == 0 ? 2 : 1)) { v0 += vp[(q * 2) * P_ROWS + r]; v1 += vp[(q * 2 + 1) * P_ROWS + r]; }
+                    vel_free_arrive(sl);
                     v0 += s.f32[PF_B34]; v1 += s.f32[PF_B34 + 1];
                     p0 += v0; p1 += v1;
                     out_of_range |= !(fmaxf(fmaxf(fabsf(p0), fabsf(p1)), fmaxf(fabsf(v0), fabsf(v1))) <= 6.0e4f);   // fp16 range guard
