@@ -57,9 +57,11 @@ int sw_lstm_seq_fwd(const float* lstm_pack, const float* x, int in_dim, int n_ro
                     float* x_last, float* stash_gates, float* stash_xh, int sm_count, void* stream);
 
 /* Tensor-core variant of sw_lstm_seq_fwd for the inference path (zero initial state, no stash, no y_out): the recurrent
- * projection h . Whh^T as tcgen05.mma on fp16 hi/lo split operands (fp32 accumulate in TMEM), Wx . x4 + b as fp32 FMAs.
- * enc_w16 / enc_f32 from packing.pack_encoder_tcx: Whh hi | lo fp16 canonical [2][8][256][8]; wx4 [256][4] | bL [256]. */
-int sw_lstm_seq_fwd_tcx(const void* enc_w16, const float* enc_f32, const float* x, int in_dim, int n_rows,
+ * projection h . Whh^T as tcgen05.mma on fp16 hi/lo split operands (fp32 accumulate in TMEM); Wx . x4 + b enters as one extra
+ * K block of the same MMA ([x_hi | x_lo | x_hi | 1 | 1 | 0 0] . [Wx_hi | Wx_hi | Wx_lo | b_hi | b_lo | 0 0]^T), gate rows
+ * pre-scaled by -log2(e) / -2 log2(e) so that the accumulator is the ex2 argument of the cell update.
+ * enc_w16 from packing.pack_encoder_tcx: Whh hi | lo fp16 canonical [2][8][256][8], then the x block [2][256][8]. */
+int sw_lstm_seq_fwd_tcx(const void* enc_w16, const float* x, int in_dim, int n_rows,
                         int n_steps, float* h_out, float* c_out, float* x_last, int sm_count, void* stream);
 
 /* Backward of sw_lstm_seq_fwd from a zero initial state.  Replaces autograd through nn.LSTM

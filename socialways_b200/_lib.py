@@ -23,7 +23,7 @@ _PROTOTYPES = {
     "sw_pool_pack_floats": (_I, []),
     "sw_decode_pack_t_floats": (_I, []),
     "sw_lstm_seq_fwd": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P]),
-    "sw_lstm_seq_fwd_tcx": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
+    "sw_lstm_seq_fwd_tcx": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _I, _P]),
     "sw_lstm_seq_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "sw_pool_fwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "sw_pool_bwd": (_I, [_P] * 17 + [_I, _I, _P]),

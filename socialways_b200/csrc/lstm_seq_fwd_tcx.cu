@@ -1,9 +1,12 @@
 // Tensor-core observation encoder: LSTM over the observed sequence from a zero state (reference EncoderLstm
 // observation pass, train.py:404 -> :262-269, with get_traj_4d :130-134 fused in) -- the inference-path variant of
-// lstm_seq_fwd.cu (no backward stash), same fp16 hi/lo split scheme as decode_fwd_tcx.cu:
-//     gates[128 x 256] = h (K = 64, hi|lo fp16 in shared memory) . Whh^T   as 3 tcgen05.mma passes, fp32 accumulate in TMEM
-//                      + Wx . x4_t + b                                      as fp32 FMAs in the epilogue (x4 never rounded)
-// One CTA = one 128-row tile, 256 threads (2 per row: column halves), 111 KB shared memory and 256 TMEM columns, so TWO
+// lstm_seq_fwd.cu (no backward stash), same fp16 hi/lo split scheme and the same operand tricks as the decode kernels:
+//     gates[128 x 256] = h (K = 64, hi|lo fp16 in shared memory) . Whh^T          3 tcgen05.mma passes, fp32 accumulate in TMEM
+//                      + [x_hi | x_lo | x_hi | 1 | 1 | 0 0] . [Wx_hi | Wx_hi | Wx_lo | b_hi | b_lo | 0 0]^T   ONE extra K block
+// with the gate rows of Whh / Wx / b pre-scaled on the host by -log2(e) (i, f, o) and -2 log2(e) (g): the accumulator IS the ex2
+// argument of the logistic forms, the epilogue is the cell update alone (the first version formed Wx.x + b and the scales in
+// the epilogue: ~61 instead of ~37 instructions per hidden unit, 0.26 -> see DESIGN.md).  h_0 = 0: step 0 issues the x block only.
+// One CTA = one 128-row tile, 256 threads (2 per row: unit halves), 108 KB shared memory and 256 TMEM columns, so TWO
 // CTAs are co-resident per SM and the MMAs of one overlap the gate epilogue of the other.
 #include <cuda_fp16.h>
 
@@ -13,13 +16,12 @@
 namespace sw {
 
 constexpr int E_ROWS = 128, E_THREADS = 256;
-constexpr int EW_HI = 0, EW_LO = 64 * 256, EW_TOTAL = 2 * 64 * 256;       // Whh hi | lo, canonical [8][256][8]
-constexpr int EF_WX4 = 0, EF_BL = 1024, EF_TOTAL = 1280;                  // wx4[256][4] | bL[256]
+constexpr int EW_HI = 0, EW_LO = 64 * 256, EW_XK = 2 * 64 * 256, EW_TOTAL = 2 * 64 * 256 + 256 * 16;   // Whh hi | lo [8][256][8], x block [2][256][8]
 
 struct EncSmem {
-    __half w[EW_TOTAL];                // 65 536 B
+    __half w[EW_TOTAL];                // 73 728 B
     __half h[2][8 * E_ROWS * 8];       // 32 768 B
-    float f32[EF_TOTAL];               //  5 120 B
+    __half xk[2 * E_ROWS * 8];         //  4 096 B: x-feedback A operand, one K block [2 chunks][128][8]
     unsigned long long bar;
     uint32_t tmem_base;
 };
@@ -33,7 +35,7 @@ __device__ __forceinline__ void enc_split2(float a, float b, uint32_t& hi, uint3
 }
 
 __global__ void __launch_bounds__(E_THREADS, 2)
-lstm_seq_fwd_tcx_kernel(const __half* __restrict__ w16, const float* __restrict__ wf32, const float* __restrict__ x, int in_dim,
+lstm_seq_fwd_tcx_kernel(const __half* __restrict__ w16, const float* __restrict__ x, int in_dim,
                         int n_rows, int T, float* __restrict__ h_out, float* __restrict__ c_out, float* __restrict__ x_last,
                         int n_tiles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -44,7 +46,6 @@ lstm_seq_fwd_tcx_kernel(const __half* __restrict__ w16, const float* __restrict_
 
     for (int i = tid * 8; i < EW_TOTAL; i += E_THREADS * 8)
         *reinterpret_cast<uint4*>(s.w + i) = __ldg(reinterpret_cast<const uint4*>(w16 + i));
-    for (int i = tid; i < EF_TOTAL; i += E_THREADS) s.f32[i] = __ldg(wf32 + i);
     if (warp == 0) {
         ptx::tcgen05_alloc(ptx::cta_group_1, &s.tmem_base, 256u);
         ptx::tcgen05_relinquish_alloc_permit(ptx::cta_group_1);
@@ -60,46 +61,60 @@ lstm_seq_fwd_tcx_kernel(const __half* __restrict__ w16, const float* __restrict_
     const uint32_t tmem = __shfl_sync(0xffffffffu, s.tmem_base, 0);
     const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16) + cq * 128;
     uint32_t ph = 0;
-    const float4* wx4 = reinterpret_cast<const float4*>(s.f32 + EF_WX4);
-    const float* bL = s.f32 + EF_BL;
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int row = tile * E_ROWS + r;
         const bool valid = row < n_rows;
         const float* xr = x + (size_t)(valid ? row : 0) * T * in_dim;
-        float c[32];
-#pragma unroll
-        for (int u = 0; u < 32; ++u) c[u] = 0.0f;
-        // h_0 = 0
-        for (int i = tid * 8; i < 2 * 8 * E_ROWS * 8; i += E_THREADS * 8) *reinterpret_cast<uint4*>(&s.h[0][0] + i) = make_uint4(0, 0, 0, 0);
-        ptx::fence_proxy_async(ptx::space_shared);
-        ptx::tcgen05_fence_before_thread_sync();
-        __syncthreads();
-
-        for (int t = 0; t < T; ++t) {
-            if (warp == 0) {    // one elected lane issues the 12 MMAs back to back (sw_umma.cuh: single-thread issue forms)
-                ptx::tcgen05_fence_after_thread_sync();
-                if (elect_one()) {
-                    umma1_ss<256, 256, 4>(tmem, s.h[0], s.w + EW_HI, 0u, false);
-                    umma1_ss<256, 256, 4>(tmem, s.h[0], s.w + EW_LO, 0u, true);
-                    umma1_ss<256, 256, 4>(tmem, s.h[1], s.w + EW_HI, 0u, true);
-                    umma1_commit(&s.bar);
-                }
-                __syncwarp();
-            }
-            // the 4-d state (p_t, p_t - p_{t-1}), v_0 := v_1 (train.py:131-133), formed while the MMAs run
-            float x0 = 0.f, x1 = 0.f, x2 = 0.f, x3 = 0.f;
+        // the 4-d state (p_t, p_t - p_{t-1}), v_0 := v_1 (train.py:131-133)
+        auto load_x = [&](int t) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid) {
                 if (in_dim == 2) {
                     const int tv = (t == 0) ? 1 : t;
                     const float2 p = __ldg(reinterpret_cast<const float2*>(xr) + t);
                     const float2 a = __ldg(reinterpret_cast<const float2*>(xr) + tv), b = __ldg(reinterpret_cast<const float2*>(xr) + tv - 1);
-                    x0 = p.x; x1 = p.y; x2 = a.x - b.x; x3 = a.y - b.y;
+                    v = make_float4(p.x, p.y, a.x - b.x, a.y - b.y);
                 } else {
-                    const float4 p = __ldg(reinterpret_cast<const float4*>(xr) + t);
-                    x0 = p.x; x1 = p.y; x2 = p.z; x3 = p.w;
+                    v = __ldg(reinterpret_cast<const float4*>(xr) + t);
                 }
-                if (t == T - 1 && x_last && cq == 0) *reinterpret_cast<float4*>(x_last + (size_t)row * 4) = make_float4(x0, x1, x2, x3);
+            }
+            return v;
+        };
+        // x_t -> hi|lo x block of the gate MMA (the unit-half-0 thread of the row)
+        auto put_x = [&](const float4& v) {
+            uint32_t hp, lp, hv, lv;
+            enc_split2(v.x, v.y, hp, lp);
+            enc_split2(v.z, v.w, hv, lv);
+            *reinterpret_cast<uint4*>(s.xk + (size_t)r * 8) = make_uint4(hp, hv, lp, lv);                      // k 0..7
+            *reinterpret_cast<uint4*>(s.xk + (size_t)(E_ROWS + r) * 8) = make_uint4(hp, hv, 0x3C003C00u, 0u);  // k 8..15
+        };
+        float c[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) c[u] = 0.0f;
+        float4 xt = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cq == 0) { xt = load_x(0); put_x(xt); }
+        ptx::fence_proxy_async(ptx::space_shared);
+        ptx::tcgen05_fence_before_thread_sync();
+        __syncthreads();
+
+        for (int t = 0; t < T; ++t) {
+            if (warp == 0) {    // one elected lane issues the MMAs back to back (sw_umma.cuh: single-thread issue forms)
+                ptx::tcgen05_fence_after_thread_sync();
+                if (elect_one()) {
+                    if (t > 0) {                                  // h_0 = 0: no recurrent term at step 0
+                        umma1_ss<256, 256, 4>(tmem, s.h[0], s.w + EW_HI, 0u, false);
+                        umma1_ss<256, 256, 4>(tmem, s.h[0], s.w + EW_LO, 0u, true);
+                        umma1_ss<256, 256, 4>(tmem, s.h[1], s.w + EW_HI, 0u, true);
+                    }
+                    umma1_ss<256, 256, 1>(tmem, s.xk, s.w + EW_XK, 0u, t > 0);
+                    umma1_commit(&s.bar);
+                }
+                __syncwarp();
+            }
+            if (cq == 0) {      // x_last = x_{T-1}; the next step's state is fetched while the MMAs run
+                if (t == T - 1) { if (valid && x_last) *reinterpret_cast<float4*>(x_last + (size_t)row * 4) = xt; }
+                else xt = load_x(t + 1);
             }
             mbar_wait(&s.bar, ph); ph ^= 1;
             ptx::tcgen05_fence_after_thread_sync();
@@ -115,12 +130,8 @@ lstm_seq_fwd_tcx_kernel(const __half* __restrict__ w16, const float* __restrict_
 #pragma unroll
                     for (int w2 = 0; w2 < 2; ++w2)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int n = cq * 128 + part * 32 + (u + w2) * 4 + q;
-                            const float4 w = wx4[n];
-                            g[w2][q] = __uint_as_float(a[(u + w2) * 4 + q]) + bL[n] + fmaf(w.x, x0, fmaf(w.y, x1, fmaf(w.z, x2, w.w * x3)));
-                        }
-                    lstm_cell_pair(g[0], g[1], c[part * 8 + u], c[part * 8 + u + 1], hv[u], hv[u + 1]);
+                        for (int q = 0; q < 4; ++q) g[w2][q] = __uint_as_float(a[(u + w2) * 4 + q]);
+                    lstm_cell_pair_prescaled(g[0], g[1], c[part * 8 + u], c[part * 8 + u + 1], hv[u], hv[u + 1]);
                 }
                 if (t == T - 1) {
                     if (valid) {
@@ -137,6 +148,7 @@ lstm_seq_fwd_tcx_kernel(const __half* __restrict__ w16, const float* __restrict_
                     *reinterpret_cast<uint4*>(s.h[1] + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
             }
+            if (cq == 0 && t + 1 < T) put_x(xt);                  // (this step's MMAs, the only readers of the x block, have completed)
             ptx::fence_proxy_async(ptx::space_shared);
             ptx::tcgen05_fence_before_thread_sync();
             __syncthreads();
@@ -154,9 +166,9 @@ lstm_seq_fwd_tcx_kernel(const __half* __restrict__ w16, const float* __restrict_
 
 }  // namespace sw
 
-extern "C" int sw_lstm_seq_fwd_tcx(const void* enc_w16, const float* enc_f32, const float* x, int in_dim, int n_rows,
+extern "C" int sw_lstm_seq_fwd_tcx(const void* enc_w16, const float* x, int in_dim, int n_rows,
                                    int n_steps, float* h_out, float* c_out, float* x_last, int sm_count, void* stream) {
-    if (!enc_w16 || !enc_f32 || !x || !h_out || !c_out) return SW_ERR_ARG;
+    if (!enc_w16 || !x || !h_out || !c_out) return SW_ERR_ARG;
     if (n_rows <= 0 || sm_count <= 0 || (in_dim != 2 && in_dim != 4)) return SW_ERR_ARG;
     if (n_steps < (in_dim == 2 ? 2 : 1)) return SW_ERR_UNSUPPORTED;
     const int tiles = (n_rows + sw::E_ROWS - 1) / sw::E_ROWS;
@@ -164,7 +176,7 @@ extern "C" int sw_lstm_seq_fwd_tcx(const void* enc_w16, const float* enc_f32, co
     SW_SET_MAX_SMEM(sw::lstm_seq_fwd_tcx_kernel, smem);
     const int grid = tiles < 2 * sm_count ? tiles : 2 * sm_count;
     sw::lstm_seq_fwd_tcx_kernel<<<grid, sw::E_THREADS, smem, (cudaStream_t)stream>>>(
-        (const __half*)enc_w16, enc_f32, x, in_dim, n_rows, n_steps, h_out, c_out, x_last, tiles);
+        (const __half*)enc_w16, x, in_dim, n_rows, n_steps, h_out, c_out, x_last, tiles);
     SW_CUDA_TRY(cudaGetLastError());
     return SW_OK;
 }

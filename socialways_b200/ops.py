@@ -124,7 +124,7 @@ def lstm_seq(lstm_pack, x, h_in=None, c_in=None, want_y=False, want_x_last=False
     return dict(h=h, c=c, y=y, x_last=xl, stash_gates=sg, stash_xh=sx)
 
 
-def lstm_seq_tcx(enc_w16, enc_f32, x):
+def lstm_seq_tcx(enc_w16, x):
     """sw_lstm_seq_fwd_tcx: tensor-core observation encoder (zero initial state, inference only)."""
     x = _f32(x)
     n, t, d = x.shape
@@ -132,7 +132,9 @@ def lstm_seq_tcx(enc_w16, enc_f32, x):
     if enc_w16.dtype != torch.float16 or not enc_w16.is_contiguous():
         raise ValueError("lstm_seq_tcx: fp16 contiguous weight pack expected (packing.pack_encoder_tcx)")
     h, c, xl = torch.empty(n, H, device=dev), torch.empty(n, H, device=dev), torch.empty(n, 4, device=dev)
-    code = _lib.lib().sw_lstm_seq_fwd_tcx(enc_w16.data_ptr(), _lib.ptr(_f32(enc_f32)), _lib.ptr(x), d, n, t, _lib.ptr(h),
+    if enc_w16.numel() != 2 * 64 * 256 + 256 * 16:
+        raise ValueError("lstm_seq_tcx: pack size does not match the kernel's (packing.pack_encoder_tcx)")
+    code = _lib.lib().sw_lstm_seq_fwd_tcx(enc_w16.data_ptr(), _lib.ptr(x), d, n, t, _lib.ptr(h),
                                           _lib.ptr(c), _lib.ptr(xl), sm_count(dev), _stream())
     _lib.check(code, "sw_lstm_seq_fwd_tcx")
     return dict(h=h, c=c, x_last=xl)

@@ -183,9 +183,15 @@ def pack_pool_tcx(fc2_w):
 
 
 def pack_encoder_tcx(lstm_pack):
-    """Operands of the tensor-core observation encoder (csrc/lstm_seq_fwd_tcx.cu): Whh [256 n'][64 k] as canonical
-    hi | lo fp16 blocks (x = hi + lo), and fp32 [1280] = wx4 [256 n'][4] | bL [256]."""
-    hi, lo = _split_f16(lstm_pack[4:68].t().contiguous())
-    w16 = torch.cat([_canonical_kmajor(hi), _canonical_kmajor(lo)]).contiguous()
-    f32 = torch.cat([lstm_pack[0:4].t().reshape(-1), lstm_pack[68]]).contiguous()
-    return w16, f32
+    """Operand of the tensor-core observation encoder (csrc/lstm_seq_fwd_tcx.cu), a 1-tuple (w16,): Whh [256 n'][64 k] as
+    canonical hi | lo fp16 blocks (x = hi + lo), then the x-feedback K block [2][256][8] with rows
+    [Wx_hi(4) | Wx_hi(4) | Wx_lo(4) | b_hi | b_lo | 0 0] -- the three products of the hi/lo split of  Wx . x4 + b  in ONE K block
+    against the A row [x_hi | x_lo | x_hi | 1 | 1 | 0 0].  Gate rows carry the ex2 prescale (-log2 e for i, f, o; -2 log2 e for g)."""
+    scale = _gate_prescale(lstm_pack.device, lstm_pack.dtype)
+    hi, lo = _split_f16((lstm_pack[4:68].t() * scale[:, None]).contiguous())
+    wx_hi, wx_lo = _split_f16((lstm_pack[0:4].t() * scale[:, None]).contiguous())
+    bl_hi, bl_lo = _split_f16((lstm_pack[68] * scale).contiguous())
+    zero = torch.zeros(256, 2, device=lstm_pack.device, dtype=torch.float16)
+    xkb = torch.cat([wx_hi, wx_hi, wx_lo, bl_hi[:, None], bl_lo[:, None], zero], dim=1)      # [256, 16]
+    w16 = torch.cat([_canonical_kmajor(hi), _canonical_kmajor(lo), _canonical_kmajor(xkb)]).contiguous()
+    return (w16,)
