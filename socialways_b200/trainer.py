@@ -401,7 +401,11 @@ class SocialWaysTrainer:
                         step = NativeStep(self, self._native_packs, hi - lo, self.generator.scene_index(sub, hi - lo, dev), g_hi - g_lo)
                         ent = self._native_steps[key] = dict(step=step, graph=None, seen=0)
                 self._native_plan.append((g_lo, g_hi, lo, hi, ent))
+        trace = [] if os.environ.get("SW_TRACE_TRAIN") else None    # per-iteration (host ms, GPU ms) of this rank, printed per epoch
         for g_lo, g_hi, lo, hi, ent in self._native_plan:
+            if trace is not None:
+                e0 = torch.cuda.Event(enable_timing=True); e0.record()
+                trace.append([time.perf_counter(), e0, None, hi - lo])
             self._native_iteration = getattr(self, "_native_iteration", 0) + 1
             global_bs = g_hi - g_lo
             # train.py:471-473: two numpy scalars, then the noise of the GLOBAL mini-batch from torch's CPU generator
@@ -441,6 +445,10 @@ class SocialWaysTrainer:
                 step.run()
             ent["seen"] += 1
             stats_acc += step.stats
+            if trace is not None:
+                e1 = torch.cuda.Event(enable_timing=True); e1.record()
+                trace[-1][2] = e1
+                trace[-1][0] = (time.perf_counter() - trace[-1][0]) * 1e3
             if log_losses:                                    # tests: one host read per iteration
                 v = step.stats.tolist()
                 self.loss_log.append(dict(d_loss=v[2], d_fake=v[3], d_real=v[4], d_info=v[5], g_fool=v[6], g_info=v[7]))
@@ -452,6 +460,10 @@ class SocialWaysTrainer:
         vals = stats_acc.tolist()
         for o in (self.predictor_optimizer, self.D_optimizer):
             o.check_status()
+        if trace is not None:
+            torch.cuda.synchronize()
+            print(f"[rank {self.rank}] train_native epoch: total {1e3 * (time.perf_counter() - tic):.2f} ms; per iteration (rows, host ms, gpu ms): "
+                  + ", ".join(f"({r}, {h:.2f}, {a.elapsed_time(b):.2f})" for h, a, b, r in trace if b is not None), flush=True)
         train_ADE, train_FDE = vals[0] / self.n_train_samples, vals[1] / self.n_train_samples
         self.last_epoch_mean_losses = dict(zip(("d_loss", "d_fake", "d_real", "d_info", "g_fool", "g_info"),
                                                [v / max(1, n_iter) for v in vals[2:]]))
