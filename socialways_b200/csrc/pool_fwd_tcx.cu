@@ -26,7 +26,10 @@
 
 namespace sw {
 
-constexpr int PT_THREADS = 128;      // thread p = pair p of the current tile = TMEM lane p
+constexpr int PT_GROUP = 128;        // one 128-pair tile per thread group: thread p of the group = pair p of its tile = TMEM lane p
+constexpr int PT_THREADS = 256;      // TWO groups per CTA work on two tiles at a time (own operand buffer, TMEM columns and barrier)
+                                     // against ONE staged span: the tile chain (features -> MMA -> epilogue) is latency-bound, and
+                                     // the second group doubles the warps per SM at the same shared-memory footprint
 #ifndef SW_PT_ROWS
 #define SW_PT_ROWS 64     // agent rows per work unit (A/B-tested with -DSW_PT_ROWS=32 / 128)
 #endif
@@ -53,8 +56,8 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
                     int n_agents, int span_cap, int pair_cap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __half* w2 = reinterpret_cast<__half*>(smem_raw);                       // [2][2048]           8 KB
-    __half* a1s = w2 + 2 * 2048;                                            // [2][4][128][8]     16 KB
-    float* p1 = reinterpret_cast<float*>(a1s + 2 * 4096);                   // [32][4]
+    __half* a1s_all = w2 + 2 * 2048;                                        // [group][2][4][128][8]   2 x 16 KB
+    float* p1 = reinterpret_cast<float*>(a1s_all + 2 * 2 * 4096);           // [32][4]
     float* b2 = p1 + 128;                                                   // [64]
     float* sx = b2 + 64;                                                    // [span][4]
     float* sh = sx + span_cap * 4;                                          // [span][64] (read lane <-> column only), if staged
@@ -62,9 +65,12 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
     float* sig = su_raw + span_cap * PT_LD + 4;                             // [pair_cap]
     int* off = reinterpret_cast<int*>(sig + pair_cap);                      // [PT_ROWS + 1] pair offsets of the unit's rows
     int* sstart = off + PT_ROWS + 1;                                        // [PT_ROWS] first agent of the row's scene
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sstart + PT_ROWS + 1);   // 8 B aligned (even int count)
-    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bar + 1);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(sstart + PT_ROWS + 1);  // [2], 8 B aligned (even int count)
+    uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(bars + 2);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = tid >> 7, gt = tid & (PT_GROUP - 1);                    // tile group, pair slot inside the group's tile
+    __half* a1s = a1s_all + grp * 2 * 4096;
+    unsigned long long* bar = bars + grp;
 
     const int row0 = units ? units[2 * blockIdx.x] : blockIdx.x * PT_ROWS;
     const int row1 = units ? row0 + units[2 * blockIdx.x + 1] : min(row0 + PT_ROWS, n_agents);
@@ -100,11 +106,12 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
         off[tid + 1] = scene_offsets[sc + 1] - scene_offsets[sc];         // scene size, prefix-summed below
     }
     if (warp == 0) {
-        ptx::tcgen05_alloc(ptx::cta_group_1, tmem_base_s, 64u);
+        ptx::tcgen05_alloc(ptx::cta_group_1, tmem_base_s, 128u);
         ptx::tcgen05_relinquish_alloc_permit(ptx::cta_group_1);
     }
     if (tid == 0) {
-        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(bar), 1);
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(bars), 1);
+        ptx::mbarrier_init(reinterpret_cast<uint64_t*>(bars + 1), 1);
         ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
     }
     __syncthreads();
@@ -116,13 +123,14 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
     ptx::tcgen05_fence_before_thread_sync();
     __syncthreads();
     ptx::tcgen05_fence_after_thread_sync();
-    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_base_s, 0);
-    const uint32_t tl = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_base_s, 0) + (uint32_t)(grp * 64);     // this group's 64 columns
+    const uint32_t tl = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int P = off[R];
     uint32_t ph = 0;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" :: "r"(1 + grp), "n"(PT_GROUP) : "memory"); };
 
-    for (int t0 = 0; t0 < P; t0 += PT_THREADS) {
-        const int q = t0 + tid;
+    for (int t0 = grp * PT_GROUP; t0 < P; t0 += PT_THREADS) {     // the groups take alternate tiles; a group's loop is its own
+        const int q = t0 + gt;
         const bool valid = q < P;
         int i = 0, j = 0;
         float a1[32];
@@ -158,13 +166,13 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) split2_pt(a1[c * 8 + 2 * e], a1[c * 8 + 2 * e + 1], hi[e], lo[e]);
-            *reinterpret_cast<uint4*>(a1s + ((size_t)c * PT_THREADS + tid) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(a1s + 4096 + ((size_t)c * PT_THREADS + tid) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(a1s + ((size_t)c * PT_GROUP + gt) * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(a1s + 4096 + ((size_t)c * PT_GROUP + gt) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
         ptx::fence_proxy_async(ptx::space_shared);
         ptx::tcgen05_fence_before_thread_sync();
-        __syncthreads();
-        if (warp == 0) {                                // a2 = a1 . W2^T : [128 pairs] x [64] x K = 32, three passes
+        group_sync();
+        if ((warp & 3) == 0) {                          // a2 = a1 . W2^T : [128 pairs] x [64] x K = 32, three passes
             ptx::tcgen05_fence_after_thread_sync();
             if (elect_one()) {                          // single-lane issue (sw_umma.cuh)
                 umma1_ss<64, 64, 2>(tmem, a1s, w2, 0u, false);
@@ -191,8 +199,9 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
             if (valid) sig[q] = (j == i) ? -1000.0f : sigma;              // train.py:170
         }
         ptx::tcgen05_fence_before_thread_sync();
-        __syncthreads();
+        group_sync();
     }
+    __syncthreads();                                    // both groups' scores are in shared memory
 
     // softmax over the scene (train.py:172) and S_i = sum_j a_ij h_j on the RAW h (:173); a group of G lanes per row
     {
@@ -238,7 +247,7 @@ pool_fwd_tcx_kernel(const float* __restrict__ pool_pack, const __half* __restric
     }
     ptx::tcgen05_fence_before_thread_sync();
     __syncthreads();
-    if (warp == 0) ptx::tcgen05_dealloc(ptx::cta_group_1, tmem, 64u);
+    if (warp == 0) ptx::tcgen05_dealloc(ptx::cta_group_1, __shfl_sync(0xffffffffu, *tmem_base_s, 0), 128u);
 }
 
 }  // namespace sw
@@ -261,7 +270,7 @@ extern "C" int sw_pool_fwd_tcx(const float* pool_pack, const void* pool_w16, con
     // multiple of 4: keeps every shared-memory array behind the (u | beta) rows (65 floats each) 16-byte aligned, the mbarrier 8
     const int span_cap = units ? (max_unit_span + 3) & ~3 : sw::PT_ROWS + 2 * (max_scene - 1);
     const int pair_cap = ((units ? max_unit_pairs : sw::PT_ROWS * max_scene) + 3) & ~3;
-    const size_t fixed = 2 * 2048 * 2 + 2 * 4096 * 2 + (size_t)(128 + 64 + 4) * 4 + (size_t)(2 * sw::PT_ROWS + 2) * 4 + 16;
+    const size_t fixed = 2 * 2048 * 2 + 2 * 2 * 4096 * 2 + (size_t)(128 + 64 + 4) * 4 + (size_t)(2 * sw::PT_ROWS + 2) * 4 + 24;
     const size_t no_h = fixed + (size_t)(span_cap * (4 + sw::PT_LD) + pair_cap) * 4;
     const size_t with_h = no_h + (size_t)span_cap * SW_H * 4;
     const char* knob = getenv("SW_POOL_STAGE_H");                   // A/B knob (profiles/): default = measured best
