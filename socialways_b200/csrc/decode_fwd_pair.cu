@@ -259,7 +259,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
         // =========================== the 16 epilogue warps ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);           // this thread's lane, slot 0, column 0
-        uint32_t ph_l[2] = {0, 0}, ph_g[2] = {0, 0}, ph_z[2] = {0, 0};
+        uint32_t ph = 0;                    // barrier parities, one register: bit sl = full[sl][0], bit 2 + sl = gates, bit 4 + sl = noise block
         // every warp: "my operand writes are done" -> one arrival on the leader CTA's barrier
         // (address of ready[0] in the LEADER CTA's shared memory, computed once: ready[1], ready_x[0], ready_x[1] follow at +8 ...)
         uint32_t ready0_leader;
@@ -291,6 +291,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             int abase[2], agent[2];
             float4 sreg[2][4], hreg[2][2][2];
             float2 xl = make_float2(0.f, 0.f);
+            float* out_row = out;           // where this thread emits (the rows of the slot it finishes; one slot at most)
             // ---------------- tile prologue, both slots: every global load coalesced and issued up front ----------------
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
@@ -318,7 +319,10 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                         hreg[sl][i][1] = __ldg(src + 1);
                     }
                 }
-                if (fin[sl] && valid[sl]) xl = __ldg(reinterpret_cast<const float2*>(x_last + (size_t)agent[sl] * 4));
+                if (fin[sl] && valid[sl]) {
+                    xl = __ldg(reinterpret_cast<const float2*>(x_last + (size_t)agent[sl] * 4));
+                    out_row = out + (size_t)(row0[sl] + r) * n_next * 4;
+                }
             }
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
@@ -330,7 +334,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                     const int g = tid + i * Q_EPI, row = g >> 4, piece = g & 15;
                     sS[row * 16 + (piece ^ (row & 7))] = sreg[sl][i];
                 }
-                if (has_tile[sl]) { mbar_wait(&s.bar_z[sl], ph_z[sl]); ph_z[sl] ^= 1; }
+                if (has_tile[sl]) { mbar_wait(&s.bar_z[sl], (ph >> (4 + sl)) & 1u); ph ^= 16u << sl; }
                 epi_sync();
                 // [S ; z] (K = 96 = 24 pieces): this thread owns pieces 6 cq .. 6 cq + 5 of its row -> hi|lo TMEM A operand
                 uint32_t hi[12], lo[12];
@@ -385,7 +389,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 sc[sl] = scratch + ((size_t)blockIdx.x * 2 + sl) * P_SCRATCH_F4_PER_SLOT + (size_t)kb0[sl] * 4 * P_ROWS + r;
                 if (sl >= n_act) continue;
                 const uint32_t ta = tl + (uint32_t)(sl * 256) + PC_R1 + kb0[sl] * 16;
-                wait_full3(&s.full[sl][0], ph_l[sl]); ph_l[sl] ^= 1;      // c1 + b1 -> scratch (the K blocks this thread re-reads)
+                wait_full3(&s.full[sl][0], (ph >> sl) & 1u); ph ^= 1u << sl;      // c1 + b1 -> scratch (the K blocks this thread re-reads)
                 if (three[sl]) c1_to_scratch<Q_NB>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
                 else           c1_to_scratch<Q_NS>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
                 arrive(&s.ready[sl]);                                     // -> layer 1 of step 0
@@ -401,9 +405,9 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             auto phase_l1 = [&](auto slc) {
                 constexpr int sl = decltype(slc)::value;
                 const uint32_t ta = tl + (uint32_t)(sl * 256) + PC_R1 + kb0[sl] * 16;
-                if (three[sl]) l1_epilogue<Q_NB>(ta, sc[sl], &s.full[sl][0], ph_l[sl], cpre);
-                else           l1_epilogue<Q_NS>(ta, sc[sl], &s.full[sl][0], ph_l[sl], cpre);
-                ph_l[sl] ^= 1;
+                if (three[sl]) l1_epilogue<Q_NB>(ta, sc[sl], &s.full[sl][0], (ph >> sl) & 1u, cpre);
+                else           l1_epilogue<Q_NS>(ta, sc[sl], &s.full[sl][0], (ph >> sl) & 1u, cpre);
+                ph ^= 1u << sl;
                 arrive(&s.ready[sl]);                                     // -> layer 2 (+ h part of gates half 0)
             };
             // ---------------- layer-2 epilogue + folded layers 3+4 (80 -> 2), row finish ----------------
@@ -416,7 +420,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
 #pragma unroll
                 for (int j = 0; j < 5; ++j) bb[j] = b2[j];
 #endif
-                wait_full3(&s.full[sl][0], ph_l[sl]); ph_l[sl] ^= 1;
+                wait_full3(&s.full[sl][0], (ph >> sl) & 1u); ph ^= 1u << sl;
                 float v0 = 0.0f, v1 = 0.0f;
                 {
                     uint32_t acc[20];
@@ -462,7 +466,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                         arrive(&s.ready_x[sl]);                           // -> x blocks of the gates, h part of half 1
                     }
                     if (valid[sl])
-                        *reinterpret_cast<float4*>(out + ((size_t)(row0[sl] + r) * n_next + t) * 4) = make_float4(p0, p1, v0, v1);
+                        *reinterpret_cast<float4*>(out_row + (size_t)t * 4) = make_float4(p0, p1, v0, v1);
                 }
             };
             // ---------------- LSTM cell: 8 units of gates half 0 (units 8 cq ..), then 8 units of half 1 (units 32 + 8 cq ..) ----------------
@@ -471,7 +475,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 const uint32_t tls = tl + (uint32_t)(sl * 256);
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
-                    if (half == 0) wait_full3(&s.full[sl][1], ph_g[sl]);
+                    if (half == 0) wait_full3(&s.full[sl][1], (ph >> (2 + sl)) & 1u);
                     uint32_t a[32];
                     tmem_ld<32>(tls + half * 128 + cq * 32, a);
                     ptx::tcgen05_wait_ld();
@@ -493,12 +497,12 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
 #pragma unroll
                     for (int e = 0; e < 4; ++e) psplit2(hv[2 * e], hv[2 * e + 1], hh[e], ll[e]);
                     // h is an operand of the half-1 gate MMAs: nothing may overwrite it before they have completed
-                    if (half == 0) wait_full3(&s.full[sl][2], ph_g[sl]);
+                    if (half == 0) wait_full3(&s.full[sl][2], (ph >> (2 + sl)) & 1u);
                     const size_t off = ((size_t)(half * 4 + cq) * P_ROWS + r) * 8;
                     *reinterpret_cast<uint4*>(s.h[sl][0] + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
                     *reinterpret_cast<uint4*>(s.h[sl][1] + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
                 }
-                ph_g[sl] ^= 1;
+                ph ^= 4u << sl;
                 ptx::fence_proxy_async(ptx::space_shared);
                 arrive(&s.ready[sl]);                                     // -> next step's layer 1
             };

@@ -1,5 +1,7 @@
 """Thin tensor-level wrappers over the C-ABI (include/socialways_b200.h): allocate outputs with torch,
 pass raw device pointers + the current CUDA stream.  No arithmetic happens here."""
+import os
+
 import numpy as np
 import torch
 
@@ -65,6 +67,7 @@ class SceneIndex:
         32 rows (16 beyond 256 agents) of that scene alone, so a unit's span is the unit itself or one scene."""
         if self._pool_units is None:
             big_rows = 32 if self.max_scene <= 256 else 16
+            cap = int(os.environ.get("SW_POOL_UNIT_ROWS", "64"))     # A/B knob; must not exceed the kernel's SW_PT_ROWS
             units, span, pairs = [], 1, 1
             start, rows, npairs = 0, 0, 0
             offs = np.concatenate([[0], np.cumsum(self.sizes)])
@@ -78,7 +81,7 @@ class SceneIndex:
                         units.append((int(offs[s_i]) + r0, r)); span, pairs = max(span, a), max(pairs, r * a)
                     start = int(offs[s_i + 1])
                     continue
-                if rows + a > 64:
+                if rows + a > cap:
                     units.append((start, rows)); span, pairs = max(span, rows), max(pairs, npairs)
                     start, rows, npairs = int(offs[s_i]), 0, 0
                 if rows == 0:
