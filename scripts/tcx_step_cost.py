@@ -1,4 +1,5 @@
-"""Split the tcx decode kernel time into per-tile overhead (prologue + hoist) and per-step cost: T(n_next) = P + n_next * S."""
+"""Split the decode kernel time into per-tile overhead (prologue + hoist) and per-step cost: T(n_next) = P + n_next * S.
+    python scripts/tcx_step_cost.py [tcx|pair]"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -17,15 +18,18 @@ c = torch.randn(n, 64, device="cuda") * 0.3
 pooled = torch.randn(n, 64, device="cuda") * 0.3
 noise = torch.rand(k, n, 32, device="cuda")
 xl = torch.rand(n, 4, device="cuda")
+which = sys.argv[1] if len(sys.argv) > 1 else "pair"
+run = (lambda T, out: ops.decode_pair(*pk["pair"], h, c, pooled, noise, xl, T, out=out)) if which == "pair" else \
+      (lambda T, out: ops.decode_tcx(*pk["tcx"], h, c, pooled, noise, xl, T, out=out))
 res = {}
 for T in (1, 2, 6, 12, 24):
     out = torch.empty(k, n, T, 4, device="cuda")
     for _ in range(2):
-        ops.decode_tcx(*pk["tcx"], h, c, pooled, noise, xl, T, out=out)
+        run(T, out)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        ops.decode_tcx(*pk["tcx"], h, c, pooled, noise, xl, T, out=out)
+        run(T, out)
     e1.record()
     torch.cuda.synchronize()
     res[T] = e0.elapsed_time(e1) / 5

@@ -289,9 +289,11 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             bool has_tile[2], valid[2];
             long long row0[2];
             int abase[2], agent[2];
-            float4 sreg[2][4], hreg[2][2][2];
             float2 xl = make_float2(0.f, 0.f);
             float* out_row = out;           // where this thread emits (the rows of the slot it finishes; one slot at most)
+            // cell state of this thread's units: c[sl][0..7] = units 8 cq .. (gates half 0), c[sl][8..15] = units 32 + 8 cq .. (half 1);
+            // loaded FIRST: the registers are dead until the first cell update anyway, and the loads share the latency of the others
+            float c[2][16];
             // ---------------- tile prologue, both slots: every global load coalesced and issued up front ----------------
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
@@ -301,22 +303,28 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 valid[sl] = has_tile[sl] && row0[sl] + r < n_rows;
                 abase[sl] = has_tile[sl] ? (int)(row0[sl] % n_agents) : 0;
                 agent[sl] = valid[sl] ? (abase[sl] + r) % n_agents : 0;
-                if (sl >= n_act) continue;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {                             // S tile [128][16 pieces]: piece g = tid + 512 i
-                    const int g = tid + i * Q_EPI, row = g >> 4, piece = g & 15;
-                    sreg[sl][i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (pooled && has_tile[sl] && row0[sl] + row < n_rows)
-                        sreg[sl][i] = __ldg(reinterpret_cast<const float4*>(pooled + (size_t)((abase[sl] + row) % n_agents) * SW_H) + piece);
+                for (int q = 0; q < 4; ++q) {
+                    const float4 v = valid[sl] ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent[sl] * SW_H + (q >> 1) * 32 + cq * 8) + (q & 1))
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+                    c[sl][4 * q] = v.x; c[sl][4 * q + 1] = v.y; c[sl][4 * q + 2] = v.z; c[sl][4 * q + 3] = v.w;
                 }
-                const int hrow = warp * 8 + (lane & 7);                   // h0 items: (row, chunk = (lane >> 3) + 4 i)
+                if (sl >= n_act) continue;
+                {   // S tile [128 rows][16 pieces] -> the slot's (still unused) h operand region, piece' = piece ^ (row & 7), by cp.async:
+                    // global -> shared without a register in between.  (Through registers the 8 loaded float4 of both slots did not
+                    // fit beside the cell state: ptxas spilled each one right behind its load, and every spill store waited for
+                    // its load -- the loads of the prologue ran one after the other, ~17 K clk per tile pair.)
+                    float4* sS = reinterpret_cast<float4*>(s.h[sl][0]);
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    hreg[sl][i][0] = hreg[sl][i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (has_tile[sl] && row0[sl] + hrow < n_rows) {
-                        const float4* src = reinterpret_cast<const float4*>(h0 + (size_t)((abase[sl] + hrow) % n_agents) * SW_H) + ((lane >> 3) + 4 * i) * 2;
-                        hreg[sl][i][0] = __ldg(src);
-                        hreg[sl][i][1] = __ldg(src + 1);
+                    for (int i = 0; i < 4; ++i) {                         // piece g = tid + 512 i
+                        const int g = tid + i * Q_EPI, row = g >> 4, piece = g & 15;
+                        float4* dst = sS + row * 16 + (piece ^ (row & 7));
+                        if (pooled && has_tile[sl] && row0[sl] + row < n_rows) {
+                            const float4* src = reinterpret_cast<const float4*>(pooled + (size_t)((abase[sl] + row) % n_agents) * SW_H) + piece;
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+                        } else {
+                            *dst = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
                     }
                 }
                 if (fin[sl] && valid[sl]) {
@@ -329,11 +337,20 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 if (sl >= n_act) continue;
                 float4* sS = reinterpret_cast<float4*>(s.h[sl][0]);       // [128 rows][16 pieces], piece' = piece ^ (row & 7); 32 KB = h hi|lo
                 const float4* sZ = reinterpret_cast<const float4*>(s.zst[sl]);   // [128 rows][8 pieces], TMA swizzle: piece' = piece ^ (row & 7)
+                // h0 items of this slot: (row, 8-column chunk = (lane >> 3) + 4 i), 8 rows x 128 B per instruction; requested here,
+                // consumed after the staging below (one slot's worth of registers at a time)
+                float4 hreg[2][2];
+                const int hrow = warp * 8 + (lane & 7);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int g = tid + i * Q_EPI, row = g >> 4, piece = g & 15;
-                    sS[row * 16 + (piece ^ (row & 7))] = sreg[sl][i];
+                for (int i = 0; i < 2; ++i) {
+                    hreg[i][0] = hreg[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_tile[sl] && row0[sl] + hrow < n_rows) {
+                        const float4* src = reinterpret_cast<const float4*>(h0 + (size_t)((abase[sl] + hrow) % n_agents) * SW_H) + ((lane >> 3) + 4 * i) * 2;
+                        hreg[i][0] = __ldg(src);
+                        hreg[i][1] = __ldg(src + 1);
+                    }
                 }
+                asm volatile("cp.async.wait_all;" ::: "memory");          // this thread's pieces of the S tile(s) have landed
                 if (has_tile[sl]) { mbar_wait(&s.bar_z[sl], (ph >> (4 + sl)) & 1u); ph ^= 16u << sl; }
                 epi_sync();
                 // [S ; z] (K = 96 = 24 pieces): this thread owns pieces 6 cq .. 6 cq + 5 of its row -> hi|lo TMEM A operand
@@ -356,14 +373,13 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                     const int un = ub + sl + 2 * n_pairs, tn = 2 * un + (int)cta;
                     if (tid == 0 && un < n_units && tn < n_tiles) prefetch_noise(sl, tn);
                 }
-                const int hrow = warp * 8 + (lane & 7);
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {                             // h0 -> hi|lo operand chunks [chunk][row][8]
                     uint32_t hh[4], ll[4];
-                    psplit2(hreg[sl][i][0].x, hreg[sl][i][0].y, hh[0], ll[0]);
-                    psplit2(hreg[sl][i][0].z, hreg[sl][i][0].w, hh[1], ll[1]);
-                    psplit2(hreg[sl][i][1].x, hreg[sl][i][1].y, hh[2], ll[2]);
-                    psplit2(hreg[sl][i][1].z, hreg[sl][i][1].w, hh[3], ll[3]);
+                    psplit2(hreg[i][0].x, hreg[i][0].y, hh[0], ll[0]);
+                    psplit2(hreg[i][0].z, hreg[i][0].w, hh[1], ll[1]);
+                    psplit2(hreg[i][1].x, hreg[i][1].y, hh[2], ll[2]);
+                    psplit2(hreg[i][1].z, hreg[i][1].w, hh[3], ll[3]);
                     const size_t off = ((size_t)((lane >> 3) + 4 * i) * P_ROWS + hrow) * 8;
                     *reinterpret_cast<uint4*>(s.h[sl][0] + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
                     *reinterpret_cast<uint4*>(s.h[sl][1] + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
@@ -371,16 +387,21 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 ptx::fence_proxy_async(ptx::space_shared);
                 arrive(&s.ready[sl]);                                     // -> hoist MMAs of the slot
             }
-            // cell state of this thread's units: c[sl][0..7] = units 8 cq .. (gates half 0), c[sl][8..15] = units 32 + 8 cq .. (half 1)
-            float c[2][16];
+            {   // the NEXT tiles' rows of pooled / h0 / c0 -> L2, twelve steps ahead of their use (no registers held: prefetch only)
 #pragma unroll
-            for (int sl = 0; sl < 2; ++sl)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 v = valid[sl] ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent[sl] * SW_H + (q >> 1) * 32 + cq * 8) + (q & 1))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-                    c[sl][4 * q] = v.x; c[sl][4 * q + 1] = v.y; c[sl][4 * q + 2] = v.z; c[sl][4 * q + 3] = v.w;
+                for (int sl = 0; sl < 2; ++sl) {
+                    const int un = ub + sl + 2 * n_pairs, tn = 2 * un + (int)cta;
+                    if (un < n_units && tn < n_tiles) {
+                        const long long rown = (long long)tn * P_ROWS + (tid >> 2);          // thread -> (row = tid / 4, 64-byte quarter of the row's 256 B)
+                        if (rown < n_rows) {
+                            const size_t off = (size_t)(rown % n_agents) * SW_H + (tid & 3) * 16;
+                            if (pooled) asm volatile("prefetch.global.L2 [%0];" :: "l"(pooled + off));
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(h0 + off));
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(c0 + off));
+                        }
+                    }
                 }
+            }
             float p0 = xl.x, p1 = xl.y;                                   // state of the rows this thread finishes (one slot at most)
             bool out_of_range = false;
             float4* sc[2];
