@@ -258,6 +258,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
     } else {
         // =========================== the 16 epilogue warps ===========================
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+        const int etid = r + (cq << 7), ewarp = etid >> 5;                // = threadIdx.x / warp index of these warps, from the pinned registers
         const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);           // this thread's lane, slot 0, column 0
         uint32_t ph = 0;                    // barrier parities, one register: bit sl = full[sl][0], bit 2 + sl = gates, bit 4 + sl = noise block
         // every warp: "my operand writes are done" -> one arrival on the leader CTA's barrier
@@ -316,8 +317,8 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                     // its load -- the loads of the prologue ran one after the other, ~17 K clk per tile pair.)
                     float4* sS = reinterpret_cast<float4*>(s.h[sl][0]);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {                         // piece g = tid + 512 i
-                        const int g = tid + i * Q_EPI, row = g >> 4, piece = g & 15;
+                    for (int i = 0; i < 4; ++i) {                         // piece g = etid + 512 i
+                        const int g = etid + i * Q_EPI, row = g >> 4, piece = g & 15;
                         float4* dst = sS + row * 16 + (piece ^ (row & 7));
                         if (pooled && has_tile[sl] && row0[sl] + row < n_rows) {
                             const float4* src = reinterpret_cast<const float4*>(pooled + (size_t)((abase[sl] + row) % n_agents) * SW_H) + piece;
@@ -332,24 +333,26 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                     out_row = out + (size_t)(row0[sl] + r) * n_next * 4;
                 }
             }
+            // h0 items: (row, 8-column chunk = (lane >> 3) + 4 i), 8 rows x 128 B per instruction; requested here, consumed at the end
+            // of each slot's staging below (the S tiles no longer pass through registers, so both slots' items fit)
+            float4 hreg[2][2][2];
+            const int hrow = ewarp * 8 + (lane & 7);
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    hreg[sl][i][0] = hreg[sl][i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (has_tile[sl] && row0[sl] + hrow < n_rows) {
+                        const float4* src = reinterpret_cast<const float4*>(h0 + (size_t)((abase[sl] + hrow) % n_agents) * SW_H) + ((lane >> 3) + 4 * i) * 2;
+                        hreg[sl][i][0] = __ldg(src);
+                        hreg[sl][i][1] = __ldg(src + 1);
+                    }
+                }
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
                 if (sl >= n_act) continue;
                 float4* sS = reinterpret_cast<float4*>(s.h[sl][0]);       // [128 rows][16 pieces], piece' = piece ^ (row & 7); 32 KB = h hi|lo
                 const float4* sZ = reinterpret_cast<const float4*>(s.zst[sl]);   // [128 rows][8 pieces], TMA swizzle: piece' = piece ^ (row & 7)
-                // h0 items of this slot: (row, 8-column chunk = (lane >> 3) + 4 i), 8 rows x 128 B per instruction; requested here,
-                // consumed after the staging below (one slot's worth of registers at a time)
-                float4 hreg[2][2];
-                const int hrow = warp * 8 + (lane & 7);
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    hreg[i][0] = hreg[i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (has_tile[sl] && row0[sl] + hrow < n_rows) {
-                        const float4* src = reinterpret_cast<const float4*>(h0 + (size_t)((abase[sl] + hrow) % n_agents) * SW_H) + ((lane >> 3) + 4 * i) * 2;
-                        hreg[i][0] = __ldg(src);
-                        hreg[i][1] = __ldg(src + 1);
-                    }
-                }
                 asm volatile("cp.async.wait_all;" ::: "memory");          // this thread's pieces of the S tile(s) have landed
                 if (has_tile[sl]) { mbar_wait(&s.bar_z[sl], (ph >> (4 + sl)) & 1u); ph ^= 16u << sl; }
                 epi_sync();
@@ -371,15 +374,15 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 epi_sync();                                               // staging consumed: h region and noise buffer are free
                 {   // next tile's noise block: 12 steps ahead of its use
                     const int un = ub + sl + 2 * n_pairs, tn = 2 * un + (int)cta;
-                    if (tid == 0 && un < n_units && tn < n_tiles) prefetch_noise(sl, tn);
+                    if (etid == 0 && un < n_units && tn < n_tiles) prefetch_noise(sl, tn);
                 }
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {                             // h0 -> hi|lo operand chunks [chunk][row][8]
                     uint32_t hh[4], ll[4];
-                    psplit2(hreg[i][0].x, hreg[i][0].y, hh[0], ll[0]);
-                    psplit2(hreg[i][0].z, hreg[i][0].w, hh[1], ll[1]);
-                    psplit2(hreg[i][1].x, hreg[i][1].y, hh[2], ll[2]);
-                    psplit2(hreg[i][1].z, hreg[i][1].w, hh[3], ll[3]);
+                    psplit2(hreg[sl][i][0].x, hreg[sl][i][0].y, hh[0], ll[0]);
+                    psplit2(hreg[sl][i][0].z, hreg[sl][i][0].w, hh[1], ll[1]);
+                    psplit2(hreg[sl][i][1].x, hreg[sl][i][1].y, hh[2], ll[2]);
+                    psplit2(hreg[sl][i][1].z, hreg[sl][i][1].w, hh[3], ll[3]);
                     const size_t off = ((size_t)((lane >> 3) + 4 * i) * P_ROWS + hrow) * 8;
                     *reinterpret_cast<uint4*>(s.h[sl][0] + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
                     *reinterpret_cast<uint4*>(s.h[sl][1] + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
@@ -392,9 +395,9 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 for (int sl = 0; sl < 2; ++sl) {
                     const int un = ub + sl + 2 * n_pairs, tn = 2 * un + (int)cta;
                     if (un < n_units && tn < n_tiles) {
-                        const long long rown = (long long)tn * P_ROWS + (tid >> 2);          // thread -> (row = tid / 4, 64-byte quarter of the row's 256 B)
+                        const long long rown = (long long)tn * P_ROWS + (etid >> 2);          // thread -> (row = etid / 4, 64-byte quarter of the row's 256 B)
                         if (rown < n_rows) {
-                            const size_t off = (size_t)(rown % n_agents) * SW_H + (tid & 3) * 16;
+                            const size_t off = (size_t)(rown % n_agents) * SW_H + (etid & 3) * 16;
                             if (pooled) asm volatile("prefetch.global.L2 [%0];" :: "l"(pooled + off));
                             asm volatile("prefetch.global.L2 [%0];" :: "l"(h0 + off));
                             asm volatile("prefetch.global.L2 [%0];" :: "l"(c0 + off));
