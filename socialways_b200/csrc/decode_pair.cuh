@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#define SW_RCP_NEWTON 1      // one of the three reciprocals per unit pair on the FMA pipe (sw_umma.cuh: rcp_newton)
 #include "sw_common.cuh"
 #include "sw_umma.cuh"
 

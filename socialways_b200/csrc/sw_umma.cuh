@@ -336,6 +336,20 @@ __device__ __forceinline__ void lstm_cell_pair(const float (&ga)[4], const float
 
 // Same cell with PRE-SCALED pre-activations: e = (-log2 e . x_i, -log2 e . x_f, -2 log2 e . x_g, -log2 e . x_o), i.e. the ex2
 // arguments themselves (the scale lives in the packed gate weights, packing.pack_decoder_tcx) -- 4 multiplies per unit less.
+// Reciprocal on the FMA pipe: magic-constant seed (12 % off) + three Newton steps (relative error 6e-8).  The cell update of
+// the pair decode kernel sits at the balance point between the MUFU pipe (16 lanes/clk/SM) and instruction issue: with
+// SW_RCP_NEWTON = n (defined by the including kernel file) the first n of the 3 reciprocals per unit pair leave the MUFU pipe
+// (7 FMA-pipe instructions each).  Measured on B200, pair decode alone: n = 0: 7.98 ms, 1: 7.88, 2: 7.93, 3: 8.02; the
+// one-tile kernel and the encoder are issue-bound and lose 3 % with n = 1, so only decode_fwd_pair.cu sets it.
+__device__ __forceinline__ float rcp_newton(float x) {
+    float y = __int_as_float(0x7EF311C7 - __float_as_int(x));
+#pragma unroll
+    for (int it = 0; it < 3; ++it) y = fmaf(y, fmaf(-x, y, 1.0f), y);
+    return y;
+}
+#ifndef SW_RCP_NEWTON
+#define SW_RCP_NEWTON 0
+#endif
 __device__ __forceinline__ void lstm_cell_pair_prescaled(const float (&ea)[4], const float (&eb)[4], float& ca, float& cb,
                                                          float& ha, float& hb) {
     float cn[2];
@@ -347,14 +361,14 @@ __device__ __forceinline__ void lstm_cell_pair_prescaled(const float (&ea)[4], c
         const float ai = 1.0f + ex2_approx(fminf(e[0], 30.0f)), af = 1.0f + ex2_approx(fminf(e[1], 30.0f));
         const float ag = 1.0f + ex2_approx(fminf(e[2], 30.0f)), ao = 1.0f + ex2_approx(fminf(e[3], 30.0f));
         const float p_ig = ai * ag, p_fo = af * ao;
-        const float r = rcp_approx(p_ig * p_fo);
+        const float r = (q < SW_RCP_NEWTON) ? rcp_newton(p_ig * p_fo) : rcp_approx(p_ig * p_fo);
         const float r_ig = r * p_fo, r_fo = r * p_ig;            // 1/(ai.ag), 1/(af.ao)
         const float sig_i = ag * r_ig, tanh_g = fmaf(2.0f * ai, r_ig, -1.0f);
         cn[q] = fmaf(ao * r_fo, cs[q], sig_i * tanh_g);          // sigma(f) = ao / (af.ao)
         if (q == 0) ha = af * r_fo; else hb = af * r_fo;         // sigma(o), multiplied by tanh(c) below
     }
     const float a0 = 1.0f + expneg_clamped(2.0f * cn[0]), a1 = 1.0f + expneg_clamped(2.0f * cn[1]);
-    const float r = rcp_approx(a0 * a1);
+    const float r = (SW_RCP_NEWTON > 2) ? rcp_newton(a0 * a1) : rcp_approx(a0 * a1);
     ha *= fmaf(2.0f * a1, r, -1.0f);
     hb *= fmaf(2.0f * a0, r, -1.0f);
     ca = cn[0];
