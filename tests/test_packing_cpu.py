@@ -120,3 +120,92 @@ def test_pool_tcx_pack_reconstructs_layer_two():
     a_hi, a_lo = split(a1)
     got = a_hi @ hi.t() + a_hi @ lo.t() + a_lo @ hi.t()
     assert (got - a1 @ w.t()).abs().max() < 5e-6
+
+
+def test_pair_pack_halves_reassemble_the_one_tile_operands():
+    """pack_decoder_pair cuts every B matrix [N][K] into the two N halves the two CTAs of a pair supply; the halves of both ranks,
+    put back together, must be the matrices of pack_decoder_tcx (same split, same prescale), and the sizes must match the
+    kernel's (sw_decode_pair_pack_sizes)."""
+    from socialways_b200 import _lib
+    _, enc, dec = make_packs(3)
+    w16, f32 = packing.pack_decoder_pair(enc, dec)
+    a, b = ctypes.c_int(), ctypes.c_int()
+    assert _lib.lib().sw_decode_pair_pack_sizes(ctypes.byref(a), ctypes.byref(b)) == 0
+    assert (w16.numel(), f32.numel()) == (a.value, b.value) and w16.dtype == torch.float16
+    per_rank = w16.numel() // 2
+    one = packing.pack_decoder_tcx(enc, dec)
+    t16, tsz, tf32 = one[0].float(), one[1].float(), one[2]
+    assert torch.equal(f32, tf32)
+    ranks = [w16[i * per_rank:(i + 1) * per_rank].float() for i in range(2)]
+
+    def both(off, rows, k):           # [2 ranks][K/8][rows][8] at `off` -> [2 * rows, K]
+        return torch.cat([uncanon(r[off:off + rows * k], rows, k) for r in ranks])
+
+    # W1[h rows] hi | lo: [8][80][8] per rank
+    assert torch.equal(both(0, 80, 64), uncanon(t16[0:10240], 160, 64))
+    assert torch.equal(both(5120, 80, 64), uncanon(t16[10240:20480], 160, 64))
+    # W2 hi | lo (not stacked in the pair pack): [20][40][8] per rank vs the stacked [20][hi 80 | lo 80][8]
+    cat = uncanon(t16[20480:46080], 160, 160)
+    assert torch.equal(both(10240, 40, 160), cat[:80]) and torch.equal(both(10240 + 6400, 40, 160), cat[80:])
+    # Whh per gate half g (rows [128 g, 128 g + 128), 64 per rank), hi | lo; x-feedback K block per gate half
+    whh_hi, whh_lo = uncanon(t16[46080:62464], 256, 64), uncanon(t16[62464:78848], 256, 64)
+    xk = uncanon(t16[78848:82944], 256, 16)
+    base = 10240 + 2 * 6400
+    for g in range(2):
+        o = base + g * 8192
+        assert torch.equal(both(o, 64, 64), whh_hi[128 * g:128 * g + 128])
+        assert torch.equal(both(o + 4096, 64, 64), whh_lo[128 * g:128 * g + 128])
+        assert torch.equal(both(base + 16384 + g * 1024, 64, 16), xk[128 * g:128 * g + 128])
+    # hoisted rows of W1 (S, z): hi | lo [12][80][8] per rank vs three K = 32 chunks of [hi 160 | lo 160] rows
+    wsz_hi = torch.cat([uncanon(tsz[ch * 10240:ch * 10240 + 5120], 160, 32) for ch in range(3)], 1)
+    wsz_lo = torch.cat([uncanon(tsz[ch * 10240 + 5120:(ch + 1) * 10240], 160, 32) for ch in range(3)], 1)
+    o = base + 16384 + 2048
+    assert torch.equal(both(o, 80, 96), wsz_hi) and torch.equal(both(o + 7680, 80, 96), wsz_lo)
+
+
+def test_emulated_tensor_core_encoder_matches_the_fp32_lstm():
+    """The observation encoder the way lstm_seq_fwd_tcx_kernel computes it from pack_encoder_tcx -- zero state, per step ONE K
+    block [x_hi | x_lo | x_hi | 1 | 1 | 0 0] for Wx . x4 + b, three products for h . Whh^T from step 1 on, pre-scaled gates, the
+    shared-reciprocal cell -- over 8 steps, vs the oracle's fp32 embed + LSTM cell on the reference parameters."""
+    from oracle import socialways_oracle as so
+    P, enc, _ = make_packs(4)
+    (w16,) = packing.pack_encoder_tcx(enc)
+    assert w16.numel() == 2 * 64 * 256 + 256 * 16 and w16.dtype == torch.float16
+    w16 = w16.float()
+    whh_hi, whh_lo, xk = uncanon(w16[0:16384], 256, 64), uncanon(w16[16384:32768], 256, 64), uncanon(w16[32768:], 256, 16)
+    g = torch.Generator().manual_seed(1)
+    n, T = 48, 8
+    pos = torch.cumsum(torch.randn(n, T, 2, generator=g) * 0.05, 1) + torch.rand(n, 1, 2, generator=g)
+    vel = torch.cat([pos[:, 1:2] - pos[:, 0:1], pos[:, 1:] - pos[:, :-1]], 1)            # v_0 := v_1 (train.py:131-133)
+    x4 = torch.cat([pos, vel], 2)
+    h = c = torch.zeros(n, 64)
+    h_ref, c_ref = torch.zeros(n, 64), torch.zeros(n, 64)
+    for t in range(T):
+        x_hi, x_lo = split(x4[:, t])
+        a_blk = torch.cat([x_hi, x_lo, x_hi, torch.ones(n, 2), torch.zeros(n, 2)], 1)
+        e = a_blk @ xk.t()
+        if t > 0:
+            h_hi, h_lo = split(h)
+            e = e + h_hi @ whh_hi.t() + h_hi @ whh_lo.t() + h_lo @ whh_hi.t()
+        e = e.view(n, 64, 4)
+        ai, af, ag, ao = (1 + torch.exp2(torch.clamp(e[..., q], max=30.0)) for q in range(4))
+        r = 1.0 / (ai * ag * af * ao)
+        r_ig, r_fo = r * (af * ao), r * (ai * ag)
+        c = (ao * r_fo) * c + (ag * r_ig) * (2 * ai * r_ig - 1)
+        h = (af * r_fo) * (2 / (1 + torch.exp2(torch.clamp(-2 * LOG2E * c, max=60.0))) - 1)
+        emb = x4[:, t] @ P["encoder.embed.weight"].t() + P["encoder.embed.bias"]
+        h_ref, c_ref = so.lstm_cell(emb, h_ref, c_ref, P["encoder.lstm.weight_ih_l0"], P["encoder.lstm.weight_hh_l0"],
+                                    P["encoder.lstm.bias_ih_l0"], P["encoder.lstm.bias_hh_l0"])
+    assert (h - h_ref).abs().max() < 3e-6 and (c - c_ref).abs().max() < 3e-6
+
+
+def test_newton_reciprocal_of_the_pair_kernel_cell():
+    """rcp_newton (csrc/sw_umma.cuh): magic-constant seed + three Newton steps, over the range the cell update feeds it
+    (products of four (1 + 2^e) terms, e <= 30): relative error below 1e-7."""
+    x = torch.exp2(torch.linspace(0.0, 120.0, 200001)).float()
+    seed = (torch.tensor(0x7EF311C7, dtype=torch.int32) - x.view(torch.int32)).view(torch.float32)
+    y = seed
+    for _ in range(3):
+        y = y + y * (1.0 - x * y)
+    rel = ((y.double() * x.double()) - 1.0).abs().max().item()
+    assert rel < 1.2e-7, rel
