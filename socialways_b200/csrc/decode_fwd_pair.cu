@@ -231,11 +231,12 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 __syncwarp();
             };
             for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
-                const int n_act = ub + 1 < n_units ? 2 : 1;
+                // (both slots always run: the slot of a unit or tile beyond the batch works on zero rows -- at most one tile per
+                //  pair at the very end -- which keeps every "is the slot active" test out of the step loops)
 #pragma unroll 1
-                for (int sl = 0; sl < n_act; ++sl) issue_hoist(sl);
+                for (int sl = 0; sl < 2; ++sl) issue_hoist(sl);
 #pragma unroll 1
-                for (int sl = 0; sl < n_act; ++sl) issue_l1(sl);       // layer 1 of step 0
+                for (int sl = 0; sl < 2; ++sl) issue_l1(sl);           // layer 1 of step 0
                 // Step loop.  The slots run HALF A STEP apart (slot 1 behind): the epilogue warps visit
                 //   L1(0,t)  cell(1,t-1)  L2(0,t)  L1(1,t)  cell(0,t)  L2(1,t)
                 // so that the long MMA group (layer 2 + the h part of gates half 0: ~2.5 K clk) of one slot runs under the long
@@ -247,7 +248,6 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
 #pragma unroll 1
                     for (int e = 0; e < 6; ++e) {
                         const int sl = e & 1, kind = e % 3;
-                        if (sl >= n_act) continue;
                         if (kind == 0) issue_l2(sl, feed_back);
                         else if (kind == 1) { if (sl == 1 ? t > 0 : feed_back) issue_l1(sl); }
                         else if (feed_back) issue_x(sl);
@@ -286,7 +286,6 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
         if (fin[1]) vel_free_arrive(1);
 
         for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
-            const int n_act = ub + 1 < n_units ? 2 : 1;
             bool has_tile[2], valid[2];
             long long row0[2];
             int abase[2], agent[2];
@@ -299,7 +298,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
                 const int tile = 2 * (ub + sl) + (int)cta;
-                has_tile[sl] = sl < n_act && tile < n_tiles;              // the odd last unit has one tile only
+                has_tile[sl] = tile < n_tiles;                            // a slot without a tile (end of the batch) runs on zero rows
                 row0[sl] = (long long)tile * P_ROWS;
                 valid[sl] = has_tile[sl] && row0[sl] + r < n_rows;
                 abase[sl] = has_tile[sl] ? (int)(row0[sl] % n_agents) : 0;
@@ -310,7 +309,6 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                                                : make_float4(0.f, 0.f, 0.f, 0.f);
                     c[sl][4 * q] = v.x; c[sl][4 * q + 1] = v.y; c[sl][4 * q + 2] = v.z; c[sl][4 * q + 3] = v.w;
                 }
-                if (sl >= n_act) continue;
                 {   // S tile [128 rows][16 pieces] -> the slot's (still unused) h operand region, piece' = piece ^ (row & 7), by cp.async:
                     // global -> shared without a register in between.  (Through registers the 8 loaded float4 of both slots did not
                     // fit beside the cell state: ptxas spilled each one right behind its load, and every spill store waited for
@@ -350,7 +348,6 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 }
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
-                if (sl >= n_act) continue;
                 float4* sS = reinterpret_cast<float4*>(s.h[sl][0]);       // [128 rows][16 pieces], piece' = piece ^ (row & 7); 32 KB = h hi|lo
                 const float4* sZ = reinterpret_cast<const float4*>(s.zst[sl]);   // [128 rows][8 pieces], TMA swizzle: piece' = piece ^ (row & 7)
                 asm volatile("cp.async.wait_all;" ::: "memory");          // this thread's pieces of the S tile(s) have landed
@@ -405,13 +402,12 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                     }
                 }
             }
-            float p0 = xl.x, p1 = xl.y;                                   // state of the rows this thread finishes (one slot at most)
             bool out_of_range = false;
+            float p0 = xl.x, p1 = xl.y;                                   // state of the rows this thread finishes (one slot at most)
             float4* sc[2];
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
                 sc[sl] = scratch + ((size_t)blockIdx.x * 2 + sl) * P_SCRATCH_F4_PER_SLOT + (size_t)kb0[sl] * 4 * P_ROWS + r;
-                if (sl >= n_act) continue;
                 const uint32_t ta = tl + (uint32_t)(sl * 256) + PC_R1 + kb0[sl] * 16;
                 wait_full3(&s.full[sl][0], (ph >> sl) & 1u); ph ^= 1u << sl;      // c1 + b1 -> scratch (the K blocks this thread re-reads)
                 if (three[sl]) c1_to_scratch<Q_NB>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
@@ -538,13 +534,13 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             for (int t = 0; t < n_next; ++t) {
                 const bool feed_back = t + 1 < n_next;
                 phase_l1(S0{});
-                if (n_act > 1 && t > 0) phase_cell(S1{});
-                if (n_act > 1) c1_prefetch(S1{});
+                if (t > 0) phase_cell(S1{});
+                c1_prefetch(S1{});
                 phase_l2(S0{}, t, feed_back);
-                if (n_act > 1) phase_l1(S1{});
+                phase_l1(S1{});
                 if (feed_back) phase_cell(S0{});
                 if (feed_back) c1_prefetch(S0{});
-                if (n_act > 1) phase_l2(S1{}, t, feed_back);
+                phase_l2(S1{}, t, feed_back);
             }
             if (out_of_range && status) {
                 if ((fin[0] && valid[0]) || (fin[1] && valid[1])) atomicOr(status, 1);
