@@ -53,6 +53,7 @@ struct PairSmem {
     unsigned long long ready[2];             // operands written: 32 warp arrivals (16 warps x 2 CTAs), used in the leader CTA
     unsigned long long ready_x[2];           // x block written: 8 arrivals (the 4 finishing warps x 2 CTAs)
     unsigned long long full[2][3];           // MMA completion: hoist / L1 / L2 | gates half 0 | gates half 1
+    unsigned long long vfree[2];             // partial velocities consumed by the finishing warps (4 warp arrivals per step)
     unsigned long long bar_z[2];             // TMA: the slot's noise block
     unsigned long long bar_w;                // TMA: weights
     uint32_t tmem_base;
@@ -64,12 +65,11 @@ __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, %0;" :: "
 // finishing warps wait for all 16
 __device__ __forceinline__ void vel_arrive(int sl) { asm volatile("bar.arrive %0, %1;" :: "r"(2 + sl), "n"(Q_EPI) : "memory"); }
 __device__ __forceinline__ void vel_sync(int sl) { asm volatile("bar.sync %0, %1;" :: "r"(2 + sl), "n"(Q_EPI) : "memory"); }
-// ... and the way back (named barrier 4 + slot): the finishing warps announce "partials consumed", the contributing warps pass
-// it before they overwrite the buffer a step later.  The arrival is a whole step old by then (the next write sits behind this
-// slot's cell update, layer-1 MMAs and layer-1 epilogue, all of which wait for the finishing warps), so nobody ever blocks
-// here; it makes the write-after-read order explicit instead of implied by the mbarrier / MMA chain (and visible to racecheck).
-__device__ __forceinline__ void vel_free_arrive(int sl) { asm volatile("bar.arrive %0, %1;" :: "r"(4 + sl), "n"(Q_EPI) : "memory"); }
-__device__ __forceinline__ void vel_free_sync(int sl) { asm volatile("bar.sync %0, %1;" :: "r"(4 + sl), "n"(Q_EPI) : "memory"); }
+// ... and the way back (mbarrier vfree[slot], 4 warp arrivals): the finishing warps announce "partials consumed", a contributing
+// warp checks it before it overwrites the buffer a step later.  The arrival is a whole step old by then (the next write sits
+// behind this slot's cell update, layer-1 MMAs and layer-1 epilogue, all of which wait for the finishing warps), so the check
+// passes at once; it makes the write-after-read order explicit instead of implied by the mbarrier / MMA chain.  (A named
+// barrier in its place -- bar.sync for the 12 contributing warps -- made those warps wait for EACH OTHER: 2 % of all samples.)
 __device__ __forceinline__ void wait_full3(unsigned long long* bar, uint32_t parity) {
     mbar_wait(bar, parity);
     ptx::tcgen05_fence_after_thread_sync();
@@ -155,6 +155,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.ready_x[sl]), 8);
             for (int j = 0; j < 3; ++j) ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.full[sl][j]), 1);
             ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar_z[sl]), 1);
+            ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.vfree[sl]), 4);
         }
         ptx::mbarrier_init(reinterpret_cast<uint64_t*>(&s.bar_w), 1);
         ptx::fence_mbarrier_init(ptx::sem_release, ptx::scope_cluster);
@@ -260,7 +261,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
         asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
         const int etid = r + (cq << 7), ewarp = etid >> 5;                // = threadIdx.x / warp index of these warps, from the pinned registers
         const uint32_t tl = tmem + ((uint32_t)(lq * 32) << 16);           // this thread's lane, slot 0, column 0
-        uint32_t ph = 0;                    // barrier parities, one register: bit sl = full[sl][0], bit 2 + sl = gates, bit 4 + sl = noise block
+        uint32_t ph = 0;                    // barrier parities, one register: bit sl = full[sl][0], bit 2 + sl = gates, bit 4 + sl = noise block, bit 6 + sl = vfree
         // every warp: "my operand writes are done" -> one arrival on the leader CTA's barrier
         // (address of ready[0] in the LEADER CTA's shared memory, computed once: ready[1], ready_x[0], ready_x[1] follow at +8 ...)
         uint32_t ready0_leader;
@@ -282,8 +283,6 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             fin[1] = cq == 1;
         }
         const bool three[2] = {cq < 2, cq >= 2};
-        if (fin[0]) vel_free_arrive(0);     // prime the "partials consumed" barriers: the first step of the first tile finds them passed
-        if (fin[1]) vel_free_arrive(1);
 
         for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
             bool has_tile[2], valid[2];
@@ -462,8 +461,9 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                     }
                 }
                 ptx::tcgen05_fence_before_thread_sync();
+                ph ^= 64u << sl;            // parity of vfree[sl]: one phase per step
                 if (!fin[sl]) {
-                    vel_free_sync(sl);
+                    mbar_wait(&s.vfree[sl], (ph >> (6 + sl)) & 1u);     // phase of the PREVIOUS step (a fresh barrier passes parity 1: first step)
                     s.vpart[sl][(cq * 2) * P_ROWS + r] = v0; s.vpart[sl][(cq * 2 + 1) * P_ROWS + r] = v1;
                     vel_arrive(sl);     // (bar.arrive orders the shared-memory writes above before the finishing warps' reads)
                 } else {            // velocity, integration, emit; (p, v) -> hi|lo x block of the gate MMA
@@ -472,7 +472,8 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         if (q != (sl == 0 ? 2 : 1)) { v0 += vp[(q * 2) * P_ROWS + r]; v1 += vp[(q * 2 + 1) * P_ROWS + r]; }
-                    vel_free_arrive(sl);
+                    __syncwarp();
+                    if (lane == 0) ptx::mbarrier_arrive(reinterpret_cast<uint64_t*>(&s.vfree[sl]));
                     v0 += s.f32[PF_B34]; v1 += s.f32[PF_B34 + 1];
                     p0 += v0; p1 += v1;
                     out_of_range |= !(fmaxf(fmaxf(fabsf(p0), fabsf(p1)), fmaxf(fabsf(v0), fabsf(v1))) <= 6.0e4f);   // fp16 range guard
