@@ -283,6 +283,12 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             fin[1] = cq == 1;
         }
         const bool three[2] = {cq < 2, cq >= 2};
+        // this thread's scratch lines (float4 index; fixed for the whole kernel): pinned, or ptxas re-derives them from S2R ctaid /
+        // tid (~30 instructions) at every c1 prefetch
+        uint32_t sc_idx[2];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) sc_idx[sl] = (blockIdx.x * 2 + sl) * P_SCRATCH_F4_PER_SLOT + kb0[sl] * 4 * P_ROWS + r;
+        asm volatile("" : "+r"(sc_idx[0]), "+r"(sc_idx[1]));
 
         for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
             bool has_tile[2], valid[2];
@@ -406,7 +412,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             float4* sc[2];
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
-                sc[sl] = scratch + ((size_t)blockIdx.x * 2 + sl) * P_SCRATCH_F4_PER_SLOT + (size_t)kb0[sl] * 4 * P_ROWS + r;
+                sc[sl] = scratch + sc_idx[sl];
                 const uint32_t ta = tl + (uint32_t)(sl * 256) + PC_R1 + kb0[sl] * 16;
                 wait_full3(&s.full[sl][0], (ph >> sl) & 1u); ph ^= 1u << sl;      // c1 + b1 -> scratch (the K blocks this thread re-reads)
                 if (three[sl]) c1_to_scratch<Q_NB>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
