@@ -36,10 +36,7 @@
 namespace sw {
 
 constexpr int Q_EPI = 512;            // epilogue threads (warps 0..15)
-#ifndef Q_BIG
-#define Q_BIG 3
-#endif
-constexpr int Q_NB = Q_BIG, Q_NS = 5 - Q_BIG;   // layer-1 K blocks of a "big" / "small" quarter (2 big + 2 small = 10 blocks)
+constexpr int Q_NB = 3, Q_NS = 2;     // layer-1 K blocks of a "big" / "small" quarter (2 big + 2 small = 10 blocks; 4 / 1 measured equal)
 constexpr int Q_THREADS = 640;        // + the issuing warp's warpgroup (register file = 4 x 16 K: a 17th warp alone would cap
                                       //   every thread at 96 registers; setmaxnreg moves the idle group's registers over)
 
@@ -440,11 +437,6 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 constexpr int sl = decltype(slc)::value;
                 const float4* b2 = reinterpret_cast<const float4*>(s.f32 + PF_B2 + cq * 20);
                 const float4* w34 = reinterpret_cast<const float4*>(s.f32 + PF_W34 + cq * 40);
-#ifdef Q_P2_PRELOAD
-                float4 bb[5];
-#pragma unroll
-                for (int j = 0; j < 5; ++j) bb[j] = b2[j];
-#endif
                 wait_full3(&s.full[sl][0], (ph >> sl) & 1u); ph ^= 1u << sl;
                 float v0 = 0.0f, v1 = 0.0f;
                 {
@@ -453,11 +445,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                     ptx::tcgen05_wait_ld();
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
-#ifdef Q_P2_PRELOAD
-                        const float4 b = bb[j], wa = w34[2 * j], wb = w34[2 * j + 1];
-#else
                         const float4 b = b2[j], wa = w34[2 * j], wb = w34[2 * j + 1];
-#endif
                         const float y0 = lrelu02(__uint_as_float(acc[4 * j]) + b.x), y1 = lrelu02(__uint_as_float(acc[4 * j + 1]) + b.y);
                         const float y2 = lrelu02(__uint_as_float(acc[4 * j + 2]) + b.z), y3 = lrelu02(__uint_as_float(acc[4 * j + 3]) + b.w);
                         v0 = fmaf(y0, wa.x, v0); v1 = fmaf(y0, wa.y, v1);
@@ -514,11 +502,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                         for (int w2 = 0; w2 < 2; ++w2)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) g[w2][q] = __uint_as_float(a[(uu + w2) * 4 + q]);
-#ifdef Q_CELL2
-                        lstm_cell_pair_prescaled_x2(g[0], g[1], c[sl][half * 8 + uu], c[sl][half * 8 + uu + 1], hv[uu], hv[uu + 1]);
-#else
                         lstm_cell_pair_prescaled(g[0], g[1], c[sl][half * 8 + uu], c[sl][half * 8 + uu + 1], hv[uu], hv[uu + 1]);
-#endif
                     }
                     uint32_t hh[4], ll[4];
 #pragma unroll

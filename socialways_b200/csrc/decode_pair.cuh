@@ -33,19 +33,6 @@ __device__ __forceinline__ void psplit2(float a, float b, uint32_t& hi, uint32_t
     hi = *reinterpret_cast<const uint32_t*>(&h2);
     lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
-template <int NL, int KB>
-__device__ __forceinline__ void pmma3_ss(uint32_t d, const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo,
-                                         bool leader) {
-    pmma_ss<NL, KB>(d, a_hi, b_hi, PFMT, false, leader);
-    pmma_ss<NL, KB>(d, a_hi, b_lo, PFMT, true, leader);
-    pmma_ss<NL, KB>(d, a_lo, b_hi, PFMT, true, leader);
-}
-template <int NL, int KB, int A_STRIDE>
-__device__ __forceinline__ void pmma3_ts(uint32_t d, uint32_t a_hi, uint32_t a_lo, const __half* b_hi, const __half* b_lo, bool leader) {
-    pmma_ts<NL, KB, A_STRIDE>(d, a_hi, b_hi, PFMT, false, leader);
-    pmma_ts<NL, KB, A_STRIDE>(d, a_hi, b_lo, PFMT, true, leader);
-    pmma_ts<NL, KB, A_STRIDE>(d, a_lo, b_hi, PFMT, true, leader);
-}
 // single-thread forms (inside `if (elect_one())`)
 template <int NL, int KB>
 __device__ __forceinline__ void pmma3_ss1(uint32_t d, const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo) {

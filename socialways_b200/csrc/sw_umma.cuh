@@ -120,17 +120,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// arrive on the mbarrier at the same shared-memory offset as `bar` in CTA `cta` of the cluster.  Default semantics
-// (.release.cta), as CUTLASS's ClusterBarrier::arrive(cta_id): the cluster-scope form costs MEMBAR.ALL.GPU + ERRBAR per
-// arrival and CCTL.IVALL (an L1 invalidation) per wait -- 47 % of all stall samples of the first version of
-// the pair decode kernel (ncu).  What crosses the pair here is consumed by the tensor core's async proxy (shared-memory operands,
-// made visible by fence.proxy.async before the arrival) or lives in TMEM (tcgen05.wait::st + fence::before_thread_sync).
-__device__ __forceinline__ void mbar_arrive_cluster(unsigned long long* bar, uint32_t cta) {
-    uint32_t ra;
-    const uint32_t la = (uint32_t)__cvta_generic_to_shared(bar);
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(cta));
-    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(ra) : "memory");
-}
+// (Remote arrivals -- mapa + mbarrier.arrive.shared::cluster, default .release.cta semantics as CUTLASS's
+// ClusterBarrier::arrive(cta_id) -- are issued inline by the kernels: the cluster-scope form costs MEMBAR.ALL.GPU + ERRBAR per
+// arrival and CCTL.IVALL per wait, 47 % of all stall samples of the first pair kernel.  What crosses the pair is consumed by
+// the tensor core's async proxy (shared-memory operands, made visible by fence.proxy.async before the arrival) or lives in
+// TMEM (tcgen05.wait::st + fence::before_thread_sync).)
 // wait on a barrier of this CTA whose arrivals come from the peer CTA (operand-ready) or from a multicast tcgen05.commit
 __device__ __forceinline__ void mbar_wait_cluster(unsigned long long* bar, uint32_t parity) { mbar_wait(bar, parity); }
 // completion of every MMA issued so far by this thread -> one arrival on `bar` in BOTH CTAs of the pair
@@ -296,8 +290,6 @@ __device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t* v) {
 // exp2-based activations: abs error ~5e-7 (ex2.approx 2^-22 rel, rcp.approx 1 ulp) at ~5 instructions
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f); }
 
 
 // e^{-x} for the logistic forms below, argument clamped so that products of two (1 + e) terms stay finite
@@ -307,34 +299,8 @@ __device__ __forceinline__ float expneg_clamped(float x) { return ex2_approx(fmi
 // so the four logistic denominators of a unit share ONE reciprocal, 1/(A.B.C.D), from which 1/A .. 1/D follow by
 // multiplications, and the two tanh(c) of the unit pair share another: 10 ex2 + 3 rcp per 2 units instead of 10 + 10.
 // Exponents are clamped at 2^30 so that the 4-fold product stays finite (sigma(x) floors at 2^-30 ~ 1e-9: far below
-// fp32 resolution of the cell update).  g = pre-activations (i, f, g, o); c updated in place.
-__device__ __forceinline__ float expneg30(float x) { return ex2_approx(fminf(-1.4426950408889634f * x, 30.0f)); }
-__device__ __forceinline__ void lstm_cell_pair(const float (&ga)[4], const float (&gb)[4], float& ca, float& cb,
-                                               float& ha, float& hb) {
-    float cn[2];
-    const float* gs[2] = {ga, gb};
-    const float cs[2] = {ca, cb};
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const float* g = gs[q];
-        const float ai = 1.0f + expneg30(g[0]), af = 1.0f + expneg30(g[1]);
-        const float ag = 1.0f + expneg30(2.0f * g[2]), ao = 1.0f + expneg30(g[3]);
-        const float p_ig = ai * ag, p_fo = af * ao;
-        const float r = rcp_approx(p_ig * p_fo);
-        const float r_ig = r * p_fo, r_fo = r * p_ig;            // 1/(ai.ag), 1/(af.ao)
-        const float sig_i = ag * r_ig, tanh_g = fmaf(2.0f * ai, r_ig, -1.0f);
-        cn[q] = fmaf(ao * r_fo, cs[q], sig_i * tanh_g);          // sigma(f) = ao / (af.ao)
-        if (q == 0) ha = af * r_fo; else hb = af * r_fo;         // sigma(o), multiplied by tanh(c) below
-    }
-    const float a0 = 1.0f + expneg_clamped(2.0f * cn[0]), a1 = 1.0f + expneg_clamped(2.0f * cn[1]);
-    const float r = rcp_approx(a0 * a1);
-    ha *= fmaf(2.0f * a1, r, -1.0f);
-    hb *= fmaf(2.0f * a0, r, -1.0f);
-    ca = cn[0];
-    cb = cn[1];
-}
-
-// Same cell with PRE-SCALED pre-activations: e = (-log2 e . x_i, -log2 e . x_f, -2 log2 e . x_g, -log2 e . x_o), i.e. the ex2
+// fp32 resolution of the cell update).  c updated in place.
+// PRE-SCALED pre-activations: e = (-log2 e . x_i, -log2 e . x_f, -2 log2 e . x_g, -log2 e . x_o), i.e. the ex2
 // arguments themselves (the scale lives in the packed gate weights, packing.pack_decoder_tcx) -- 4 multiplies per unit less.
 // Reciprocal on the FMA pipe: magic-constant seed (12 % off) + three Newton steps (relative error 6e-8).  The cell update of
 // the pair decode kernel sits at the balance point between the MUFU pipe (16 lanes/clk/SM) and instruction issue: with
@@ -373,47 +339,6 @@ __device__ __forceinline__ void lstm_cell_pair_prescaled(const float (&ea)[4], c
     hb *= fmaf(2.0f * a0, r, -1.0f);
     ca = cn[0];
     cb = cn[1];
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 -- one issue slot for two IEEE fp32 operations on a 64-bit register
-// pair).  The epilogues of the decode kernels are bound by instruction issue and dependency latency at 4 warps per scheduler,
-// not by the FMA pipe, so halving the instruction count of the arithmetic that comes in identical pairs (two hidden units,
-// two columns) is worth more than anything the pipes themselves could give.
-// ---------------------------------------------------------------------------------------------------------------
-struct f32x2 { unsigned long long v; };
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpk2(f32x2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
-
-// lstm_cell_pair_prescaled with the two units of the pair carried as the two halves of fp32x2 values: the same formulas and
-// the same operation order per unit (bit-identical results), 46 instead of 74 instructions per pair.
-__device__ __forceinline__ void lstm_cell_pair_prescaled_x2(const float (&ea)[4], const float (&eb)[4], float& ca, float& cb,
-                                                            float& ha, float& hb) {
-    const f32x2 one = pk2(1.0f, 1.0f), mone = pk2(-1.0f, -1.0f);
-    const f32x2 ai = add2(one, pk2(ex2_approx(fminf(ea[0], 30.0f)), ex2_approx(fminf(eb[0], 30.0f))));
-    const f32x2 af = add2(one, pk2(ex2_approx(fminf(ea[1], 30.0f)), ex2_approx(fminf(eb[1], 30.0f))));
-    const f32x2 ag = add2(one, pk2(ex2_approx(fminf(ea[2], 30.0f)), ex2_approx(fminf(eb[2], 30.0f))));
-    const f32x2 ao = add2(one, pk2(ex2_approx(fminf(ea[3], 30.0f)), ex2_approx(fminf(eb[3], 30.0f))));
-    const f32x2 p_ig = mul2(ai, ag), p_fo = mul2(af, ao);
-    const f32x2 pp = mul2(p_ig, p_fo);
-    float ppa, ppb;
-    unpk2(pp, ppa, ppb);
-    const f32x2 r = pk2(rcp_approx(ppa), rcp_approx(ppb));
-    const f32x2 r_ig = mul2(r, p_fo), r_fo = mul2(r, p_ig);            // 1/(ai.ag), 1/(af.ao)
-    const f32x2 sig_i = mul2(ag, r_ig), tanh_g = fma2(add2(ai, ai), r_ig, mone);
-    const f32x2 cn = fma2(mul2(ao, r_fo), pk2(ca, cb), mul2(sig_i, tanh_g));   // sigma(f) = ao / (af.ao)
-    const f32x2 so = mul2(af, r_fo);                                    // sigma(o)
-    float cna, cnb;
-    unpk2(cn, cna, cnb);
-    const float a0 = 1.0f + expneg_clamped(2.0f * cna), a1 = 1.0f + expneg_clamped(2.0f * cnb);
-    const float rr = rcp_approx(a0 * a1);
-    const f32x2 th = pk2(fmaf(2.0f * a1, rr, -1.0f), fmaf(2.0f * a0, rr, -1.0f));
-    unpk2(mul2(so, th), ha, hb);
-    ca = cna;
-    cb = cnb;
 }
 
 // bf16-mode cell: hardware tanh (MUFU.TANH, rel. error 2^-11, below the bf16 operand rounding), 5 MUFU per unit
