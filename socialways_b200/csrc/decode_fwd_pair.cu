@@ -74,15 +74,18 @@ __device__ __forceinline__ void wait_full3(unsigned long long* bar, uint32_t par
 
 // layer-1 epilogue of NKB K blocks: a1 = lrelu(acc + c1) -> hi|lo fp16 written in place (hi -> columns +0..7, lo -> +8..15 of
 // the 16 accumulator columns the thread has just read); c1 (+ b1) comes from this thread's scratch lines, one block ahead
-template <int NKB>
-__device__ __forceinline__ void l1_epilogue(uint32_t t_acc, const float4* sc, unsigned long long* bar, uint32_t parity, float4 (&cn)[4]) {
+// `third`: the thread owns three blocks (a "big" quarter), else two.  ONE copy of the block code serves both cases (the step
+// loop is ~50 KB of SASS and sensitive to its size: a second copy of the step costs 18 %).
+__device__ __forceinline__ void l1_epilogue(uint32_t t_acc, const float4* sc, unsigned long long* bar, uint32_t parity, float4 (&cn)[4],
+                                            bool third) {
     // cn = c1 of the first block, loaded a whole phase earlier (c1_prefetch): the scratch lives in L2 (~700 clk away; the L1 is
     // all shared memory here), and a load issued just before the barrier wait was exposed at every phase start
     wait_full3(bar, parity);
 #pragma unroll
-    for (int kb = 0; kb < NKB; ++kb) {
+    for (int kb = 0; kb < Q_NB; ++kb) {
+        if (kb == Q_NB - 1 && !third) break;
         const float4 cc[4] = {cn[0], cn[1], cn[2], cn[3]};
-        if (kb + 1 < NKB) {
+        if (kb + 1 < Q_NS || (kb + 1 < Q_NB && third)) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) cn[q] = __ldcg(sc + ((kb + 1) * 4 + q) * P_ROWS);
         }
@@ -427,8 +430,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             auto phase_l1 = [&](auto slc) {
                 constexpr int sl = decltype(slc)::value;
                 const uint32_t ta = tl + (uint32_t)(sl * 256) + PC_R1 + kb0[sl] * 16;
-                if (three[sl]) l1_epilogue<Q_NB>(ta, sc[sl], &s.full[sl][0], (ph >> sl) & 1u, cpre);
-                else           l1_epilogue<Q_NS>(ta, sc[sl], &s.full[sl][0], (ph >> sl) & 1u, cpre);
+                l1_epilogue(ta, sc[sl], &s.full[sl][0], (ph >> sl) & 1u, cpre, three[sl]);
                 ph ^= 1u << sl;
                 arrive(&s.ready[sl]);                                     // -> layer 2 (+ h part of gates half 0)
             };
