@@ -163,7 +163,8 @@ int sw_decode_tcx_pack_sizes(int* n_w16, int* n_wsz16, int* n_f32);
  * weight matrix), all 16 epilogue warps of a CTA serve two tile slots alternately (while they work on one slot's epilogue the
  * tensor pipe runs the other slot's MMAs), a dedicated warp issues every MMA of the pair, and the hoisted layer-1 term lives
  * in `scratch` (device memory, sw_decode_pair_scratch_bytes(sm_count) bytes, 16-byte aligned; written and re-read inside the
- * launch, contents meaningless afterwards; one buffer per concurrently running launch).
+ * launch, contents meaningless afterwards; one buffer per concurrently running launch).  h0 and c0 must be 32-byte aligned
+ * (their rows are read in 32-byte pieces), pooled and noise 16-byte aligned: SW_ERR_ARG otherwise.
  * Same inputs / outputs / status word / arithmetic as sw_decode_fwd_tcx; pack from packing.pack_decoder_pair
  * (sizes via sw_decode_pair_pack_sizes).  Replaces the loop of predict(), reference train.py:418-430, x K samples. */
 int sw_decode_fwd_pair(const void* pair_w16, const float* pair_f32, const float* h0, const float* c0, const float* pooled,

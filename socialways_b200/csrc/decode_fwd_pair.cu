@@ -35,6 +35,13 @@
 
 namespace sw {
 
+#ifdef SW_PAIR_TRACE      // timeline of one tile pair (scripts/pair_trace.py): clock64 of thread 0 of CTA 0 at the marked points
+__device__ long long g_pair_trace[64];
+#define SW_TR(i) do { if (tr_on) g_pair_trace[i] = clock64(); } while (0)
+#else
+#define SW_TR(i) do { } while (0)
+#endif
+
 constexpr int Q_EPI = 512;            // epilogue threads (warps 0..15)
 constexpr int Q_NB = 3, Q_NS = 2;     // layer-1 K blocks of a "big" / "small" quarter (2 big + 2 small = 10 blocks; 4 / 1 measured equal)
 constexpr int Q_THREADS = 640;        // + the issuing warp's warpgroup (register file = 4 x 16 K: a 17th warp alone would cap
@@ -67,6 +74,13 @@ __device__ __forceinline__ void vel_sync(int sl) { asm volatile("bar.sync %0, %1
 // behind this slot's cell update, layer-1 MMAs and layer-1 epilogue, all of which wait for the finishing warps), so the check
 // passes at once; it makes the write-after-read order explicit instead of implied by the mbarrier / MMA chain.  (A named
 // barrier in its place -- bar.sync for the 12 contributing warps -- made those warps wait for EACH OTHER: 2 % of all samples.)
+// 32 bytes of a row in ONE request (LDG.256): the per-row loads of the tile prologue touch a different cache line per lane, and
+// the tag stage of L1 serves ~1 line per clock -- with 16-byte loads the c0 rows of a tile pair took ~7 K clk to ISSUE
+__device__ __forceinline__ void ldg256(const float* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
 __device__ __forceinline__ void wait_full3(unsigned long long* bar, uint32_t parity) {
     mbar_wait(bar, parity);
     ptx::tcgen05_fence_after_thread_sync();
@@ -104,19 +118,21 @@ __device__ __forceinline__ void l1_epilogue(uint32_t t_acc, const float4* sc, un
     ptx::tcgen05_wait_st();
 }
 
-// c1 + b1 of NKB K blocks: TMEM -> this thread's scratch lines (once per tile)
-template <int NKB>
-__device__ __forceinline__ void c1_to_scratch(uint32_t t_acc, float4* sc, const float* __restrict__ b1) {
+// c1 + b1 of this thread's K blocks (2, or 3 with `third`): TMEM -> its scratch lines (once per tile); all loads in flight before the one wait
+__device__ __forceinline__ void c1_to_scratch(uint32_t t_acc, float4* sc, const float* __restrict__ b1, bool third) {
+    uint32_t v[Q_NB][16];
 #pragma unroll
-    for (int kb = 0; kb < NKB; ++kb) {
-        uint32_t v[16];
-        tmem_ld<16>(t_acc + kb * 16, v);
-        ptx::tcgen05_wait_ld();
+    for (int kb = 0; kb < Q_NB; ++kb)
+        if (kb < Q_NS || third) tmem_ld<16>(t_acc + kb * 16, v[kb]);
+    ptx::tcgen05_wait_ld();
+#pragma unroll
+    for (int kb = 0; kb < Q_NB; ++kb) {
+        if (kb >= Q_NS && !third) break;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 b = *reinterpret_cast<const float4*>(b1 + kb * 16 + 4 * q);
-            __stcg(sc + (kb * 4 + q) * P_ROWS, make_float4(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y,
-                                                          __uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w));
+            __stcg(sc + (kb * 4 + q) * P_ROWS, make_float4(__uint_as_float(v[kb][4 * q]) + b.x, __uint_as_float(v[kb][4 * q + 1]) + b.y,
+                                                          __uint_as_float(v[kb][4 * q + 2]) + b.z, __uint_as_float(v[kb][4 * q + 3]) + b.w));
         }
     }
 }
@@ -231,7 +247,17 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 }
                 __syncwarp();
             };
-            for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
+            // agent of the first row of each slot's tile, carried from tile to tile (the tiles of a slot advance by 4 n_pairs tiles): one
+        // 64-bit modulo per kernel; rows inside a tile wrap with a compare (the prologue spent ~3 K clk per tile pair in `%`)
+        int abase[2];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) abase[sl] = (int)(((long long)(2 * (2 * pair + sl) + (int)cta) * P_ROWS) % n_agents);
+        const int astep = (int)(((long long)4 * n_pairs * P_ROWS) % n_agents);
+        auto wrap = [&](int v) {            // v < n_agents + 128: one round unless the batch has fewer than 128 agents
+            while (v >= n_agents) v -= n_agents;
+            return v;
+        };
+        for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
                 // (both slots always run: the slot of a unit or tile beyond the batch works on zero rows -- at most one tile per
                 //  pair at the very end -- which keeps every "is the slot active" test out of the step loops)
 #pragma unroll 1
@@ -290,10 +316,24 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
         for (int sl = 0; sl < 2; ++sl) sc_idx[sl] = (blockIdx.x * 2 + sl) * P_SCRATCH_F4_PER_SLOT + kb0[sl] * 4 * P_ROWS + r;
         asm volatile("" : "+r"(sc_idx[0]), "+r"(sc_idx[1]));
 
+        // agent of the first row of each slot's tile, carried from tile to tile (the tiles of a slot advance by 4 n_pairs tiles): one
+        // 64-bit modulo per kernel; rows inside a tile wrap with a compare (the prologue spent ~3 K clk per tile pair in `%`)
+        int abase[2];
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) abase[sl] = (int)(((long long)(2 * (2 * pair + sl) + (int)cta) * P_ROWS) % n_agents);
+        const int astep = (int)(((long long)4 * n_pairs * P_ROWS) % n_agents);
+        auto wrap = [&](int v) {            // v < n_agents + 128: one round unless the batch has fewer than 128 agents
+            while (v >= n_agents) v -= n_agents;
+            return v;
+        };
         for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
+#ifdef SW_PAIR_TRACE
+            const bool tr_on = blockIdx.x == 0 && etid == 0 && ub == 2 * pair + 2 * (2 * n_pairs);
+#endif
+            SW_TR(0);
             bool has_tile[2], valid[2];
             long long row0[2];
-            int abase[2], agent[2];
+            int rows_here[2], agent[2];     // rows of the tile inside the batch (0: no tile, < 128: last tile)
             float2 xl = make_float2(0.f, 0.f);
             float* out_row = out;           // where this thread emits (the rows of the slot it finishes; one slot at most)
             // cell state of this thread's units: c[sl][0..7] = units 8 cq .. (gates half 0), c[sl][8..15] = units 32 + 8 cq .. (half 1);
@@ -305,32 +345,37 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 const int tile = 2 * (ub + sl) + (int)cta;
                 has_tile[sl] = tile < n_tiles;                            // a slot without a tile (end of the batch) runs on zero rows
                 row0[sl] = (long long)tile * P_ROWS;
-                valid[sl] = has_tile[sl] && row0[sl] + r < n_rows;
-                abase[sl] = has_tile[sl] ? (int)(row0[sl] % n_agents) : 0;
-                agent[sl] = valid[sl] ? (abase[sl] + r) % n_agents : 0;
+                rows_here[sl] = has_tile[sl] ? (int)(n_rows - row0[sl] < P_ROWS ? n_rows - row0[sl] : P_ROWS) : 0;
+                valid[sl] = r < rows_here[sl];
+                agent[sl] = valid[sl] ? wrap(abase[sl] + r) : 0;
+                SW_TR(49 + 4 * sl);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 v = valid[sl] ? __ldg(reinterpret_cast<const float4*>(c0 + (size_t)agent[sl] * SW_H + (q >> 1) * 32 + cq * 8) + (q & 1))
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-                    c[sl][4 * q] = v.x; c[sl][4 * q + 1] = v.y; c[sl][4 * q + 2] = v.z; c[sl][4 * q + 3] = v.w;
+                for (int half = 0; half < 2; ++half) {                    // units 8 cq .. and 32 + 8 cq ..: 32 contiguous bytes each
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                    if (valid[sl]) ldg256(c0 + (size_t)agent[sl] * SW_H + half * 32 + cq * 8, a, b);
+                    c[sl][8 * half] = a.x; c[sl][8 * half + 1] = a.y; c[sl][8 * half + 2] = a.z; c[sl][8 * half + 3] = a.w;
+                    c[sl][8 * half + 4] = b.x; c[sl][8 * half + 5] = b.y; c[sl][8 * half + 6] = b.z; c[sl][8 * half + 7] = b.w;
                 }
+                SW_TR(50 + 4 * sl);
                 {   // S tile [128 rows][16 pieces] -> the slot's (still unused) h operand region, piece' = piece ^ (row & 7), by cp.async:
                     // global -> shared without a register in between.  (Through registers the 8 loaded float4 of both slots did not
                     // fit beside the cell state: ptxas spilled each one right behind its load, and every spill store waited for
                     // its load -- the loads of the prologue ran one after the other, ~17 K clk per tile pair.)
                     float4* sS = reinterpret_cast<float4*>(s.h[sl][0]);
+                    // piece g = etid + 512 i: row (etid >> 4) + 32 i, the same 16-byte piece and swizzle term for every i; rows outside the
+                    // batch (and every row without a pooled term) are zero-filled by the copy itself (src-size 0): no branch
+                    const int row_a = etid >> 4, piece = etid & 15;
+                    const uint32_t dst0 = (uint32_t)__cvta_generic_to_shared(sS + row_a * 16 + (piece ^ (row_a & 7)));
+                    int a = wrap(abase[sl] + row_a);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {                         // piece g = etid + 512 i
-                        const int g = etid + i * Q_EPI, row = g >> 4, piece = g & 15;
-                        float4* dst = sS + row * 16 + (piece ^ (row & 7));
-                        if (pooled && has_tile[sl] && row0[sl] + row < n_rows) {
-                            const float4* src = reinterpret_cast<const float4*>(pooled + (size_t)((abase[sl] + row) % n_agents) * SW_H) + piece;
-                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
-                        } else {
-                            *dst = make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
+                    for (int i = 0; i < 4; ++i) {
+                        const bool ok = pooled && row_a + 32 * i < rows_here[sl];
+                        const float* src = ok ? pooled + (size_t)a * SW_H + piece * 4 : c0;
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst0 + (uint32_t)(i * 32 * 16 * 16)), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+                        a = wrap(a + 32);
                     }
                 }
+                SW_TR(51 + 4 * sl);
                 if (fin[sl] && valid[sl]) {
                     xl = __ldg(reinterpret_cast<const float2*>(x_last + (size_t)agent[sl] * 4));
                     out_row = out + (size_t)(row0[sl] + r) * n_next * 4;
@@ -338,6 +383,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             }
             // h0 items: (row, 8-column chunk = (lane >> 3) + 4 i), 8 rows x 128 B per instruction; requested here, consumed at the end
             // of each slot's staging below (the S tiles no longer pass through registers, so both slots' items fit)
+            SW_TR(1);
             float4 hreg[2][2][2];
             const int hrow = ewarp * 8 + (lane & 7);
 #pragma unroll
@@ -345,19 +391,21 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     hreg[sl][i][0] = hreg[sl][i][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (has_tile[sl] && row0[sl] + hrow < n_rows) {
-                        const float4* src = reinterpret_cast<const float4*>(h0 + (size_t)((abase[sl] + hrow) % n_agents) * SW_H) + ((lane >> 3) + 4 * i) * 2;
-                        hreg[sl][i][0] = __ldg(src);
-                        hreg[sl][i][1] = __ldg(src + 1);
+                    if (hrow < rows_here[sl]) {
+                        ldg256(h0 + (size_t)wrap(abase[sl] + hrow) * SW_H + ((lane >> 3) + 4 * i) * 8, hreg[sl][i][0], hreg[sl][i][1]);
                     }
                 }
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
                 float4* sS = reinterpret_cast<float4*>(s.h[sl][0]);       // [128 rows][16 pieces], piece' = piece ^ (row & 7); 32 KB = h hi|lo
                 const float4* sZ = reinterpret_cast<const float4*>(s.zst[sl]);   // [128 rows][8 pieces], TMA swizzle: piece' = piece ^ (row & 7)
+                SW_TR(2 + 8 * sl);
                 asm volatile("cp.async.wait_all;" ::: "memory");          // this thread's pieces of the S tile(s) have landed
+                SW_TR(3 + 8 * sl);
                 if (has_tile[sl]) { mbar_wait(&s.bar_z[sl], (ph >> (4 + sl)) & 1u); ph ^= 16u << sl; }
+                SW_TR(4 + 8 * sl);
                 epi_sync();
+                SW_TR(5 + 8 * sl);
                 // [S ; z] (K = 96 = 24 pieces): this thread owns pieces 6 cq .. 6 cq + 5 of its row -> hi|lo TMEM A operand
                 uint32_t hi[12], lo[12];
 #pragma unroll
@@ -373,7 +421,9 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 tmem_st<12>(tls + PC_AHI + cq * 12, hi);
                 tmem_st<12>(tls + PC_ALO + cq * 12, lo);
                 ptx::tcgen05_wait_st();
+                SW_TR(6 + 8 * sl);
                 epi_sync();                                               // staging consumed: h region and noise buffer are free
+                SW_TR(7 + 8 * sl);
                 {   // next tile's noise block: 12 steps ahead of its use
                     const int un = ub + sl + 2 * n_pairs, tn = 2 * un + (int)cta;
                     if (etid == 0 && un < n_units && tn < n_tiles) prefetch_noise(sl, tn);
@@ -391,22 +441,9 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 }
                 ptx::fence_proxy_async(ptx::space_shared);
                 arrive(&s.ready[sl]);                                     // -> hoist MMAs of the slot
+                SW_TR(8 + 8 * sl);
             }
-            {   // the NEXT tiles' rows of pooled / h0 / c0 -> L2, twelve steps ahead of their use (no registers held: prefetch only)
-#pragma unroll
-                for (int sl = 0; sl < 2; ++sl) {
-                    const int un = ub + sl + 2 * n_pairs, tn = 2 * un + (int)cta;
-                    if (un < n_units && tn < n_tiles) {
-                        const long long rown = (long long)tn * P_ROWS + (etid >> 2);          // thread -> (row = etid / 4, 64-byte quarter of the row's 256 B)
-                        if (rown < n_rows) {
-                            const size_t off = (size_t)(rown % n_agents) * SW_H + (etid & 3) * 16;
-                            if (pooled) asm volatile("prefetch.global.L2 [%0];" :: "l"(pooled + off));
-                            asm volatile("prefetch.global.L2 [%0];" :: "l"(h0 + off));
-                            asm volatile("prefetch.global.L2 [%0];" :: "l"(c0 + off));
-                        }
-                    }
-                }
-            }
+            SW_TR(18);
             bool out_of_range = false;
             float p0 = xl.x, p1 = xl.y;                                   // state of the rows this thread finishes (one slot at most)
             float4* sc[2];
@@ -415,9 +452,26 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 sc[sl] = scratch + sc_idx[sl];
                 const uint32_t ta = tl + (uint32_t)(sl * 256) + PC_R1 + kb0[sl] * 16;
                 wait_full3(&s.full[sl][0], (ph >> sl) & 1u); ph ^= 1u << sl;      // c1 + b1 -> scratch (the K blocks this thread re-reads)
-                if (three[sl]) c1_to_scratch<Q_NB>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
-                else           c1_to_scratch<Q_NS>(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16);
+                SW_TR(19 + 2 * sl);
+                c1_to_scratch(ta, sc[sl], s.f32 + PF_B1 + kb0[sl] * 16, three[sl]);
                 arrive(&s.ready[sl]);                                     // -> layer 1 of step 0
+                SW_TR(20 + 2 * sl);
+            }
+            {   // the NEXT tiles' rows of pooled / h0 / c0 -> L2, twelve steps ahead of their use (no registers held: prefetch only);
+                // issued here, under the layer-1 MMAs of step 0 (before the c1 pass it delayed the first step by ~1.2 K clk)
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl) {
+                    const int un = ub + sl + 2 * n_pairs, tn = 2 * un + (int)cta;
+                    abase[sl] += astep;                                   // -> the slot's next tile
+                    if (abase[sl] >= n_agents) abase[sl] -= n_agents;
+                    if (un < n_units && tn < n_tiles && (long long)tn * P_ROWS + (etid >> 2) < n_rows) {
+                        // thread -> (row = etid / 4, 64-byte quarter of the row's 256 B)
+                        const size_t off = (size_t)wrap(abase[sl] + (etid >> 2)) * SW_H + (etid & 3) * 16;
+                        if (pooled) asm volatile("prefetch.global.L2 [%0];" :: "l"(pooled + off));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(h0 + off));
+                        asm volatile("prefetch.global.L2 [%0];" :: "l"(c0 + off));
+                    }
+                }
             }
 
             // ---------------- layer 1 epilogue: a1 = lrelu(acc + c1) -> hi|lo in place ----------------
@@ -526,15 +580,23 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             c1_prefetch(S0{});
             for (int t = 0; t < n_next; ++t) {
                 const bool feed_back = t + 1 < n_next;
+                SW_TR(24 + (t < 2 ? 0 : t == n_next - 1 ? 16 : 8));
                 phase_l1(S0{});
+                SW_TR(25 + (t < 2 ? 0 : t == n_next - 1 ? 16 : 8));
                 if (t > 0) phase_cell(S1{});
                 c1_prefetch(S1{});
+                SW_TR(26 + (t < 2 ? 0 : t == n_next - 1 ? 16 : 8));
                 phase_l2(S0{}, t, feed_back);
+                SW_TR(27 + (t < 2 ? 0 : t == n_next - 1 ? 16 : 8));
                 phase_l1(S1{});
+                SW_TR(28 + (t < 2 ? 0 : t == n_next - 1 ? 16 : 8));
                 if (feed_back) phase_cell(S0{});
                 if (feed_back) c1_prefetch(S0{});
+                SW_TR(29 + (t < 2 ? 0 : t == n_next - 1 ? 16 : 8));
                 phase_l2(S1{}, t, feed_back);
+                SW_TR(30 + (t < 2 ? 0 : t == n_next - 1 ? 16 : 8));
             }
+            SW_TR(48);
             if (out_of_range && status) {
                 if ((fin[0] && valid[0]) || (fin[1] && valid[1])) atomicOr(status, 1);
             }
@@ -555,6 +617,13 @@ static int pair_grid(long long tiles, int sm_count) {
     if (pairs < 1) pairs = 1;
     return (int)(2 * pairs);
 }
+
+#ifdef SW_PAIR_TRACE
+extern "C" int sw_pair_trace_read(long long* out64) {
+    SW_CUDA_TRY(cudaMemcpyFromSymbol(out64, sw::g_pair_trace, sizeof(long long) * 64));
+    return SW_OK;
+}
+#endif
 
 extern "C" long long sw_decode_pair_scratch_bytes(int sm_count) {
     if (sm_count < 2) return 0;
@@ -579,6 +648,7 @@ extern "C" int sw_decode_fwd_pair(const void* pair_w16, const float* pair_f32, c
     const long long tiles = (n_rows + sw::P_ROWS - 1) / sw::P_ROWS;
     if (tiles > 0x3fffffffLL) return SW_ERR_UNSUPPORTED;
     if (((uintptr_t)noise & 15u) != 0) return SW_ERR_ARG;
+    if ((((uintptr_t)h0 | (uintptr_t)c0) & 31u) != 0 || (pooled && ((uintptr_t)pooled & 15u) != 0)) return SW_ERR_ARG;    // 32-byte row pieces (LDG.256), 16-byte cp.async
     CUtensorMap noise_map;
     const int rc = encode_noise_map2(&noise_map, noise, n_rows);
     if (rc != SW_OK) return rc;

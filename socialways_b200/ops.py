@@ -328,7 +328,12 @@ def decode_pair(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, statu
         out = torch.empty(k, n, n_next, 4, device=noise.device)
     if scratch is None:
         scratch = decode_pair_scratch(noise.device)
-    code = _lib.lib().sw_decode_fwd_pair(w16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(_f32(h0)), _lib.ptr(_f32(c0)),
+    h0, c0 = _f32(h0), _f32(c0)
+    if h0.data_ptr() % 32:      # the kernel reads the state rows in 32-byte pieces (a view at an odd element offset of a larger buffer)
+        h0 = h0.clone()
+    if c0.data_ptr() % 32:
+        c0 = c0.clone()
+    code = _lib.lib().sw_decode_fwd_pair(w16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(h0), _lib.ptr(c0),
                                          _lib.ptr(None if pooled is None else _f32(pooled)), _lib.ptr(noise),
                                          _lib.ptr(_f32(x_last)), _lib.ptr(out), scratch.data_ptr(), scratch.numel(),
                                          None if status is None else status.data_ptr(), n, k, n_next,
