@@ -247,17 +247,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 }
                 __syncwarp();
             };
-            // agent of the first row of each slot's tile, carried from tile to tile (the tiles of a slot advance by 4 n_pairs tiles): one
-        // 64-bit modulo per kernel; rows inside a tile wrap with a compare (the prologue spent ~3 K clk per tile pair in `%`)
-        int abase[2];
-#pragma unroll
-        for (int sl = 0; sl < 2; ++sl) abase[sl] = (int)(((long long)(2 * (2 * pair + sl) + (int)cta) * P_ROWS) % n_agents);
-        const int astep = (int)(((long long)4 * n_pairs * P_ROWS) % n_agents);
-        auto wrap = [&](int v) {            // v < n_agents + 128: one round unless the batch has fewer than 128 agents
-            while (v >= n_agents) v -= n_agents;
-            return v;
-        };
-        for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
+            for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
                 // (both slots always run: the slot of a unit or tile beyond the batch works on zero rows -- at most one tile per
                 //  pair at the very end -- which keeps every "is the slot active" test out of the step loops)
 #pragma unroll 1
@@ -326,6 +316,28 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             while (v >= n_agents) v -= n_agents;
             return v;
         };
+        // cell state of this thread's units: c[sl][0..7] = units 8 cq .. (gates half 0), c[sl][8..15] = units 32 + 8 cq .. (half 1).
+        // The rows of a tile pair are requested during the LAST step of the pair before it (after the final cell update the
+        // registers are dead; the loads land under the remaining layer-1 / layer-2 phases instead of in the next prologue, whose
+        // ~190 KB of row loads are bound by the L2 -> SM bandwidth); abase[] must already refer to the tiles being loaded.
+        float c[2][16];
+        auto load_c0 = [&](int ubx) {
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                const int tile = 2 * (ubx + sl) + (int)cta;
+                const long long left = n_rows - (long long)tile * P_ROWS;
+                const bool ok = tile < n_tiles && r < left;
+                const float* src = c0 + (size_t)wrap(abase[sl] + r) * SW_H + cq * 8;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {                    // units 8 cq .. and 32 + 8 cq ..: 32 contiguous bytes each
+                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+                    if (ok) ldg256(src + half * 32, a, b);
+                    c[sl][8 * half] = a.x; c[sl][8 * half + 1] = a.y; c[sl][8 * half + 2] = a.z; c[sl][8 * half + 3] = a.w;
+                    c[sl][8 * half + 4] = b.x; c[sl][8 * half + 5] = b.y; c[sl][8 * half + 6] = b.z; c[sl][8 * half + 7] = b.w;
+                }
+            }
+        };
+        load_c0(2 * pair);
         for (int ub = 2 * pair; ub < n_units; ub += 2 * n_pairs) {
 #ifdef SW_PAIR_TRACE
             const bool tr_on = blockIdx.x == 0 && etid == 0 && ub == 2 * pair + 2 * (2 * n_pairs);
@@ -336,9 +348,6 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
             int rows_here[2], agent[2];     // rows of the tile inside the batch (0: no tile, < 128: last tile)
             float2 xl = make_float2(0.f, 0.f);
             float* out_row = out;           // where this thread emits (the rows of the slot it finishes; one slot at most)
-            // cell state of this thread's units: c[sl][0..7] = units 8 cq .. (gates half 0), c[sl][8..15] = units 32 + 8 cq .. (half 1);
-            // loaded FIRST: the registers are dead until the first cell update anyway, and the loads share the latency of the others
-            float c[2][16];
             // ---------------- tile prologue, both slots: every global load coalesced and issued up front ----------------
 #pragma unroll
             for (int sl = 0; sl < 2; ++sl) {
@@ -349,13 +358,6 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 valid[sl] = r < rows_here[sl];
                 agent[sl] = valid[sl] ? wrap(abase[sl] + r) : 0;
                 SW_TR(49 + 4 * sl);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {                    // units 8 cq .. and 32 + 8 cq ..: 32 contiguous bytes each
-                    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-                    if (valid[sl]) ldg256(c0 + (size_t)agent[sl] * SW_H + half * 32 + cq * 8, a, b);
-                    c[sl][8 * half] = a.x; c[sl][8 * half + 1] = a.y; c[sl][8 * half + 2] = a.z; c[sl][8 * half + 3] = a.w;
-                    c[sl][8 * half + 4] = b.x; c[sl][8 * half + 5] = b.y; c[sl][8 * half + 6] = b.z; c[sl][8 * half + 7] = b.w;
-                }
                 SW_TR(50 + 4 * sl);
                 {   // S tile [128 rows][16 pieces] -> the slot's (still unused) h operand region, piece' = piece ^ (row & 7), by cp.async:
                     // global -> shared without a register in between.  (Through registers the 8 loaded float4 of both slots did not
@@ -585,6 +587,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 SW_TR(25 + (t < 2 ? 0 : t == n_next - 1 ? 16 : 8));
                 if (t > 0) phase_cell(S1{});
                 c1_prefetch(S1{});
+                if (!feed_back) load_c0(ub + 2 * n_pairs);               // (the cell updates of this tile pair are done)
                 SW_TR(26 + (t < 2 ? 0 : t == n_next - 1 ? 16 : 8));
                 phase_l2(S0{}, t, feed_back);
                 SW_TR(27 + (t < 2 ? 0 : t == n_next - 1 ? 16 : 8));
