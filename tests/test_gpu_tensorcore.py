@@ -209,6 +209,34 @@ def test_pair_decode_tile_and_unit_edge_cases(rows, k, n_next):
     assert int(status.item()) == 0
 
 
+def test_pair_decode_state_rows_at_odd_offsets_and_few_agents():
+    """The pair kernel reads h0 / c0 in 32-byte row pieces (LDG.256) and carries the agent index of a tile instead of taking a
+    modulo per row: state tensors that start 16 bytes into a buffer (the wrapper realigns them; the C entry point refuses them),
+    and batches of fewer agents than a tile has rows (every tile wraps around the agent table several times)."""
+    import socialways_b200 as sw
+    from socialways_b200 import _lib, ops
+    torch.manual_seed(3)
+    gen = sw.Generator(use_social=True).cuda().requires_grad_(False)
+    pk = gen.packs()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    for n, k in ((5, 60), (127, 9), (1, 300), (200, 3)):
+        buf = torch.randn(3, n * 64 + 4, device="cuda", generator=g) * 0.3
+        h, c, pooled = (buf[i, 4:].view(n, 64) for i in range(3))       # 16-byte aligned, not 32
+        assert h.data_ptr() % 32 == 16
+        x_last = torch.randn(n, 4, device="cuda", generator=g) * 0.1
+        noise = torch.rand(k, n, 32, device="cuda", generator=g)
+        want = ops.decode(pk["enc"], pk["dec"], h.contiguous(), c.contiguous(), pooled.contiguous(), noise, x_last, 12)
+        got = ops.decode_pair(*pk["pair"], h, c, pooled, noise, x_last, 12)
+        assert (got - want).abs().max().item() < 2e-5
+    out = torch.empty(k, n, 12, 4, device="cuda")
+    scratch = ops.decode_pair_scratch(out.device)
+    w16, f32 = pk["pair"]
+    code = _lib.lib().sw_decode_fwd_pair(w16.data_ptr(), f32.data_ptr(), h.data_ptr(), c.contiguous().data_ptr(), pooled.data_ptr(),
+                                         noise.data_ptr(), x_last.data_ptr(), out.data_ptr(), scratch.data_ptr(), scratch.numel(),
+                                         None, n, k, 12, ops.sm_count(out.device), None)
+    assert code != 0                                                   # SW_ERR_ARG: h0 not 32-byte aligned
+
+
 @pytest.mark.parametrize("prec", SPLIT_KERNELS)
 @pytest.mark.parametrize("case", ["train_toy_216.npz", "train_ragged.npz"])
 def test_fp16x2_on_trained_weights(case, prec):
