@@ -51,19 +51,20 @@ FLOPS_PER_TRAJ_EXECUTED = 12 * 2 * (64 * 160 + 160 * 80 + 80 * 2) + 11 * 2 * 68 
 # trajectories of that launch (655 360): profiles/r2_decode_pair.txt, r1_decode_tcx.txt, r1_decode_fp32_ffma.txt.
 # Algorithmic: 128 B noise in + 192 B (p, v) x 12 out = 320 B per trajectory.
 NCU_DRAM_BYTES_PER_TRAJ = {"fp16x2": (152.396544e6 + 120.195072e6) / 655360, "fp16x2s": (115.264768e6 + 92.413184e6) / 655360,
-                           "fp32": (114.652672e6 + 91.719424e6) / 655360, "bf16": None}
+                           "fp32": (114.652672e6 + 91.719424e6) / 655360, "bf16": None, "bf16p": None}
 
 
 KERNEL_OF = {"fp32": "decode_fwd_kernel", "fp16x2": "decode_fwd_pair_kernel", "fp16x2s": "decode_fwd_tcx_kernel",
-             "bf16": "decode_fwd_tc_kernel"}
+             "bf16": "decode_fwd_tc_kernel", "bf16p": "decode_fwd_pair_bf16_kernel"}
 DTYPE_OF = {"fp32": "f32", "fp16x2": "f32 (fp16 hi/lo split operands on tcgen05, fp32 accumulate)",
-            "fp16x2s": "f32 (fp16 hi/lo split operands on tcgen05, fp32 accumulate)", "bf16": "bf16"}
+            "fp16x2s": "f32 (fp16 hi/lo split operands on tcgen05, fp32 accumulate)", "bf16": "bf16", "bf16p": "bf16"}
 NOTE_OF = {"fp32": "fp32 FFMA path; CUDA-core fp32 peak is ~74 TFLOP/s",
            "fp16x2": "tcgen05: 3 MMAs per product on fp16 hi/lo split operands, fp32 accumulate in TMEM; matches the fp32 "
                      "oracle to ~1e-6 (tests/test_gpu_tensorcore.py), i.e. inside the 1e-4 ADE/FDE parity bar; executed "
                      "tensor FLOPs are 3x the algorithmic ones",
            "fp16x2s": "the same arithmetic as fp16x2 on the one-tile-per-SM kernel (decode_fwd_tcx.cu)",
-           "bf16": "tcgen05 bf16 operands / fp32 accumulate in TMEM (fast mode, outside the 1e-4 parity bar)"}
+           "bf16": "tcgen05 bf16 operands / fp32 accumulate in TMEM (fast mode, outside the 1e-4 parity bar)",
+           "bf16p": "the CTA-pair kernel on single bf16 operands (one MMA per product; fast mode, outside the 1e-4 parity bar)"}
 
 
 def make_scenes(n_scenes, seed):
@@ -398,7 +399,7 @@ def run_ours(args):
         if timed and headline:
             s0, s1, s2, s3 = ev(), ev(), ev(), ev()
             s0.record()
-        split = precision in ("fp16x2", "fp16x2s")
+        split = precision in ("fp16x2", "fp16x2s", "bf16p")
         if split:
             enc = ops.lstm_seq_tcx(*pk["enc_tcx"], obsv_d)
         else:
@@ -424,6 +425,8 @@ def run_ours(args):
             ops.decode_pair(*pk["pair"], enc["h"], enc["c"], pooled, noise_d, enc["x_last"], N_NEXT, out=out)
         elif precision == "fp16x2s":
             ops.decode_tcx(*pk["tcx"], enc["h"], enc["c"], pooled, noise_d, enc["x_last"], N_NEXT, out=out)
+        elif precision == "bf16p":
+            ops.decode_pair(*pk["pair_bf16"], enc["h"], enc["c"], pooled, noise_d, enc["x_last"], N_NEXT, out=out, bf16=True)
         else:
             ops.decode(pk["enc"], pk["dec"], enc["h"], enc["c"], pooled, noise_d, enc["x_last"], N_NEXT, out=out)
         if timed:
@@ -458,7 +461,7 @@ def run_ours(args):
     # ---------------- the other decode kernels, same inputs, reported beside the headline ----------------
     ref_out = out.clone()
     others = {}
-    for other in [p for p in ("fp32", "fp16x2", "fp16x2s", "bf16") if p != args.precision]:
+    for other in [p for p in ("fp32", "fp16x2", "fp16x2s", "bf16", "bf16p") if p != args.precision]:
         other_events = []
         for _ in range(args.warmup):
             step_resident(False, other)
@@ -584,13 +587,13 @@ def run_ours(args):
             # the other kernels of the step, live CUDA-event times (north_star asks for the pairwise kernel's HBM figure;
             # it is compute-bound -- SURVEY.md D9 -- so the fraction is small by construction)
             "secondary_kernels": {
-                "pool_fwd_tcx_kernel" if args.precision in ("fp16x2", "fp16x2s") and A_PER_SCENE <= ops.pool_tcx_max_scene() else "pool_fwd_kernel": {
+                "pool_fwd_tcx_kernel" if args.precision in ("fp16x2", "fp16x2s", "bf16p") and A_PER_SCENE <= ops.pool_tcx_max_scene() else "pool_fwd_kernel": {
                                     "kernel_ms": pool_ms, "bound": "hbm (as asked; actually compute-bound)",
                                     "algorithmic_bytes": n * 788, "achieved_gbs": n * 788 / (pool_ms * 1e-3) / 1e9,
                                     "peak_gbs": pk_["hbm_gbs"], "frac_of_hbm": n * 788 / (pool_ms * 1e-3) / 1e9 / pk_["hbm_gbs"],
                                     "achieved_tflops_fp32": n * A_PER_SCENE * 4544 / (pool_ms * 1e-3) / 1e12,
                                     "note": "788 B/agent = x_last 16 + h 256 + (u|beta) 260 read, S 256 written"},
-                "encoder": {"kernel": "lstm_seq_fwd_tcx_kernel" if args.precision in ("fp16x2", "fp16x2s") else "lstm_seq_fwd_kernel",
+                "encoder": {"kernel": "lstm_seq_fwd_tcx_kernel" if args.precision in ("fp16x2", "fp16x2s", "bf16p") else "lstm_seq_fwd_kernel",
                             "kernel_ms": enc_ms,
                             "achieved_tflops": n * 528384 / (enc_ms * 1e-3) / 1e12,
                             "frac_of_tensor_peak": n * 528384 / (enc_ms * 1e-3) / 1e12 / peak}},
@@ -630,9 +633,9 @@ def main():
     ap.add_argument("--train-n", type=int, default=65536 // 6 * 6, help="trajectories of the scaled toy set (configs[3])")
     ap.add_argument("--train-batches", default="4096,49152", help="global mini-batch sizes of the train_step block")
     ap.add_argument("--train-epochs", type=int, default=3, help="timed epochs per batch size")
-    ap.add_argument("--precision", default="fp16x2", choices=["fp32", "fp16x2", "fp16x2s", "bf16"],
+    ap.add_argument("--precision", default="fp16x2", choices=["fp32", "fp16x2", "fp16x2s", "bf16", "bf16p"],
                     help="decode kernel of the headline line: fp16x2 = tcgen05 on fp16 hi/lo split operands "
-                         "(fp32-faithful, default), fp32 = CUDA-core FFMA, bf16 = tcgen05 on bf16 operands (fast mode)")
+                         "(fp32-faithful, default), fp32 = CUDA-core FFMA, bf16 = tcgen05 on bf16 operands (fast mode, one tile per SM), bf16p = the CTA-pair kernel on bf16 operands")
     ap.add_argument("--agents-per-scene", type=int, default=8,
                     help="8 = BASELINE configs[1] (ETH-shaped, the headline); 32 = Zara-shaped; 256 with --k 128 = the dense-crowd "
                          "stress of configs[4] (give --scenes so that scenes x agents x K fits the GPU)")

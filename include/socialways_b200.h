@@ -171,6 +171,14 @@ int sw_decode_fwd_pair(const void* pair_w16, const float* pair_f32, const float*
                        const float* noise, const float* x_last, float* out, void* scratch, long long scratch_bytes,
                        int* status, int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 int sw_decode_pair_pack_sizes(int* n_w16, int* n_f32);
+
+/* The bf16 build of the same kernel (csrc/decode_fwd_pair_bf16.cu): single bf16 operands, ONE tcgen05.mma per product instead of
+ * the three of the hi/lo split (the x-feedback block keeps hi + lo).  Fast mode (BASELINE configs[2] names bf16): ~3e-3 from the
+ * fp32 path in normalised coordinates, not inside the 1e-4 parity bar.  Same arguments; pack from
+ * packing.pack_decoder_pair(..., bf16=True) (same sizes and layout, bf16 bit patterns). */
+int sw_decode_fwd_pair_bf16(const void* pair_w16, const float* pair_f32, const float* h0, const float* c0, const float* pooled,
+                            const float* noise, const float* x_last, float* out, void* scratch, long long scratch_bytes,
+                            int* status, int n_agents, int n_samples, int n_next, int sm_count, void* stream);
 long long sw_decode_pair_scratch_bytes(int sm_count);
 
 /* Discriminator FC heads (train.py:281-292, 300-309), one thread per trajectory, all 8 Linear layers fused.

@@ -36,6 +36,7 @@ _PROTOTYPES = {
     "sw_decode_fwd_tcx": (_I, [_P] * 10 + [_I, _I, _I, _I, _P]),
     "sw_decode_tcx_pack_sizes": (_I, [_P, _P, _P]),
     "sw_decode_fwd_pair": (_I, [_P] * 9 + [ctypes.c_longlong, _P, _I, _I, _I, _I, _P]),
+    "sw_decode_fwd_pair_bf16": (_I, [_P] * 9 + [ctypes.c_longlong, _P, _I, _I, _I, _I, _P]),
     "sw_decode_pair_pack_sizes": (_I, [_P, _P]),
     "sw_decode_pair_scratch_bytes": (ctypes.c_longlong, [_I]),
     "sw_disc_heads_pack_floats": (_I, [_I, _I]),

@@ -33,6 +33,14 @@
 
 #include "decode_pair.cuh"
 
+#if SW_PAIR_BF16        // the bf16 build of this file (decode_fwd_pair_bf16.cu): own kernel and entry point, shared host helpers
+#define PAIR_KERNEL decode_fwd_pair_bf16_kernel
+#define PAIR_ENTRY sw_decode_fwd_pair_bf16
+#else
+#define PAIR_KERNEL decode_fwd_pair_kernel
+#define PAIR_ENTRY sw_decode_fwd_pair
+#endif
+
 namespace sw {
 
 #ifdef SW_PAIR_TRACE      // timeline of one tile pair (scripts/pair_trace.py): clock64 of thread 0 of CTA 0 at the marked points
@@ -113,7 +121,11 @@ __device__ __forceinline__ void l1_epilogue(uint32_t t_acc, const float4* sc, un
             psplit2(lrelu02(y0), lrelu02(y1), pc[2 * q], pc[8 + 2 * q]);
             psplit2(lrelu02(y2), lrelu02(y3), pc[2 * q + 1], pc[8 + 2 * q + 1]);
         }
+#if SW_PAIR_BF16
+        tmem_st<8>(t_acc + kb * 16, pc);                  // hi only
+#else
         tmem_st<16>(t_acc + kb * 16, pc);
+#endif
     }
     ptx::tcgen05_wait_st();
 }
@@ -138,7 +150,7 @@ __device__ __forceinline__ void c1_to_scratch(uint32_t t_acc, float4* sc, const 
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Q_THREADS, 1)
-decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][32] fp32, box 128 x 32, 128-byte swizzle */,
+PAIR_KERNEL(const __grid_constant__ CUtensorMap noise_map /* [n_rows][32] fp32, box 128 x 32, 128-byte swizzle */,
                        const __half* __restrict__ w16 /* [2 ranks][PW_TOTAL] */, const float* __restrict__ wf32,
                        const float* __restrict__ h0, const float* __restrict__ c0, const float* __restrict__ pooled,
                        const float* __restrict__ x_last, float* __restrict__ out, float4* __restrict__ scratch,
@@ -421,7 +433,9 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                 }
                 const uint32_t tls = tl + (uint32_t)(sl * 256);
                 tmem_st<12>(tls + PC_AHI + cq * 12, hi);
+#if !SW_PAIR_BF16
                 tmem_st<12>(tls + PC_ALO + cq * 12, lo);
+#endif
                 ptx::tcgen05_wait_st();
                 SW_TR(6 + 8 * sl);
                 epi_sync();                                               // staging consumed: h region and noise buffer are free
@@ -439,7 +453,9 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                     psplit2(hreg[sl][i][1].z, hreg[sl][i][1].w, hh[3], ll[3]);
                     const size_t off = ((size_t)((lane >> 3) + 4 * i) * P_ROWS + hrow) * 8;
                     *reinterpret_cast<uint4*>(s.h[sl][0] + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+#if !SW_PAIR_BF16
                     *reinterpret_cast<uint4*>(s.h[sl][1] + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+#endif
                 }
                 ptx::fence_proxy_async(ptx::space_shared);
                 arrive(&s.ready[sl]);                                     // -> hoist MMAs of the slot
@@ -534,7 +550,7 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                         psplit2(p0, p1, hp, lp);
                         psplit2(v0, v1, hv, lv);
                         *reinterpret_cast<uint4*>(s.xk[sl] + (size_t)r * 8) = make_uint4(hp, hv, lp, lv);                      // k 0..7
-                        *reinterpret_cast<uint4*>(s.xk[sl] + (size_t)(P_ROWS + r) * 8) = make_uint4(hp, hv, 0x3C003C00u, 0u);  // k 8..15
+                        *reinterpret_cast<uint4*>(s.xk[sl] + (size_t)(P_ROWS + r) * 8) = make_uint4(hp, hv, P_ONE2, 0u);  // k 8..15
                         ptx::fence_proxy_async(ptx::space_shared);
                         arrive(&s.ready_x[sl]);                           // -> x blocks of the gates, h part of half 1
                     }
@@ -569,7 +585,9 @@ decode_fwd_pair_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows]
                     if (half == 0) wait_full3(&s.full[sl][2], (ph >> (2 + sl)) & 1u);
                     const size_t off = ((size_t)(half * 4 + cq) * P_ROWS + r) * 8;
                     *reinterpret_cast<uint4*>(s.h[sl][0] + off) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+#if !SW_PAIR_BF16
                     *reinterpret_cast<uint4*>(s.h[sl][1] + off) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+#endif
                 }
                 ph ^= 4u << sl;
                 ptx::fence_proxy_async(ptx::space_shared);
@@ -621,6 +639,7 @@ static int pair_grid(long long tiles, int sm_count) {
     return (int)(2 * pairs);
 }
 
+#if !SW_PAIR_BF16
 #ifdef SW_PAIR_TRACE
 extern "C" int sw_pair_trace_read(long long* out64) {
     SW_CUDA_TRY(cudaMemcpyFromSymbol(out64, sw::g_pair_trace, sizeof(long long) * 64));
@@ -640,7 +659,11 @@ extern "C" int sw_decode_pair_pack_sizes(int* n_w16, int* n_f32) {
     return SW_OK;
 }
 
-extern "C" int sw_decode_fwd_pair(const void* pair_w16, const float* pair_f32, const float* h0, const float* c0,
+#else
+extern "C" long long sw_decode_pair_scratch_bytes(int sm_count);
+#endif
+
+extern "C" int PAIR_ENTRY(const void* pair_w16, const float* pair_f32, const float* h0, const float* c0,
                                   const float* pooled, const float* noise, const float* x_last, float* out, void* scratch,
                                   long long scratch_bytes, int* status, int n_agents, int n_samples, int n_next, int sm_count,
                                   void* stream) {
@@ -656,9 +679,9 @@ extern "C" int sw_decode_fwd_pair(const void* pair_w16, const float* pair_f32, c
     const int rc = encode_noise_map2(&noise_map, noise, n_rows);
     if (rc != SW_OK) return rc;
     const int smem = (int)sizeof(sw::PairSmem);
-    SW_SET_MAX_SMEM(sw::decode_fwd_pair_kernel, smem);
+    SW_SET_MAX_SMEM(sw::PAIR_KERNEL, smem);
     const int grid = pair_grid(tiles, sm_count);
-    sw::decode_fwd_pair_kernel<<<grid, sw::Q_THREADS, smem, (cudaStream_t)stream>>>(
+    sw::PAIR_KERNEL<<<grid, sw::Q_THREADS, smem, (cudaStream_t)stream>>>(
         noise_map, (const __half*)pair_w16, pair_f32, h0, c0, pooled, x_last, out, (float4*)scratch, status, n_agents, n_rows, n_next,
         (int)tiles);
     SW_CUDA_TRY(cudaGetLastError());

@@ -3,6 +3,7 @@
 // pair MMAs, and the host-side tensor map of the noise tensor.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
 #define SW_RCP_NEWTON 1      // one of the three reciprocals per unit pair on the FMA pipe (sw_umma.cuh: rcp_newton)
@@ -22,10 +23,26 @@ constexpr int PW_W1H_HI = 0, PW_W1H_LO = 5120,                                  
               PW_TOTAL = PW_WSZ_LO + 7680;
 constexpr int PF_B1 = 0, PF_B2 = 160, PF_B34 = 240, PF_W34 = 256, PF_TOTAL = 256 + 160;
 constexpr uint32_t PC_R1 = 0, PC_R2 = 160, PC_AHI = 160, PC_ALO = 208;
-constexpr uint32_t PFMT = 0;          // fp16
+// SW_PAIR_BF16 = 1 (csrc/decode_fwd_pair_bf16.cu): the same kernel on single bf16 operands -- ONE MMA per product instead of the
+// three of the fp16 hi/lo split, no lo operand parts except in the x-feedback block (positions keep hi + lo).  The "fast mode"
+// BASELINE configs[2] names; ~3e-3 from the fp32 path instead of ~1e-6.
+#ifndef SW_PAIR_BF16
+#define SW_PAIR_BF16 0
+#endif
+constexpr uint32_t PFMT = SW_PAIR_BF16 ? 1 : 0;            // operand format of the instruction descriptor: fp16 / bf16
+constexpr uint32_t P_ONE2 = SW_PAIR_BF16 ? 0x3F803F80u : 0x3C003C00u;   // (1, 1) in the operand format
 // c1 scratch: [cta][slot][10 K blocks][4][128 rows] float4
 constexpr int P_SCRATCH_F4_PER_SLOT = 10 * 4 * P_ROWS;
 
+#if SW_PAIR_BF16
+__device__ __forceinline__ void psplit2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    const float2 back = __bfloat1622float2(h2);
+    const __nv_bfloat162 l2 = __floats2bfloat162_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);        // (dead code wherever the lo part is not stored)
+}
+#else
 __device__ __forceinline__ void psplit2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h2 = __floats2half2_rn(a, b);
     const float2 back = __half22float2(h2);
@@ -33,18 +50,23 @@ __device__ __forceinline__ void psplit2(float a, float b, uint32_t& hi, uint32_t
     hi = *reinterpret_cast<const uint32_t*>(&h2);
     lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
+#endif
 // single-thread forms (inside `if (elect_one())`)
 template <int NL, int KB>
 __device__ __forceinline__ void pmma3_ss1(uint32_t d, const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo) {
     pmma1_ss<NL, KB>(d, a_hi, b_hi, PFMT, false);
+#if !SW_PAIR_BF16
     pmma1_ss<NL, KB>(d, a_hi, b_lo, PFMT, true);
     pmma1_ss<NL, KB>(d, a_lo, b_hi, PFMT, true);
+#endif
 }
 template <int NL, int KB, int A_STRIDE>
 __device__ __forceinline__ void pmma3_ts1(uint32_t d, uint32_t a_hi, uint32_t a_lo, const __half* b_hi, const __half* b_lo) {
     pmma1_ts<NL, KB, A_STRIDE>(d, a_hi, b_hi, PFMT, false);
+#if !SW_PAIR_BF16
     pmma1_ts<NL, KB, A_STRIDE>(d, a_hi, b_lo, PFMT, true);
     pmma1_ts<NL, KB, A_STRIDE>(d, a_lo, b_hi, PFMT, true);
+#endif
 }
 
 }  // namespace sw

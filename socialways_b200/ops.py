@@ -312,10 +312,11 @@ def decode_pair_scratch(device):
     return _PAIR_SCRATCH[key]
 
 
-def decode_pair(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, status=None, scratch=None):
+def decode_pair(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, status=None, scratch=None, bf16=False):
     """sw_decode_fwd_pair: the fp16 hi/lo split tcgen05 decode kernel with two tiles in flight per SM (CTA pairs, cta_group::2,
     epilogue warps in ping-pong over two tile slots, dedicated issuing warp); same inputs, outputs and arithmetic as decode_tcx.
-    Packs from packing.pack_decoder_pair."""
+    Packs from packing.pack_decoder_pair.  bf16=True: sw_decode_fwd_pair_bf16, the same kernel on single bf16 operands (fast mode,
+    ~3e-3; pack with pack_decoder_pair(..., bf16=True))."""
     noise = _f32(noise)
     k, n, z = noise.shape
     if z != Z or h0.shape != (n, H):
@@ -333,12 +334,13 @@ def decode_pair(w16, f32, h0, c0, pooled, noise, x_last, n_next, out=None, statu
         h0 = h0.clone()
     if c0.data_ptr() % 32:
         c0 = c0.clone()
-    code = _lib.lib().sw_decode_fwd_pair(w16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(h0), _lib.ptr(c0),
-                                         _lib.ptr(None if pooled is None else _f32(pooled)), _lib.ptr(noise),
-                                         _lib.ptr(_f32(x_last)), _lib.ptr(out), scratch.data_ptr(), scratch.numel(),
-                                         None if status is None else status.data_ptr(), n, k, n_next,
-                                         sm_count(noise.device), _stream())
-    _lib.check(code, "sw_decode_fwd_pair")
+    entry = _lib.lib().sw_decode_fwd_pair_bf16 if bf16 else _lib.lib().sw_decode_fwd_pair
+    code = entry(w16.data_ptr(), _lib.ptr(_f32(f32)), _lib.ptr(h0), _lib.ptr(c0),
+                 _lib.ptr(None if pooled is None else _f32(pooled)), _lib.ptr(noise),
+                 _lib.ptr(_f32(x_last)), _lib.ptr(out), scratch.data_ptr(), scratch.numel(),
+                 None if status is None else status.data_ptr(), n, k, n_next,
+                 sm_count(noise.device), _stream())
+    _lib.check(code, "sw_decode_fwd_pair_bf16" if bf16 else "sw_decode_fwd_pair")
     return out
 
 

@@ -81,6 +81,14 @@ def _split_f16(w):
     return hi, lo
 
 
+def _split_bf16_bits(w):
+    """hi / lo split in bf16, returned as the BIT PATTERNS in fp16-typed tensors (the packs are typed fp16; the bf16 kernels read
+    the same 16-bit lanes with the bf16 operand format)."""
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi.view(torch.float16), lo.view(torch.float16)
+
+
 LOG2E = 1.4426950408889634
 
 
@@ -131,7 +139,7 @@ def pack_decoder_tcx(lstm_pack, dec_pack):
     return w16, wsz16, f32
 
 
-def pack_decoder_pair(lstm_pack, dec_pack):
+def pack_decoder_pair(lstm_pack, dec_pack, bf16=False):
     """Operands of the CTA-pair decode kernel (csrc/decode_fwd_pair.cu, tcgen05 cta_group::2): the same hi/lo split matrices
     as `pack_decoder_tcx`, but every B matrix [N][K] is cut into the two N halves the two CTAs of a pair supply (rank 0: rows
     [0, N/2), rank 1: [N/2, N)), each canonical K-major.
@@ -140,7 +148,10 @@ def pack_decoder_pair(lstm_pack, dec_pack):
          them) hi | lo [8][64][8]; the x-feedback K block per gate half [2][64][8] (k 0..3 Wx_hi, 4..7 Wx_hi, 8..11 Wx_lo,
          12 b_hi, 13 b_lo, 14..15 zero); the hoisted rows of W1 (S: k 0..63, z: 64..95) hi | lo [12][80][8] -- resident in the
          pair kernel.  Gate rows carry the ex2 prescale.
-    f32  [416]: b1 [160] | b2 [80] | b34 [2] | pad | W34 [80 k][2]  (as pack_decoder_tcx)"""
+    f32  [416]: b1 [160] | b2 [80] | b34 [2] | pad | W34 [80 k][2]  (as pack_decoder_tcx)
+    bf16=True: the same image with bf16 bit patterns, for sw_decode_fwd_pair_bf16 (which reads the hi parts only, except in the
+    x-feedback block)."""
+    _split_f16 = _split_bf16_bits if bf16 else globals()["_split_f16"]
     w1 = dec_pack[:25600].view(160, 160).t()                  # [n, k], k order {h, S, z}
     b1 = dec_pack[25600:25760]
     w2 = dec_pack[25760:38560].view(160, 80).t()

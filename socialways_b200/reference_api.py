@@ -280,6 +280,7 @@ class Generator(nn.Module):
                 packs["tc_w16"], packs["tc_f32"] = packing.pack_decoder_tc(packs["enc"], packs["dec"])
                 packs["tcx"] = packing.pack_decoder_tcx(packs["enc"], packs["dec"])
                 packs["pair"] = packing.pack_decoder_pair(packs["enc"], packs["dec"])
+                packs["pair_bf16"] = packing.pack_decoder_pair(packs["enc"], packs["dec"], bf16=True)
                 packs["enc_tcx"] = packing.pack_encoder_tcx(packs["enc"])
                 packs["pool_tcx"] = packing.pack_pool_tcx(fe[2].weight)
                 # weights beyond fp16's range (|w| > 65 504 -> inf in the hi part) poison the split: raise the status word now
@@ -327,7 +328,8 @@ class Generator(nn.Module):
         """K-sample predict(): noise [K,N,32] -> [K,N,n_next,4].  The observation encoding and the
         pooled social vector do not depend on the sample and are computed once.
         precision: "fp32" = FFMA decode kernel; "fp16x2" = tcgen05 kernel on fp16 hi/lo split operands
-        (fp32-faithful, ~1e-6); "bf16" = tcgen05 kernel on bf16 operands (fast mode, ~2e-3).
+        (fp32-faithful, ~1e-6); "bf16" / "bf16p" = tcgen05 kernels on bf16 operands (fast modes, ~3e-3; "bf16p" = the
+        CTA-pair kernel of "fp16x2" with one MMA per product).
         noise=None, seed=s, k=K: the K x N x 32 latent noise is drawn ON THE DEVICE (Philox4x32-10, sw_noise_uniform) instead
         of being supplied by the caller -- same distribution as the reference's torch.rand (train.py:584), a different
         stream, and no 128 B / trajectory upload; `seed` may be an int or (seed, offset)."""
@@ -343,8 +345,10 @@ class Generator(nn.Module):
             noise = ops.noise_uniform((k, n, self.noise_len), obsv_p.device, sd, off, out=noise_buf)
         # "fp16x2" decodes with two tiles in flight per SM (CTA pairs, csrc/decode_fwd_pair.cu); "fp16x2s" = the same arithmetic
         # on the one-tile-per-SM kernel (csrc/decode_fwd_tcx.cu)
-        single = precision == "fp16x2s"
-        if single:
+        # "bf16p" = the CTA-pair kernel on single bf16 operands (encoder and pooling as in "fp16x2"); "bf16" = the older one-tile
+        # bf16 kernel with the FFMA encoder / pooling
+        single, pair_bf16 = precision == "fp16x2s", precision == "bf16p"
+        if single or pair_bf16:
             precision = "fp16x2"
         if precision == "fp16x2":           # both recurrent kernels on the tensor cores (fp16 hi/lo split operands)
             enc = ops.lstm_seq_tcx(*pk["enc_tcx"], obsv_p)
@@ -363,11 +367,13 @@ class Generator(nn.Module):
         if single:
             return ops.decode_tcx(*pk["tcx"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out,
                                   status=self._status_word(obsv_p.device))
+        if pair_bf16:
+            return ops.decode_pair(*pk["pair_bf16"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out, bf16=True)
         if precision == "fp16x2":
             return ops.decode_pair(*pk["pair"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out,
                                    status=self._status_word(obsv_p.device))
         if precision != "fp32":
-            raise ValueError("precision must be 'fp32', 'fp16x2', 'fp16x2s' or 'bf16'")
+            raise ValueError("precision must be 'fp32', 'fp16x2', 'fp16x2s', 'bf16' or 'bf16p'")
         return ops.decode(pk["enc"], pk["dec"], enc["h"], enc["c"], pooled, noise, enc["x_last"], n_next, out=out)
 
     def predict(self, obsv_p, noise, n_next, sub_batches=()):

@@ -78,6 +78,36 @@ def test_tc_decode_vs_bf16_emulation_and_oracle(sizes, k):
     assert ((got[..., :2] - prev) - got[..., 2:]).abs().max().item() < 1e-6
 
 
+@pytest.mark.parametrize("sizes,k", [([8] * 16, 1), ([5, 1, 32, 2, 9], 3), ([8] * 40, 7), ([6] * 36, 2)])
+def test_pair_bf16_fast_mode_vs_oracle_and_older_bf16_kernel(sizes, k):
+    """precision="bf16p": the CTA-pair kernel on single bf16 operands (csrc/decode_fwd_pair_bf16.cu).  Fast mode: the documented
+    accuracy cost against the fp32 oracle (the same bound as the older bf16 kernel), agreement with that kernel to bf16
+    rounding-boundary effects, exact fp32 integration p_t = p_{t-1} + v_t."""
+    import socialways_b200 as sw
+    from oracle import socialways_oracle as so
+    P = so.init_weights(seed=6)
+    data = synthetic_scenes(sizes, seed=13)
+    sc = so.IsoScale(data["obsvs"], data["preds"])
+    obsv = torch.from_numpy(sc.normalize(data["obsvs"]))
+    n = obsv.shape[0]
+    torch.manual_seed(4)
+    noise = torch.rand(k, n, 32)
+    gen = sw.Generator(use_social=True)
+    gen.load_state_dict({key: v for key, v in P.items() if not key.startswith("D.")})
+    gen = gen.cuda().requires_grad_(False)
+    got = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision="bf16p").cpu()
+    old = gen.predict_k(obsv.cuda(), noise.cuda(), 12, data["batches"], precision="bf16").cpu()
+    assert got.shape == (k, n, 12, 4) and torch.isfinite(got).all()
+    fp32 = torch.stack([so.predict(P, obsv, noise[i], 12, data["batches"], True, "closed") for i in range(k)])
+    err_fp32, err_old = (got - fp32).abs().max().item(), (got - old).abs().max().item()
+    print(f"bf16 pair decode: max |gpu - fp32 oracle| = {err_fp32:.2e}, max |gpu - one-tile bf16 kernel| = {err_old:.2e}")
+    assert err_fp32 < 1e-2, err_fp32        # observed 1.3e-3 .. 1.9e-3
+    assert err_old < 1e-2, err_old
+    last = obsv[:, -1].unsqueeze(0).unsqueeze(2).expand(k, -1, 1, -1)
+    prev = torch.cat([last, got[:, :, :-1, :2]], 2)
+    assert ((got[..., :2] - prev) - got[..., 2:]).abs().max().item() < 1e-6
+
+
 SPLIT_KERNELS = ["fp16x2", "fp16x2s"]     # CTA-pair kernel (decode_fwd_pair.cu, the default) and one-tile-per-SM kernel (decode_fwd_tcx.cu)
 
 
