@@ -23,6 +23,8 @@ out = gen.predict_k(obsv, noise, 12, data["batches"], precision="fp16x2")
 assert torch.isfinite(out).all()
 out2 = gen.predict_k(obsv, None, 12, data["batches"], precision="fp16x2", seed=3, k=2)
 assert torch.isfinite(out2).all() and not gen.fp16_overflowed()
+out3 = gen.predict_k(obsv, noise, 12, data["batches"], precision="bf16p")       # the bf16 build of the pair kernel
+assert torch.isfinite(out3).all() and (out3 - out).abs().max().item() < 5e-2
 from socialways_b200.trainer import SocialWaysTrainer
 small = synthetic_scenes([3, 8, 1, 5, 6, 2, 7, 4, 9, 3, 2, 6], seed=1)
 for tc in (True, False):
