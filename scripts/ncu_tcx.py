@@ -21,9 +21,11 @@ pooled = torch.randn(n, 64, device="cuda", generator=g) * 0.3
 noise = torch.rand(k, n, 32, device="cuda", generator=g)
 xl = torch.rand(n, 4, device="cuda", generator=g)
 out = torch.empty(k, n, T, 4, device="cuda")
-which = sys.argv[1] if len(sys.argv) > 1 else "tcx"       # "tcx" (one tile per SM) or "pair" (CTA pairs, two tiles per SM)
+which = sys.argv[1] if len(sys.argv) > 1 else "tcx"       # "tcx" (one tile per SM), "pair" (CTA pairs, two tiles per SM) or "bf16p" (pair kernel, bf16 operands)
 for _ in range(3):
-    if which == "pair":
+    if which == "bf16p":
+        ops.decode_pair(*pk["pair_bf16"], h, c, pooled, noise, xl, T, out=out, bf16=True)
+    elif which == "pair":
         ops.decode_pair(*pk["pair"], h, c, pooled, noise, xl, T, out=out)
     else:
         ops.decode_tcx(*pk["tcx"], h, c, pooled, noise, xl, T, out=out)
