@@ -22,7 +22,8 @@ noise = torch.rand(k, n, 32, device="cuda", generator=g)
 xl = torch.rand(n, 4, device="cuda", generator=g)
 gt = torch.rand(n, T, 2, device="cuda", generator=g)
 out = torch.empty(k, n, T, 4, device="cuda")
-for mode in ("decode only", "decode + best-of-K pass", "decode only, 3 ms idle between launches"):
+MODES = ("decode only", "decode + best-of-K pass", "decode only, 3 ms idle between launches")
+for mode in (MODES[:1] if len(sys.argv) > 1 and sys.argv[1] == "short" else MODES):
     ev = []
     for i in range(40):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -116,10 +116,8 @@ __device__ __forceinline__ void l1_epilogue(uint32_t t_acc, const float4* sc, un
         ptx::tcgen05_wait_ld();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float y0 = __uint_as_float(acc[4 * q]) + cc[q].x, y1 = __uint_as_float(acc[4 * q + 1]) + cc[q].y;
-            const float y2 = __uint_as_float(acc[4 * q + 2]) + cc[q].z, y3 = __uint_as_float(acc[4 * q + 3]) + cc[q].w;
-            psplit2(lrelu02(y0), lrelu02(y1), pc[2 * q], pc[8 + 2 * q]);
-            psplit2(lrelu02(y2), lrelu02(y3), pc[2 * q + 1], pc[8 + 2 * q + 1]);
+            l1_pair(acc[4 * q], acc[4 * q + 1], cc[q].x, cc[q].y, pc[2 * q], pc[8 + 2 * q]);
+            l1_pair(acc[4 * q + 2], acc[4 * q + 3], cc[q].z, cc[q].w, pc[2 * q + 1], pc[8 + 2 * q + 1]);
         }
 #if SW_PAIR_BF16
         tmem_st<8>(t_acc + kb * 16, pc);                  // hi only
@@ -576,7 +574,7 @@ PAIR_KERNEL(const __grid_constant__ CUtensorMap noise_map /* [n_rows][32] fp32, 
                         for (int w2 = 0; w2 < 2; ++w2)
 #pragma unroll
                             for (int q = 0; q < 4; ++q) g[w2][q] = __uint_as_float(a[(uu + w2) * 4 + q]);
-                        lstm_cell_pair_prescaled(g[0], g[1], c[sl][half * 8 + uu], c[sl][half * 8 + uu + 1], hv[uu], hv[uu + 1]);
+                        lstm_cell_pair_prescaled_x2(g[0], g[1], c[sl][half * 8 + uu], c[sl][half * 8 + uu + 1], hv[uu], hv[uu + 1]);
                     }
                     uint32_t hh[4], ll[4];
 #pragma unroll

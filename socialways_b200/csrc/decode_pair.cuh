@@ -6,7 +6,9 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#ifndef SW_RCP_NEWTON
 #define SW_RCP_NEWTON 1      // one of the three reciprocals per unit pair on the FMA pipe (sw_umma.cuh: rcp_newton)
+#endif
 #include "sw_common.cuh"
 #include "sw_umma.cuh"
 
@@ -51,6 +53,29 @@ __device__ __forceinline__ void psplit2(float a, float b, uint32_t& hi, uint32_t
     lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 #endif
+// lrelu(acc + c) of two columns and its hi|lo split on packed fp32x2 values (FADD2 / FMUL2 / FSUB2): max(y, 0.2 y) equals the
+// select form of lrelu02 bit for bit (signed zeros and NaN included); the split is psplit2's, same operation order
+__device__ __forceinline__ void l1_pair(uint32_t acc0, uint32_t acc1, float c0, float c1, uint32_t& hi, uint32_t& lo) {
+    const f32x2 y = add2(pk2(__uint_as_float(acc0), __uint_as_float(acc1)), pk2(c0, c1));
+    const f32x2 sc = mul2(y, pk2(0.2f, 0.2f));
+    float y0, y1, s0, s1;
+    unpk2(y, y0, y1);
+    unpk2(sc, s0, s1);
+    const float a = fmaxf(y0, s0), b = fmaxf(y1, s1);
+#if SW_PAIR_BF16
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    lo = 0u;
+#else
+    const __half2 h2 = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h2);
+    float r0, r1;
+    unpk2(sub2(pk2(a, b), pk2(back.x, back.y)), r0, r1);
+    const __half2 l2 = __floats2half2_rn(r0, r1);
+    hi = *reinterpret_cast<const uint32_t*>(&h2);
+    lo = *reinterpret_cast<const uint32_t*>(&l2);
+#endif
+}
 // single-thread forms (inside `if (elect_one())`)
 template <int NL, int KB>
 __device__ __forceinline__ void pmma3_ss1(uint32_t d, const __half* a_hi, const __half* a_lo, const __half* b_hi, const __half* b_lo) {

@@ -341,6 +341,45 @@ __device__ __forceinline__ void lstm_cell_pair_prescaled(const float (&ea)[4], c
     cb = cn[1];
 }
 
+// Packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 -- one issue slot and one register-file access for two IEEE fp32
+// operations on a 64-bit register pair) and the prescaled cell with the two units of the pair carried as the two halves of
+// fp32x2 values: the same formulas and operation order per unit (bit-identical to lstm_cell_pair_prescaled), ~46 instead of
+// ~74 instructions per pair.  Used by the pair decode kernel, which is bound by instruction issue in bursts and by the board's
+// power cap when it runs continuously (scripts/sustain_ab.sh: 7.40 -> 7.27 ms burst, 8.28 -> 8.18 ms sustained).  (Measured
+// 3 % SLOWER in an earlier version of that kernel -- before its step loop shrank -- and removed then; DESIGN.md.)
+struct f32x2 { unsigned long long v; };
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpk2(f32x2 a, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+__device__ __forceinline__ void lstm_cell_pair_prescaled_x2(const float (&ea)[4], const float (&eb)[4], float& ca, float& cb,
+                                                            float& ha, float& hb) {
+    const f32x2 one = pk2(1.0f, 1.0f), mone = pk2(-1.0f, -1.0f);
+    const f32x2 ai = add2(one, pk2(ex2_approx(fminf(ea[0], 30.0f)), ex2_approx(fminf(eb[0], 30.0f))));
+    const f32x2 af = add2(one, pk2(ex2_approx(fminf(ea[1], 30.0f)), ex2_approx(fminf(eb[1], 30.0f))));
+    const f32x2 ag = add2(one, pk2(ex2_approx(fminf(ea[2], 30.0f)), ex2_approx(fminf(eb[2], 30.0f))));
+    const f32x2 ao = add2(one, pk2(ex2_approx(fminf(ea[3], 30.0f)), ex2_approx(fminf(eb[3], 30.0f))));
+    const f32x2 p_ig = mul2(ai, ag), p_fo = mul2(af, ao);
+    const f32x2 pp = mul2(p_ig, p_fo);
+    float ppa, ppb;
+    unpk2(pp, ppa, ppb);
+    const f32x2 r = pk2((SW_RCP_NEWTON > 0) ? rcp_newton(ppa) : rcp_approx(ppa), (SW_RCP_NEWTON > 1) ? rcp_newton(ppb) : rcp_approx(ppb));
+    const f32x2 r_ig = mul2(r, p_fo), r_fo = mul2(r, p_ig);
+    const f32x2 sig_i = mul2(ag, r_ig), tanh_g = fma2(add2(ai, ai), r_ig, mone);
+    const f32x2 cn = fma2(mul2(ao, r_fo), pk2(ca, cb), mul2(sig_i, tanh_g));
+    const f32x2 so = mul2(af, r_fo);
+    float cna, cnb;
+    unpk2(cn, cna, cnb);
+    const float a0 = 1.0f + expneg_clamped(2.0f * cna), a1 = 1.0f + expneg_clamped(2.0f * cnb);
+    const float rr = rcp_approx(a0 * a1);
+    const f32x2 th = pk2(fmaf(2.0f * a1, rr, -1.0f), fmaf(2.0f * a0, rr, -1.0f));
+    unpk2(mul2(so, th), ha, hb);
+    ca = cna;
+    cb = cnb;
+}
+
 // bf16-mode cell: hardware tanh (MUFU.TANH, rel. error 2^-11, below the bf16 operand rounding), 5 MUFU per unit
 __device__ __forceinline__ float tanh_hw(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void lstm_cell_hw(const float (&g)[4], float& c, float& h) {
