@@ -518,8 +518,9 @@ PAIR_KERNEL(const __grid_constant__ CUtensorMap noise_map /* [n_rows][32] fp32, 
 #pragma unroll
                     for (int j = 0; j < 5; ++j) {
                         const float4 b = b2[j], wa = w34[2 * j], wb = w34[2 * j + 1];
-                        const float y0 = lrelu02(__uint_as_float(acc[4 * j]) + b.x), y1 = lrelu02(__uint_as_float(acc[4 * j + 1]) + b.y);
-                        const float y2 = lrelu02(__uint_as_float(acc[4 * j + 2]) + b.z), y3 = lrelu02(__uint_as_float(acc[4 * j + 3]) + b.w);
+                        float y0, y1, y2, y3;
+                        lrelu_add2(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), b.x, b.y, y0, y1);
+                        lrelu_add2(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3]), b.z, b.w, y2, y3);
                         v0 = fmaf(y0, wa.x, v0); v1 = fmaf(y0, wa.y, v1);
                         v0 = fmaf(y1, wa.z, v0); v1 = fmaf(y1, wa.w, v1);
                         v0 = fmaf(y2, wb.x, v0); v1 = fmaf(y2, wb.y, v1);

@@ -48,33 +48,28 @@ __device__ __forceinline__ void psplit2(float a, float b, uint32_t& hi, uint32_t
 __device__ __forceinline__ void psplit2(float a, float b, uint32_t& hi, uint32_t& lo) {
     const __half2 h2 = __floats2half2_rn(a, b);
     const float2 back = __half22float2(h2);
-    const __half2 l2 = __floats2half2_rn(a - back.x, b - back.y);
+    float r0, r1;
+    unpk2(sub2(pk2(a, b), pk2(back.x, back.y)), r0, r1);     // (a - back.x, b - back.y) in one FADD2
+    const __half2 l2 = __floats2half2_rn(r0, r1);
     hi = *reinterpret_cast<const uint32_t*>(&h2);
     lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 #endif
-// lrelu(acc + c) of two columns and its hi|lo split on packed fp32x2 values (FADD2 / FMUL2 / FSUB2): max(y, 0.2 y) equals the
-// select form of lrelu02 bit for bit (signed zeros and NaN included); the split is psplit2's, same operation order
-__device__ __forceinline__ void l1_pair(uint32_t acc0, uint32_t acc1, float c0, float c1, uint32_t& hi, uint32_t& lo) {
-    const f32x2 y = add2(pk2(__uint_as_float(acc0), __uint_as_float(acc1)), pk2(c0, c1));
+// lrelu(a + c) of two values on packed arithmetic: max(y, 0.2 y) equals the select form of lrelu02 bit for bit (signed zeros, NaN)
+__device__ __forceinline__ void lrelu_add2(float a0, float a1, float c0, float c1, float& o0, float& o1) {
+    const f32x2 y = add2(pk2(a0, a1), pk2(c0, c1));
     const f32x2 sc = mul2(y, pk2(0.2f, 0.2f));
     float y0, y1, s0, s1;
     unpk2(y, y0, y1);
     unpk2(sc, s0, s1);
-    const float a = fmaxf(y0, s0), b = fmaxf(y1, s1);
-#if SW_PAIR_BF16
-    const __nv_bfloat162 h2 = __floats2bfloat162_rn(a, b);
-    hi = *reinterpret_cast<const uint32_t*>(&h2);
-    lo = 0u;
-#else
-    const __half2 h2 = __floats2half2_rn(a, b);
-    const float2 back = __half22float2(h2);
-    float r0, r1;
-    unpk2(sub2(pk2(a, b), pk2(back.x, back.y)), r0, r1);
-    const __half2 l2 = __floats2half2_rn(r0, r1);
-    hi = *reinterpret_cast<const uint32_t*>(&h2);
-    lo = *reinterpret_cast<const uint32_t*>(&l2);
-#endif
+    o0 = fmaxf(y0, s0);
+    o1 = fmaxf(y1, s1);
+}
+// layer-1 epilogue of two columns: lrelu(acc + c1) and its hi|lo split, packed arithmetic throughout
+__device__ __forceinline__ void l1_pair(uint32_t acc0, uint32_t acc1, float c0, float c1, uint32_t& hi, uint32_t& lo) {
+    float a, b;
+    lrelu_add2(__uint_as_float(acc0), __uint_as_float(acc1), c0, c1, a, b);
+    psplit2(a, b, hi, lo);
 }
 // single-thread forms (inside `if (elect_one())`)
 template <int NL, int KB>
