@@ -370,14 +370,16 @@ __device__ __forceinline__ void lstm_cell_pair_prescaled_x2(const float (&ea)[4]
     const f32x2 sig_i = mul2(ag, r_ig), tanh_g = fma2(add2(ai, ai), r_ig, mone);
     const f32x2 cn = fma2(mul2(ao, r_fo), pk2(ca, cb), mul2(sig_i, tanh_g));
     const f32x2 so = mul2(af, r_fo);
-    float cna, cnb;
-    unpk2(cn, cna, cnb);
-    const float a0 = 1.0f + expneg_clamped(2.0f * cna), a1 = 1.0f + expneg_clamped(2.0f * cnb);
+    // tanh(c) = 2 / (1 + 2^(-2 log2e c)) - 1, the pair sharing one reciprocal; -2 log2e . c == -log2e . (2 c) bit for bit
+    // (doubling is exact), so the argument and the "1 +" are one packed operation each
+    float eca, ecb;
+    unpk2(mul2(cn, pk2(-2.8853900817779268f, -2.8853900817779268f)), eca, ecb);
+    float a0, a1;
+    unpk2(add2(one, pk2(ex2_approx(fminf(eca, 60.0f)), ex2_approx(fminf(ecb, 60.0f)))), a0, a1);
     const float rr = rcp_approx(a0 * a1);
     const f32x2 th = pk2(fmaf(2.0f * a1, rr, -1.0f), fmaf(2.0f * a0, rr, -1.0f));
     unpk2(mul2(so, th), ha, hb);
-    ca = cna;
-    cb = cnb;
+    unpk2(cn, ca, cb);
 }
 
 // bf16-mode cell: hardware tanh (MUFU.TANH, rel. error 2^-11, below the bf16 operand rounding), 5 MUFU per unit
