@@ -50,7 +50,7 @@ FLOPS_PER_TRAJ_EXECUTED = 12 * 2 * (64 * 160 + 160 * 80 + 80 * 2) + 11 * 2 * 68 
 # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of each decode kernel, divided by the
 # trajectories of that launch (655 360): profiles/r2_decode_pair.txt, r1_decode_tcx.txt, r1_decode_fp32_ffma.txt.
 # Algorithmic: 128 B noise in + 192 B (p, v) x 12 out = 320 B per trajectory.
-NCU_DRAM_BYTES_PER_TRAJ = {"fp16x2": (152.396544e6 + 120.195072e6) / 655360, "fp16x2s": (115.264768e6 + 92.413184e6) / 655360,
+NCU_DRAM_BYTES_PER_TRAJ = {"fp16x2": (158.654464e6 + 122.619136e6) / 655360, "fp16x2s": (115.264768e6 + 92.413184e6) / 655360,
                            "fp32": (114.652672e6 + 91.719424e6) / 655360, "bf16": None, "bf16p": None}
 
 
