@@ -131,7 +131,7 @@ lstm_seq_fwd_tcx_kernel(const __half* __restrict__ w16, const float* __restrict_
                     for (int w2 = 0; w2 < 2; ++w2)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) g[w2][q] = __uint_as_float(a[(u + w2) * 4 + q]);
-                    lstm_cell_pair_prescaled(g[0], g[1], c[part * 8 + u], c[part * 8 + u + 1], hv[u], hv[u + 1]);
+                    lstm_cell_pair_prescaled_x2(g[0], g[1], c[part * 8 + u], c[part * 8 + u + 1], hv[u], hv[u + 1]);   // packed fp32x2 form (bit-identical)
                 }
                 if (t == T - 1) {
                     if (valid) {
