@@ -122,6 +122,26 @@ def test_pool_tcx_pack_reconstructs_layer_two():
     assert (got - a1 @ w.t()).abs().max() < 5e-6
 
 
+def test_pair_pack_bf16_has_the_fp16_layout_with_bf16_bit_patterns():
+    """pack_decoder_pair(bf16=True) (operands of sw_decode_fwd_pair_bf16): same sizes and element order as the fp16 hi/lo image;
+    every 16-bit lane read as bf16 is the bf16 split of the same weight -- hi parts agree with the fp16 hi parts to bf16 rounding,
+    hi + lo reproduces the weight to 2^-16 relative."""
+    _, enc, dec = make_packs(5)
+    w16, f32 = packing.pack_decoder_pair(enc, dec)
+    b16, bf32 = packing.pack_decoder_pair(enc, dec, bf16=True)
+    assert b16.shape == w16.shape and b16.dtype == torch.float16 and torch.equal(f32, bf32)
+    as_bf = b16.view(torch.bfloat16).float()
+    as_f = w16.float()
+    # W1[h rows] of rank 0: hi block [0, 5120), lo block [5120, 10240)
+    hi_f, lo_f = as_f[0:5120], as_f[5120:10240]
+    hi_b, lo_b = as_bf[0:5120], as_bf[5120:10240]
+    w = hi_f + lo_f                                           # the fp32 weight to 2^-22
+    assert (hi_b - w).abs().max() <= (w.abs() * 2.0 ** -8).max()
+    assert ((hi_b + lo_b) - w).abs().max() <= (w.abs().max() * 2.0 ** -15)
+    # the ones of the x-feedback block live in the A operand (kernel side); its bias columns are bf16 splits of the same bias
+    assert torch.isfinite(as_bf).all()
+
+
 def test_pair_pack_halves_reassemble_the_one_tile_operands():
     """pack_decoder_pair cuts every B matrix [N][K] into the two N halves the two CTAs of a pair supply; the halves of both ranks,
     put back together, must be the matrices of pack_decoder_tcx (same split, same prescale), and the sizes must match the
