@@ -418,7 +418,7 @@ decode_fwd_tcx_kernel(const __grid_constant__ CUtensorMap noise_map /* [n_rows][
                     for (int w2 = 0; w2 < 2; ++w2)
 #pragma unroll
                         for (int q = 0; q < 4; ++q) g[w2][q] = __uint_as_float(a[(u + w2) * 4 + q]);
-                    lstm_cell_pair_prescaled(g[0], g[1], c[round * 8 + u], c[round * 8 + u + 1], hv[u], hv[u + 1]);
+                    lstm_cell_pair_prescaled_x2(g[0], g[1], c[round * 8 + u], c[round * 8 + u + 1], hv[u], hv[u + 1]);
                 }
                 uint32_t hi[4], lo[4];
 #pragma unroll
