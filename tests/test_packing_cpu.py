@@ -229,3 +229,22 @@ def test_newton_reciprocal_of_the_pair_kernel_cell():
         y = y + y * (1.0 - x * y)
     rel = ((y.double() * x.double()) - 1.0).abs().max().item()
     assert rel < 1.2e-7, rel
+
+
+def test_packed_epilogue_identities_hold_bit_for_bit_in_fp32():
+    """The packed fp32x2 epilogues of the decode kernels rely on two rewrites being exact in IEEE fp32 (sw_umma.cuh / decode_pair.cuh):
+    lrelu as max(y, 0.2 y) instead of the select form, and -2 log2e . c instead of -log2e . (2 c)."""
+    import numpy as np
+    rng = np.random.default_rng(0)
+    y = np.concatenate([rng.standard_normal(200000).astype(np.float32) * np.float32(10.0) ** rng.integers(-30, 30, 200000).astype(np.float32),
+                        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 3e38, -3e38], np.float32)])
+    with np.errstate(all="ignore"):
+        select = np.where(y > 0, y, np.float32(0.2) * y).astype(np.float32)
+        viamax = np.fmax(y, np.float32(0.2) * y).astype(np.float32)      # fmaxf: the non-NaN operand wins, NaN only if both are
+    same = (select.view(np.uint32) == viamax.view(np.uint32)) | (np.isnan(select) & np.isnan(viamax))
+    assert same.all()
+    c = y[np.isfinite(y) & (np.abs(y) < 1e37) & (np.abs(y) > 1e-30)]
+    a = np.float32(-1.4426950408889634) * (np.float32(2.0) * c)
+    b = np.float32(-2.8853900817779268) * c
+    assert np.float32(-2.8853900817779268) == np.float32(2.0) * np.float32(-1.4426950408889634)
+    assert (a.view(np.uint32) == b.view(np.uint32)).all()
